@@ -1,0 +1,452 @@
+"""ORACLE — CPU restatement of the tinyfusers denoising hot path (TEST INFRASTRUCTURE ONLY).
+
+This module restates, function by function, the arithmetic of the reference's SD1.x UNet step
+(`/root/reference`, Fatlonder/tinyfusers) in plain torch-CPU / numpy. It exists to *check* the CUDA
+path; nothing in the product (`tinyfusers_b200/`) imports it. Only `tests/`, `__graft_entry__.smoke()`
+and `bench.py`'s cpu_baseline / `--impl reference` legs may use it.
+
+Parity pinning:
+  * every function below is checked in tests/test_oracle_golden.py against golden vectors produced by
+    running the reference's OWN Python (imported from /root/reference with numpy standing in for CuPy;
+    script: oracle/make_golden.py, fixtures: tests/golden/*.npz);
+  * the three ops whose arithmetic lives in cuDNN / cuBLAS / a CUDA kernel (conv2d, layer_norm,
+    softmax) are additionally pinned the way the reference's own tests pin them — against
+    torch.nn.functional (tests/conv2d.py:27-33, tests/layer_norm.py:33-41, tests/sdpa.py:97-100) — and
+    the LayerNorm batch>1 stride quirk against a real cuDNN run (oracle/cudnn_probe.py, GPU box).
+
+All functions take/return torch CPU tensors in the REFERENCE layouts: NCHW images, (B, T, C) tokens,
+OIHW conv weights, (out, in) linear weights. `dtype` of the inputs decides the precision (fp32 like the
+reference, or fp64 for a tighter yardstick).
+
+`quirks=True` reproduces the reference literally (SURVEY.md §8 parity notes 1-2); `quirks=False` is
+canonical Stable Diffusion.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ------------------------------------------------------------------------------------------------
+# activations — reference: tinyfusers/storage/tensor.py:64-86
+# ------------------------------------------------------------------------------------------------
+
+
+def sigmoid(x):
+    # tensor.py:65-66   1 / (1 + exp(-x))
+    return 1 / (1 + torch.exp(-x))
+
+
+def silu(x):
+    # tensor.py:68-70   x * sigmoid(x)   (swish, tensor.py:84-86, is the same function)
+    return x * sigmoid(x)
+
+
+def quick_gelu(x):
+    # tensor.py:76-78
+    return x * sigmoid(x * 1.702)
+
+
+def gelu(x):
+    # tensor.py:80-82   tanh approximation
+    return 0.5 * x * (1 + torch.tanh(x * 0.7978845608 * (1 + 0.044715 * x * x)))
+
+
+# ------------------------------------------------------------------------------------------------
+# operators
+# ------------------------------------------------------------------------------------------------
+
+
+def linear(x, weight, bias=None):
+    # ff/linear.py:119-120   cp.dot(x, W.T) (+ bias)
+    y = x @ weight.t()
+    return y + bias if bias is not None else y
+
+
+def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1)):
+    # vision/conv2d.py:9-28 (cuDNN conv_fprop == cross-correlation; NHWC result re-read as NCHW at :27)
+    # vision/conv2d.py:55-59 (bias broadcast add). The reference's own test pins this op to
+    # torch.nn.functional.conv2d (tests/conv2d.py:27-33), which is what is used here.
+    return F.conv2d(x, weight, bias, stride=tuple(stride), padding=tuple(padding), dilation=tuple(dilation))
+
+
+def group_norm(x, num_groups, eps):
+    # ff/group_norm.py:3-11 — literal two-pass, biased variance, no affine
+    N, C, H, W = x.shape
+    xg = x.reshape(N, num_groups, -1)
+    mean = xg.mean(dim=-1, keepdim=True)
+    yn = xg - mean
+    yvar = torch.sqrt((yn * yn).mean(dim=-1, keepdim=True) + eps)
+    return (yn * (1 / yvar)).reshape(N, C, H, W)
+
+
+def group_norm_affine(x, num_groups, weight, bias, eps=1e-5):
+    # ff/group_norm.py:18-21
+    o = group_norm(x, num_groups, eps)
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    return o * weight.reshape(shape) + bias.reshape(shape)
+
+
+def layer_norm(x, weight, bias, eps=1e-5, quirks=True):
+    """ff/layer_norm.py:34-49 -> :8-32.
+
+    The reference hands cuDNN a contiguous (1,B,T,C) buffer but declares the strides
+    [B*T*C, 1, B*C, B] (layer_norm.py:10). cuDNN normalises over the last logical dim (the only dim on
+    which scale/bias have extent) and writes Y with X's strides, so logical element (b,t,c) lives at
+    memory offset  b + t*B*C + c*B.  In memory terms: view the buffer as (T, C, B) and normalise over
+    axis 1. For B == 1 this is the canonical LayerNorm over C; for B > 1 it is not (parity note 1).
+    """
+    B, T, C = x.shape
+    if not quirks or B == 1:
+        mean = x.mean(dim=-1, keepdim=True)
+        var = ((x - mean) ** 2).mean(dim=-1, keepdim=True)
+        return (x - mean) / torch.sqrt(var + eps) * weight + bias
+    mem = x.contiguous().reshape(T, C, B)
+    mean = mem.mean(dim=1, keepdim=True)
+    var = ((mem - mean) ** 2).mean(dim=1, keepdim=True)
+    y = (mem - mean) / torch.sqrt(var + eps) * weight.reshape(1, C, 1) + bias.reshape(1, C, 1)
+    return y.reshape(B, T, C)
+
+
+def softmax_rows(x):
+    # native/cuda/softmax.cu:24-112 — per row: max, exp(x - max), sum, divide
+    m = x.max(dim=-1, keepdim=True).values
+    e = torch.exp(x - m)
+    return e / e.sum(dim=-1, keepdim=True)
+
+
+def scaled_dot_product_attention(q, k, v, attn_mask=None):
+    # attention/sdpa.py:53-77 — scale * (q @ k^T) [+ mask] -> row softmax -> @ v
+    HS = q.shape[-1]
+    scale = torch.tensor(1.0 / math.sqrt(HS), dtype=torch.float32).to(q.dtype)  # cp.single, sdpa.py:62
+    preatt = scale * (q @ k.transpose(-1, -2))
+    if attn_mask is not None:
+        if attn_mask.dtype == torch.bool:
+            preatt = preatt + torch.where(attn_mask == 0, -float("inf"), 0.0).to(q.dtype)  # sdpa.py:68
+        else:
+            preatt = preatt + attn_mask
+    att = softmax_rows(preatt)
+    return att @ v
+
+
+def timestep_embedding(timesteps, dim, max_period=10000):
+    # vision/unet.py:92-97. `timesteps` is an int64 array of ONE element (example/sd1.py:73); int64 *
+    # float promotes to float64 in CuPy, so the angles are formed in fp64 and only the result is fp32.
+    half = dim // 2
+    t = np.asarray(timesteps, dtype=np.float64).reshape(-1)
+    freqs = np.exp(-np.log(float(max_period)) * np.arange(half, dtype=np.float32).astype(np.float64) / half)
+    args = t * freqs
+    out = np.concatenate((np.cos(args), np.sin(args))).reshape(1, -1).astype(np.float32)
+    return torch.from_numpy(out)
+
+
+def get_alphas_cumprod(beta_start=0.00085, beta_end=0.0120, n_training_steps=1000):
+    # variants/sd.py:61-65 (fp32 throughout)
+    betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, n_training_steps, dtype=np.float32) ** 2
+    alphas = (1.0 - betas).astype(np.float32)
+    return torch.from_numpy(np.cumprod(alphas, axis=0).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# blocks. `sd` is a flat dict  "<prefix>.<attr path>.weight|bias" -> tensor, the reference's
+# checkpoint naming (storage/state.py:4-23).
+# ------------------------------------------------------------------------------------------------
+
+
+def _w(sd, name):
+    return sd[name]
+
+
+def _b(sd, name):
+    return sd.get(name)
+
+
+def geglu(sd, p, x):
+    # ff/nn.py:5-12: proj -> split(2, axis=-1): first half = value, second half = gate
+    y = linear(x, _w(sd, p + ".proj.weight"), _b(sd, p + ".proj.bias"))
+    a, gate = y.chunk(2, dim=-1)
+    return a * gelu(gate)
+
+
+def feed_forward(sd, p, x):
+    # ff/nn.py:14-23: net = [GEGLU, identity, Linear]
+    h = geglu(sd, p + ".net.0", x)
+    return linear(h, _w(sd, p + ".net.2.weight"), _b(sd, p + ".net.2.bias"))
+
+
+def cross_attention(sd, p, x, context, n_heads, d_head, quirks=True):
+    # attention/attention.py:26-41
+    context = x if context is None else context
+    q = linear(x, _w(sd, p + ".to_q.weight"))
+    k = linear(context, _w(sd, p + ".to_k.weight"))
+    v = linear(context, _w(sd, p + ".to_v.weight"))
+    B = x.shape[0]
+    q, k, v = [y.reshape(B, -1, n_heads, d_head).permute(0, 2, 1, 3) for y in (q, k, v)]
+    o = scaled_dot_product_attention(q, k, v)  # (B, NH, T, HS)
+    if quirks:
+        # attention.py:39 reshapes (B,NH,T,HS) straight to (B,T,NH*HS) WITHOUT moving heads back
+        o = o.contiguous().reshape(B, -1, n_heads * d_head)
+    else:
+        o = o.permute(0, 2, 1, 3).reshape(B, -1, n_heads * d_head)
+    return linear(o, _w(sd, p + ".to_out.0.weight"), _b(sd, p + ".to_out.0.bias"))
+
+
+def basic_transformer_block(sd, p, x, context, n_heads, d_head, quirks=True):
+    # attention/attention.py:43-56
+    ln = lambda name, t: layer_norm(t, _w(sd, f"{p}.{name}.weight"), _b(sd, f"{p}.{name}.bias"), 1e-5, quirks)
+    x = cross_attention(sd, p + ".attn1", ln("norm1", x), None, n_heads, d_head, quirks) + x
+    x = cross_attention(sd, p + ".attn2", ln("norm2", x), context, n_heads, d_head, quirks) + x
+    x = feed_forward(sd, p + ".ff", ln("norm3", x)) + x
+    return x
+
+
+def spatial_transformer(sd, p, x, context, n_heads, d_head, quirks=True):
+    # attention/attention.py:58-76
+    b, c, h, w = x.shape
+    x_in = x
+    x = group_norm_affine(x, 32, _w(sd, p + ".norm.weight"), _b(sd, p + ".norm.bias"), 1e-5)
+    x = conv2d(x, _w(sd, p + ".proj_in.weight"), _b(sd, p + ".proj_in.bias"))
+    x = x.reshape(b, c, h * w).permute(0, 2, 1)
+    x = basic_transformer_block(sd, p + ".transformer_blocks.0", x, context, n_heads, d_head, quirks)
+    x = x.permute(0, 2, 1).reshape(b, c, h, w)
+    return conv2d(x, _w(sd, p + ".proj_out.weight"), _b(sd, p + ".proj_out.bias")) + x_in
+
+
+def res_block(sd, p, x, emb):
+    # vision/resnet.py:6-31
+    h = group_norm_affine(x, 32, _w(sd, p + ".in_layers.0.weight"), _b(sd, p + ".in_layers.0.bias"))
+    h = conv2d(silu(h), _w(sd, p + ".in_layers.2.weight"), _b(sd, p + ".in_layers.2.bias"), padding=(1, 1))
+    emb_out = linear(silu(emb), _w(sd, p + ".emb_layers.1.weight"), _b(sd, p + ".emb_layers.1.bias"))
+    h = h + emb_out.reshape(*emb_out.shape, 1, 1)
+    h = group_norm_affine(h, 32, _w(sd, p + ".out_layers.0.weight"), _b(sd, p + ".out_layers.0.bias"))
+    h = conv2d(silu(h), _w(sd, p + ".out_layers.3.weight"), _b(sd, p + ".out_layers.3.bias"), padding=(1, 1))
+    if (p + ".skip_connection.weight") in sd:
+        x = conv2d(x, _w(sd, p + ".skip_connection.weight"), _b(sd, p + ".skip_connection.bias"))
+    return x + h
+
+
+def upsample(sd, p, x):
+    # vision/unet.py:78-84 — nearest x2 then 3x3 conv
+    bs, c, py, px = x.shape
+    x = x.reshape(bs, c, py, 1, px, 1).expand(bs, c, py, 2, px, 2).reshape(bs, c, py * 2, px * 2)
+    return conv2d(x, _w(sd, p + ".conv.weight"), _b(sd, p + ".conv.bias"), padding=(1, 1))
+
+
+def downsample(sd, p, x):
+    # vision/unet.py:86-90 — 3x3 stride-2 pad-1 conv
+    return conv2d(x, _w(sd, p + ".op.weight"), _b(sd, p + ".op.bias"), stride=(2, 2), padding=(1, 1))
+
+
+# UNet structure, vision/unet.py:11-49. Entries: ("conv", cin, cout) | ("res", cin, cout) |
+# ("st", channels, heads, d_head) | ("down", c) | ("up", c)
+UNET_INPUT_BLOCKS = [
+    [("conv", 4, 320)],
+    [("res", 320, 320), ("st", 320, 8, 40)],
+    [("res", 320, 320), ("st", 320, 8, 40)],
+    [("down", 320)],
+    [("res", 320, 640), ("st", 640, 8, 80)],
+    [("res", 640, 640), ("st", 640, 8, 80)],
+    [("down", 640)],
+    [("res", 640, 1280), ("st", 1280, 8, 160)],
+    [("res", 1280, 1280), ("st", 1280, 8, 160)],
+    [("down", 1280)],
+    [("res", 1280, 1280)],
+    [("res", 1280, 1280)],
+]
+UNET_MIDDLE_BLOCK = [("res", 1280, 1280), ("st", 1280, 8, 160), ("res", 1280, 1280)]
+UNET_OUTPUT_BLOCKS = [
+    [("res", 2560, 1280)],
+    [("res", 2560, 1280)],
+    [("res", 2560, 1280), ("up", 1280)],
+    [("res", 2560, 1280), ("st", 1280, 8, 160)],
+    [("res", 2560, 1280), ("st", 1280, 8, 160)],
+    [("res", 1920, 1280), ("st", 1280, 8, 160), ("up", 1280)],
+    [("res", 1920, 640), ("st", 640, 8, 80)],
+    [("res", 1280, 640), ("st", 640, 8, 80)],
+    [("res", 960, 640), ("st", 640, 8, 80), ("up", 640)],
+    [("res", 960, 320), ("st", 320, 8, 40)],
+    [("res", 640, 320), ("st", 320, 8, 40)],
+    [("res", 640, 320), ("st", 320, 8, 40)],
+]
+CONTEXT_DIM = 768
+EMB_CHANNELS = 1280
+
+
+def _run_layer(sd, p, layer, x, emb, context, quirks):
+    kind = layer[0]
+    if kind == "conv":
+        return conv2d(x, _w(sd, p + ".weight"), _b(sd, p + ".bias"), padding=(1, 1))
+    if kind == "res":
+        return res_block(sd, p, x, emb)
+    if kind == "st":
+        return spatial_transformer(sd, p, x, context, layer[2], layer[3], quirks)
+    if kind == "down":
+        return downsample(sd, p, x)
+    if kind == "up":
+        return upsample(sd, p, x)
+    raise ValueError(kind)
+
+
+def unet_forward(sd, x, timesteps, context, prefix="model.diffusion_model", quirks=True):
+    # vision/unet.py:51-76
+    P = prefix
+    t_emb = timestep_embedding(timesteps, 320).to(x.dtype)
+    emb = linear(t_emb, _w(sd, P + ".time_embed.0.weight"), _b(sd, P + ".time_embed.0.bias"))
+    emb = linear(silu(emb), _w(sd, P + ".time_embed.2.weight"), _b(sd, P + ".time_embed.2.bias"))
+    saved = []
+    for i, block in enumerate(UNET_INPUT_BLOCKS):
+        for j, layer in enumerate(block):
+            x = _run_layer(sd, f"{P}.input_blocks.{i}.{j}", layer, x, emb, context, quirks)
+        saved.append(x)
+    for j, layer in enumerate(UNET_MIDDLE_BLOCK):
+        x = _run_layer(sd, f"{P}.middle_block.{j}", layer, x, emb, context, quirks)
+    for i, block in enumerate(UNET_OUTPUT_BLOCKS):
+        x = torch.cat((x, saved.pop()), dim=1)
+        for j, layer in enumerate(block):
+            x = _run_layer(sd, f"{P}.output_blocks.{i}.{j}", layer, x, emb, context, quirks)
+    x = group_norm_affine(x, 32, _w(sd, P + ".out.0.weight"), _b(sd, P + ".out.0.bias"))
+    return conv2d(silu(x), _w(sd, P + ".out.2.weight"), _b(sd, P + ".out.2.bias"), padding=(1, 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler step — reference: tinyfusers/variants/sd.py:14-59
+# ------------------------------------------------------------------------------------------------
+
+
+def get_x_prev_and_pred_x0(x, e_t, a_t, a_prev):
+    # sd.py:14-25 (DDIM, eta = 0 => sigma_t = 0)
+    sigma_t = 0
+    sqrt_one_minus_at = torch.sqrt(1 - a_t)
+    pred_x0 = (x - sqrt_one_minus_at * e_t) / torch.sqrt(a_t)
+    dir_xt = torch.sqrt(1.0 - a_prev - sigma_t ** 2) * e_t
+    x_prev = torch.sqrt(a_prev) * pred_x0 + dir_xt
+    return x_prev, pred_x0
+
+
+def get_model_output(sd, unconditional_context, context, latent, timestep, guidance, quirks=True):
+    # sd.py:27-46: batch = [uncond ; cond], e_t = u + g (c - u)
+    n = latent.shape[0]
+    lat2 = torch.cat((latent, latent), dim=0) if n > 1 else latent.expand(2, *latent.shape[1:])
+    ctx2 = torch.cat((unconditional_context, context), dim=0)
+    out = unet_forward(sd, lat2.contiguous(), timestep, ctx2, quirks=quirks)
+    u, c = out[0:n], out[n:2 * n]
+    return u + guidance * (c - u)
+
+
+def sampler_step(sd, unconditional_context, context, latent, timestep, a_t, a_prev, guidance, quirks=True):
+    # sd.py:56-59
+    e_t = get_model_output(sd, unconditional_context, context, latent, timestep, guidance, quirks)
+    x_prev, _ = get_x_prev_and_pred_x0(latent, e_t, a_t, a_prev)
+    return x_prev
+
+
+def sampler_schedule(steps, alphas_cumprod=None):
+    # example/sd1.py:54-57
+    timesteps = list(range(1, 1000, 1000 // steps))
+    ac = get_alphas_cumprod() if alphas_cumprod is None else alphas_cumprod
+    alphas = ac[timesteps]
+    alphas_prev = torch.cat((torch.tensor([1.0]), alphas[:-1])).float()
+    return timesteps, alphas, alphas_prev
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic weights: deterministic per key, identical for oracle and kernels.
+# ------------------------------------------------------------------------------------------------
+
+
+def _key_seed(key, seed):
+    h = 2166136261
+    for ch in key.encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return (seed * 1000003 + h) & 0x7FFFFFFF
+
+
+def _randn(key, seed, shape, std):
+    rng = np.random.Generator(np.random.Philox(_key_seed(key, seed)))
+    return torch.from_numpy((rng.standard_normal(size=shape, dtype=np.float32) * np.float32(std)))
+
+
+def _add_conv(sd, p, cin, cout, k, seed):
+    fan_in = cin * k * k
+    sd[p + ".weight"] = _randn(p + ".weight", seed, (cout, cin, k, k), 1.0 / math.sqrt(fan_in))
+    sd[p + ".bias"] = _randn(p + ".bias", seed, (cout,), 0.02)
+
+
+def _add_linear(sd, p, cin, cout, seed, bias=True):
+    sd[p + ".weight"] = _randn(p + ".weight", seed, (cout, cin), 1.0 / math.sqrt(cin))
+    if bias:
+        sd[p + ".bias"] = _randn(p + ".bias", seed, (cout,), 0.02)
+
+
+def _add_norm(sd, p, c, seed):
+    sd[p + ".weight"] = 1.0 + _randn(p + ".weight", seed, (c,), 0.02)
+    sd[p + ".bias"] = _randn(p + ".bias", seed, (c,), 0.02)
+
+
+def add_res_block(sd, p, cin, cout, seed=1234, emb=EMB_CHANNELS):
+    _add_norm(sd, p + ".in_layers.0", cin, seed)
+    _add_conv(sd, p + ".in_layers.2", cin, cout, 3, seed)
+    _add_linear(sd, p + ".emb_layers.1", emb, cout, seed)
+    _add_norm(sd, p + ".out_layers.0", cout, seed)
+    _add_conv(sd, p + ".out_layers.3", cout, cout, 3, seed)
+    if cin != cout:
+        _add_conv(sd, p + ".skip_connection", cin, cout, 1, seed)
+
+
+def add_spatial_transformer(sd, p, c, context_dim=CONTEXT_DIM, seed=1234):
+    _add_norm(sd, p + ".norm", c, seed)
+    _add_conv(sd, p + ".proj_in", c, c, 1, seed)
+    t = p + ".transformer_blocks.0"
+    for attn, cd in (("attn1", c), ("attn2", context_dim)):
+        _add_linear(sd, f"{t}.{attn}.to_q", c, c, seed, bias=False)
+        _add_linear(sd, f"{t}.{attn}.to_k", cd, c, seed, bias=False)
+        _add_linear(sd, f"{t}.{attn}.to_v", cd, c, seed, bias=False)
+        _add_linear(sd, f"{t}.{attn}.to_out.0", c, c, seed)
+    _add_linear(sd, t + ".ff.net.0.proj", c, 8 * c, seed)
+    _add_linear(sd, t + ".ff.net.2", 4 * c, c, seed)
+    for n in ("norm1", "norm2", "norm3"):
+        _add_norm(sd, f"{t}.{n}", c, seed)
+    _add_conv(sd, p + ".proj_out", c, c, 1, seed)
+
+
+def _add_layer(sd, p, layer, seed):
+    kind = layer[0]
+    if kind == "conv":
+        _add_conv(sd, p, layer[1], layer[2], 3, seed)
+    elif kind == "res":
+        add_res_block(sd, p, layer[1], layer[2], seed)
+    elif kind == "st":
+        add_spatial_transformer(sd, p, layer[1], CONTEXT_DIM, seed)
+    elif kind == "down":
+        _add_conv(sd, p + ".op", layer[1], layer[1], 3, seed)
+    elif kind == "up":
+        _add_conv(sd, p + ".conv", layer[1], layer[1], 3, seed)
+
+
+def make_unet_state_dict(seed=1234, prefix="model.diffusion_model"):
+    """Seeded synthetic UNet weights with the reference's checkpoint key names (fp32, ~3.4 GB)."""
+    sd = {}
+    P = prefix
+    _add_linear(sd, P + ".time_embed.0", 320, 1280, seed)
+    _add_linear(sd, P + ".time_embed.2", 1280, 1280, seed)
+    for i, block in enumerate(UNET_INPUT_BLOCKS):
+        for j, layer in enumerate(block):
+            _add_layer(sd, f"{P}.input_blocks.{i}.{j}", layer, seed)
+    for j, layer in enumerate(UNET_MIDDLE_BLOCK):
+        _add_layer(sd, f"{P}.middle_block.{j}", layer, seed)
+    for i, block in enumerate(UNET_OUTPUT_BLOCKS):
+        for j, layer in enumerate(block):
+            _add_layer(sd, f"{P}.output_blocks.{i}.{j}", layer, seed)
+    _add_norm(sd, P + ".out.0", 320, seed)
+    _add_conv(sd, P + ".out.2", 320, 4, 3, seed)
+    return sd
+
+
+def make_inputs(batch=1, latent_hw=64, seed=42, ctx_seed=43):
+    """SURVEY.md §8d synthetic inputs: latent ~ N(0,1) seed 42, prompt embeddings ~ N(0,1) seed 43."""
+    g = np.random.Generator(np.random.Philox(seed))
+    latent = torch.from_numpy(g.standard_normal((batch, 4, latent_hw, latent_hw), dtype=np.float32))
+    g2 = np.random.Generator(np.random.Philox(ctx_seed))
+    ctx = torch.from_numpy(g2.standard_normal((batch, 77, CONTEXT_DIM), dtype=np.float32))
+    unc = torch.from_numpy(g2.standard_normal((batch, 77, CONTEXT_DIM), dtype=np.float32))
+    return latent, unc, ctx

@@ -1,0 +1,107 @@
+// tinyfusers_b200 — process-lifetime state of the C-ABI library: error string, device probe,
+// TMA descriptor encoding through the driver entry point, launch bookkeeping.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "tf_common.cuh"
+#include "tinyfusers_b200.h"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static int g_sms = 0;
+
+void tf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* tf_last_error(void) { return g_err; }
+
+extern "C" int tf_version(void) { return 100; }
+
+int tf_launch_count_add(int n) {
+  g_launches += n;
+  return 0;
+}
+extern "C" long long tf_launch_count(void) { return g_launches.load(); }
+extern "C" void tf_launch_count_reset(void) { g_launches = 0; }
+
+int tf_num_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+extern "C" int tf_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    tf_set_error("tf_init: no CUDA device visible (%s); this library has no CPU fallback",
+                 cudaGetErrorString(e));
+    return TF_ERR_DEVICE;
+  }
+  TF_CHECK_ARG(device >= 0 && device < count, "tf_init: device %d out of range (%d visible)", device, count);
+  TF_CUDA(cudaSetDevice(device));
+  int major = 0, minor = 0;
+  TF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  TF_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10) {
+    tf_set_error("tf_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                 major, minor);
+    return TF_ERR_DEVICE;
+  }
+  g_sms = 0;
+  tf_num_sms();
+  return TF_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int tf_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base,
+                   const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                   const uint32_t* elem_strides, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    tf_set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old or no GPU)");
+    return TF_ERR_DEVICE;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tf_set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]",
+                 (int)r, rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+                 (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0), b[0],
+                 rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0);
+    return TF_ERR_ARG;
+  }
+  return TF_OK;
+}

@@ -1,0 +1,74 @@
+"""ctypes binding of libtinyfusers_b200.so — the B200 replacement for the reference's
+`tinyfusers/native/{cuda,cublas,nvrtc}/ops.py` singletons (reference: native/cublas/ops.py:3-70).
+
+Same style as the reference: one class owning `self.dll = ctypes.CDLL(...)`, explicit
+`restype` / `argtypes`, methods that return the raw integer status, a module-level singleton
+(`b200`) and status constants on it. Callers turn a non-zero status into
+`RuntimeError("<fn> failed with status <n>")` exactly like `ff/linear.py:100-103`; `check()` does that
+and appends the library's error string.
+
+There is deliberately no fallback: if the shared library is missing, importing this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtinyfusers_b200.so")
+
+c_int, c_size_t, c_void_p, c_float, c_longlong = (ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
+                                                  ctypes.c_float, ctypes.c_longlong)
+_P = c_void_p
+
+# name -> (restype, argtypes). Keep in sync with include/tinyfusers_b200.h (tests/test_abi.py checks it).
+_SIGNATURES = {
+    "tf_version": (c_int, []),
+    "tf_init": (c_int, [c_int]),
+    "tf_last_error": (ctypes.c_char_p, []),
+    "tf_launch_count": (c_longlong, []),
+    "tf_launch_count_reset": (None, []),
+    "tf_gemm_set_tuning": (c_int, [c_int, c_int]),
+    "tf_gemm_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
+                            _P, c_size_t, _P]),
+    "tf_conv2d_nhwc_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
+                                   _P, _P, c_int, c_int, _P, c_size_t, _P]),
+}
+
+
+class B200:
+    def __init__(self, path=_LIB_PATH):
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} not found: build it with `python -m tinyfusers_b200.csrc.build` "
+                "(tinyfusers_b200 has no CPU / eager fallback)")
+        self.path = path
+        self.dll = ctypes.CDLL(path)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(self.dll, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+            setattr(self, name, fn)
+        self._initialised = False
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def last_error(self):
+        msg = self.dll.tf_last_error()
+        return msg.decode() if msg else ""
+
+    def check(self, status, name):
+        if status != 0:
+            raise RuntimeError(f"{name} failed with status {status}: {self.last_error()}")
+
+    def init(self, device=0):
+        if not self._initialised:
+            self.check(self.tf_init(int(device)), "tf_init")
+            self._initialised = True
+
+
+b200 = B200()
+b200.TF_OK = 0
+b200.TF_ERR_ARG = -1
+b200.TF_ERR_UNSUPPORTED = -2
+b200.TF_ERR_DEVICE = -3
+b200.TF_EPI_NONE = 0
+b200.TF_EPI_OUT_F32 = 1
+b200.TF_EPI_GEGLU = 2
