@@ -66,6 +66,76 @@ int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel
 /* test / tuning hook: force the N tile and split-K factor of the next GEMM/conv calls (0 = auto) */
 int tf_gemm_set_tuning(int force_bn, int force_splits);
 
+/* ---- normalisation -------------------------------------------------------------------------------- */
+/* GroupNorm (+ optional SiLU), NHWC fp16 -> NHWC fp16, statistics fp32, biased variance.
+ * Replaces: group_norm / GroupNorm.__call__ (>= 8 CuPy launches)   tinyfusers/ff/group_norm.py:3-21
+ *           + Tensor.silu that always follows it in the UNet         tinyfusers/storage/tensor.py:68-70,
+ *                                                                    vision/resnet.py:8-10,17-19, vision/unet.py:45-47
+ * The input may be given as TWO channel slices (x: Cx channels, x2: Cx2 channels, each with its own pixel
+ * stride) that are normalised as their channel concatenation — this is how
+ * `cp.concatenate((x, saved_inputs.pop()), axis=1)` (vision/unet.py:72) is consumed without a copy.
+ * x2 may be NULL. gamma/beta: fp32 (C) or NULL. stats_ws: fp32 scratch, 2*groups*NI floats. */
+int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void* x2, int x2_pixel_stride,
+                          int Cx2, void* out, int out_pixel_stride, int NI, int HW, int groups,
+                          const float* gamma, const float* beta, float eps, int apply_silu, float* stats_ws,
+                          void* stream);
+
+/* LayerNorm over the last dim of a (rows, C) fp16 matrix; gamma/beta fp32.
+ * Replaces: layer_norm / LayerNorm.__call__ (cuDNN layernorm graph, rebuilt per call)
+ *           tinyfusers/ff/layer_norm.py:8-49.
+ * interleave == 1: canonical. interleave == B > 1: the reference's stride declaration at batch B
+ * (layer_norm.py:10): the buffer is viewed as (rows/B, C, B) and normalised over C. */
+int tf_layernorm_f16(const void* x, void* out, int rows, int C, const float* gamma, const float* beta, float eps,
+                     int interleave, void* stream);
+
+/* ---- attention ------------------------------------------------------------------------------------ */
+/* softmax(scale * Q K^T) V per (batch, head), flash-style on tcgen05/TMEM; scores never reach HBM.
+ * Replaces: scaled_dot_product_attention (2 cuBLAS batched SGEMMs + softmax_kernel)
+ *           tinyfusers/attention/sdpa.py:53-77, tinyfusers/native/cuda/softmax.cu:24-112.
+ * q: (B*Tq, ldq), k: (B*Tk_pad, ldk): head h at columns [h*dp, (h+1)*dp), dp = d padded to 16 with zeros;
+ * vt: (NH*dp, ldvt >= B*Tk_pad) = V transposed; keys [Tk, Tk_pad) of each batch are padding (ignored).
+ * out element (b,h,t,j<d) at b*out_stride_b + h*out_stride_h + t*out_stride_t + j — the strides select
+ * the reference's head-major reshape (attention/attention.py:39) or the canonical head merge. */
+int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
+                     long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
+                     int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream);
+int tf_attention_set_tuning(int force_bn);
+
+/* ---- small ops of the step --------------------------------------------------------------------------- */
+/* [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / (dim/2)); t = timesteps_dev[*index_dev]
+ * (index_dev may be NULL -> element 0). Angles in fp64 like the reference. out: fp32 (dim).
+ * Replaces: timestep_embedding  tinyfusers/vision/unet.py:92-97. */
+int tf_timestep_embedding_f32(const float* timesteps_dev, const int* index_dev, int dim, float max_period,
+                              float* out, void* stream);
+/* out[n] = sum_k act(x[k]) W[n,k] + bias[n] + bias2[n]; x fp32 (K), W fp16 (N,K), act = SiLU if silu_input.
+ * Replaces: Linear at M = 1 — time_embed (vision/unet.py:11,54) and ResBlock.emb_layers
+ *           (vision/resnet.py:13-16,27-28). */
+int tf_gemv_f16w(const float* x, const void* W, const float* bias, const float* bias2, float* out, int N, int K,
+                 int silu_input, void* stream);
+/* 3x3 pad-1 conv, Cin = 4, fp32 NCHW in, fp32 OIHW weights, fp16 NHWC out.
+ * Replaces: UNetModel.input_blocks[0] Conv2d(4,320)  tinyfusers/vision/unet.py:13. */
+int tf_conv3x3_smallcin_f32nchw(const float* x, const float* w, const float* bias, void* out, int NI, int Cin,
+                                int H, int W, int Cout, int out_pixel_stride, void* stream);
+/* nearest x2. Replaces: Upsample.__call__ broadcast/reshape  tinyfusers/vision/unet.py:81-83. */
+int tf_upsample_nearest2x_nhwc_f16(const void* x, int x_pixel_stride, void* out, int out_pixel_stride, int NI,
+                                   int H, int W, int C, void* stream);
+/* layout edges of the drop-in API (the reference is NCHW fp32 everywhere, vision/conv2d.py:27) */
+int tf_nchw_to_nhwc_f16(const void* x, int x_is_f32, void* out, int NI, int C, int HW, int out_pixel_stride,
+                        void* stream);
+int tf_nhwc_to_nchw(const void* x, int x_pixel_stride, void* out, int out_is_f32, int NI, int C, int HW,
+                    void* stream);
+/* prompt context (B,T,C) fp32 -> (B,Tpad,C) fp16, zero rows appended (77 -> 80 tokens) */
+int tf_pad_tokens_f32_to_f16(const float* x, void* out, int B, int T, int Tpad, int C, void* stream);
+/* e_t = u + g (c - u); x_prev = sqrt(a_prev) (x - sqrt(1-a_t) e_t)/sqrt(a_t) + sqrt(1-a_prev) e_t.
+ * eps: fp32 NHWC (2B images: [uncond ; cond]), latent: fp32 NCHW; a_t = alphas_dev[*index_dev] etc.
+ * e_t_out may be NULL. Replaces: StableDiffusion.get_model_output :44-45 and get_x_prev_and_pred_x0
+ * (tinyfusers/variants/sd.py:14-25,44-45) — ~12 CuPy launches fused into one. */
+int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride, const float* latent, float* latent_out,
+                         float* e_t_out, const float* alphas_dev, const float* alphas_prev_dev,
+                         const int* index_dev, float guidance, int B, int C, int HW, void* stream);
+/* *p_dev += delta (device-resident sampler step counter, so a captured graph can be replayed) */
+int tf_add_int(int* p_dev, int delta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,373 @@
+// tinyfusers_b200 — fused flash-style attention on tcgen05 / TMEM for sm_100a.
+//
+// Replaces the reference's scaled_dot_product_attention (tinyfusers/attention/sdpa.py:53-77):
+//   cuBLAS batched SGEMM (scores materialised in HBM, 1.07 GB at 4096 tokens) -> softmax_kernel
+//   (native/cuda/softmax.cu:24-112, three global passes per row) -> cuBLAS batched SGEMM.
+// Here scores never leave the SM: S = Q·K^T goes to TMEM, four softmax warps (one thread per query
+// row — the 32x32b TMEM load hands each thread its own row, so row max / sum need no shuffles) run the
+// online softmax and write P (fp16) to shared memory in the 128B-swizzled K-major layout, and
+// O += P·V accumulates in TMEM. S is double-buffered so QK^T of block j+1 overlaps softmax of block j.
+//
+// Operand layouts (produced by the projection GEMMs, see tinyfusers_b200/attention/attention.py):
+//   Q  : (B*Tq,      ldq)  fp16, head h at columns [h*dp, (h+1)*dp), dp = head dim padded to 16
+//                          (pad columns are exact zeros: the projection weight rows are zero-padded)
+//   K  : (B*Tk_pad,  ldk)  fp16, same head layout
+//   Vt : (NH*dp, B*Tk_pad) fp16, V transposed (tokens contiguous) — written directly by a swapped-operand GEMM
+//   O  : fp16, element (b,h,t,j) at b*osb + h*osh + t*ost + j, j < d. The reference's CrossAttention
+//        reshapes (B,NH,T,HS) straight to (B,T,NH*HS) (attention.py:39) — that is osb=NH*T*d, osh=T*d,
+//        ost=d; the canonical head merge is osb=T*NH*d, osh=d, ost=NH*d.
+// Q/K tiles use 32-byte swizzle slabs of 16 head-dim elements (any dp % 16 == 0 without padding to 64);
+// P and V^T use 128-byte swizzle atoms of 64 keys.
+#include "tf_common.cuh"
+#include "tinyfusers_b200.h"
+
+namespace {
+
+constexpr int kAttThreads = 192;
+constexpr int BQ = 128;
+
+struct AttnParams {
+  int B, NH, Tq, Tk, Tk_pad, d, dp;
+  int nkv;      // key blocks
+  int stages;   // K/V ring depth
+  uint32_t tmem_cols;
+  float scale_log2;  // (1/sqrt(d)) * log2(e)
+  __half* out;
+  long long osb, osh, ost;
+};
+
+// K-major operand, 32-byte swizzle: rows are 32 B (16 fp16), 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kAttThreads, (BN == 64) ? 2 : 1)
+tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = tf::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int ST = p.stages;
+
+  const uint32_t q_bytes = BQ * p.dp * 2;
+  const uint32_t k_bytes = BN * p.dp * 2;  // K tile and V^T tile have the same size
+  const uint32_t p_bytes = BQ * BN * 2;
+  const uint32_t smem_q = smem_base;
+  const uint32_t smem_k = smem_q + q_bytes;
+  const uint32_t smem_v = smem_k + ST * k_bytes;
+  const uint32_t smem_p = smem_v + ST * k_bytes;
+  const uint32_t bar_base = smem_p + p_bytes;
+  // barriers
+  const uint32_t q_full = bar_base;
+  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
+  auto s_full = [&](int i) { return bar_base + 8u * (1 + 2 * ST + i); };
+  auto s_empty = [&](int i) { return bar_base + 8u * (3 + 2 * ST + i); };
+  const uint32_t p_full = bar_base + 8u * (5 + 2 * ST);
+  const uint32_t pv_done = bar_base + 8u * (6 + 2 * ST);
+  const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * ST);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+  if (warp == 0 && lane == 0) {
+    tf::tma_prefetch_desc(&tmQ);
+    tf::tma_prefetch_desc(&tmK);
+    tf::tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    tf::mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      tf::mbar_init(kv_full(s), 1);
+      tf::mbar_init(kv_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tf::mbar_init(s_full(i), 1);
+      tf::mbar_init(s_empty(i), 128);
+    }
+    tf::mbar_init(p_full, 128);
+    tf::mbar_init(pv_done, 1);
+    tf::fence_mbar_init();
+  }
+  if (warp == 2) {
+    tf::tmem_alloc(tmem_slot, p.tmem_cols);
+    tf::tmem_relinquish();
+  }
+  tf::tcgen05_fence_before();
+  __syncthreads();
+  tf::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_s0 = tmem_base;            // S buffers: columns [0,BN) and [BN,2BN)
+  const uint32_t tmem_o = tmem_base + 2 * BN;    // O: dp columns
+
+  const int nkv = p.nkv;
+  const int slabs = p.dp / 16;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tf::mbar_expect_tx(q_full, q_bytes);
+      tf::tma_load_3d(smem_q, &tmQ, q_full, 0, b * p.Tq + qt * BQ, h * slabs);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % ST;
+        const uint32_t u = j / ST;
+        tf::mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
+        tf::mbar_expect_tx(kv_full(s), 2 * k_bytes);
+        const int key0 = b * p.Tk_pad + j * BN;
+        tf::tma_load_3d(smem_k + s * k_bytes, &tmK, kv_full(s), 0, key0, h * slabs);
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i)
+          tf::tma_load_2d(smem_v + s * k_bytes + i * (p.dp * 128), &tmV, kv_full(s), key0 + 64 * i, h * p.dp);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = tf::umma_idesc_f16(BQ, BN);
+      const uint32_t idesc_o = tf::umma_idesc_f16(BQ, p.dp);
+      auto issue_s = [&](int j) {
+        const int s = j % ST;
+        tf::mbar_wait(kv_full(s), (uint32_t)(j / ST) & 1u);
+        const int buf = j & 1;
+        tf::mbar_wait(s_empty(buf), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        tf::tcgen05_fence_after();
+        const uint32_t kbase = smem_k + s * k_bytes;
+        for (int k = 0; k < slabs; ++k) {
+          tf::umma_f16_ss(tmem_s0 + buf * BN, umma_desc_sw32_kmajor(smem_q + k * (BQ * 32)),
+                          umma_desc_sw32_kmajor(kbase + k * (BN * 32)), idesc_s, k > 0 ? 1u : 0u);
+        }
+        tf::umma_commit(s_full(buf));
+      };
+      tf::mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_s(j + 1);
+        tf::mbar_wait(p_full, (uint32_t)j & 1u);
+        tf::tcgen05_fence_after();
+        const int s = j % ST;
+        const uint32_t vbase = smem_v + s * k_bytes;
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint32_t atom = k >> 2, sub = k & 3;
+          tf::umma_f16_ss(tmem_o, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub,
+                          tf::umma_desc_sw128_kmajor(vbase + atom * (p.dp * 128)) + 2u * sub, idesc_o,
+                          (j > 0 || k > 0) ? 1u : 0u);
+        }
+        tf::umma_commit(pv_done);
+        tf::umma_commit(kv_empty(s));
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    float m_run = -INFINITY;  // running max, already in the scaled log2 domain
+    float l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int buf = j & 1;
+      tf::mbar_wait(s_full(buf), ((uint32_t)(j >> 1)) & 1u);
+      tf::tcgen05_fence_after();
+      uint32_t v[BN];
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) tf::tmem_ld_x32(tmem_s0 + lane_field + buf * BN + c, v + c);
+      tf::tmem_ld_wait();
+      tf::tcgen05_fence_before();
+      tf::mbar_arrive(s_empty(buf));
+      const int valid = min(BN, p.Tk - j * BN);  // keys >= Tk are padding / another batch
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BN; ++i) {
+        float x = __uint_as_float(v[i]) * p.scale_log2;
+        x = (i < valid) ? x : -INFINITY;
+        v[i] = __float_as_uint(x);
+        mx = fmaxf(mx, x);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      float rowsum = 0.f;
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int i = 0; i < BN; i += 2) {
+        const float p0 = exp2f(__uint_as_float(v[i]) - m_new);
+        const float p1 = exp2f(__uint_as_float(v[i + 1]) - m_new);
+        rowsum += p0 + p1;
+        __half2 hh = __floats2half2_rn(p0, p1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+      // P smem and O are owned by the tensor core until PV_{j-1} has completed
+      if (j > 0) {
+        tf::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+        tf::tcgen05_fence_after();
+      }
+      // P -> shared memory, K-major 128B swizzle: 16-byte chunk index XOR (row & 7)
+#pragma unroll
+      for (int a = 0; a < BN / 64; ++a) {
+        const uint32_t rbase = smem_p + a * (BQ * 128) + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t addr = rbase + ((uint32_t)(ch ^ (row & 7)) << 4);
+          const int w = a * 32 + ch * 4;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[w]), "r"(pk[w + 1]),
+                       "r"(pk[w + 2]), "r"(pk[w + 3])
+                       : "memory");
+        }
+      }
+      // rescale the running output if any row of this warp moved its max
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        for (int c = 0; c < p.dp; c += 16) {
+          uint32_t o[16];
+          tf::tmem_ld_x16(tmem_o + lane_field + c, o);
+          tf::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tf::tmem_st_x16(tmem_o + lane_field + c, o);
+        }
+        tf::tmem_st_wait();
+      }
+      tf::fence_proxy_async_smem();
+      tf::tcgen05_fence_before();
+      tf::mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> fp16 -> global ----
+    tf::mbar_wait(pv_done, (uint32_t)(nkv - 1) & 1u);
+    tf::tcgen05_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int t = qt * BQ + row;
+    __half* orow = p.out + (long long)b * p.osb + (long long)h * p.osh + (long long)t * p.ost;
+    for (int c = 0; c < p.dp; c += 16) {
+      uint32_t o[16];
+      tf::tmem_ld_x16(tmem_o + lane_field + c, o);
+      tf::tmem_ld_wait();
+      if (t < p.Tq) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            tf::Pack16 pk8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              pk8.h2[i] = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv_l,
+                                            __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + g * 8) = pk8.v;
+          }
+        }
+      }
+    }
+  }
+
+  tf::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tf::tcgen05_fence_after();
+    tf::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int g_force_attn_bn = 0;
+
+}  // namespace
+
+extern "C" int tf_attention_set_tuning(int force_bn) {
+  g_force_attn_bn = force_bn;
+  return TF_OK;
+}
+
+extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
+                                long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
+                                int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TF_CHECK_ARG(q && k && vt && out, "tf_attention_f16: null pointer");
+  TF_CHECK_ARG(B > 0 && NH > 0 && Tq > 0 && Tk > 0 && Tk_pad >= Tk, "tf_attention_f16: bad dims");
+  TF_CHECK_ARG(dp % 16 == 0 && dp >= 16 && dp <= 256 && d <= dp && d % 8 == 0,
+               "tf_attention_f16: head dim d=%d (padded %d) unsupported: need d %% 8 == 0, dp %% 16 == 0, dp <= 256", d, dp);
+  TF_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && Tk_pad % 8 == 0,
+               "tf_attention_f16: leading dims / Tk_pad must be multiples of 8");
+  TF_CHECK_ARG(ldq >= NH * dp && ldk >= NH * dp && ldvt >= B * Tk_pad, "tf_attention_f16: leading dims too small");
+  TF_CHECK_ARG(out_stride_t % 8 == 0 && out_stride_h % 8 == 0 && out_stride_b % 8 == 0,
+               "tf_attention_f16: output strides must be multiples of 8");
+  TF_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)vt & 15) == 0 &&
+                   ((uintptr_t)out & 15) == 0,
+               "tf_attention_f16: pointers must be 16-byte aligned");
+
+  int BN = (dp <= 96) ? 64 : 64;
+  if (2 * 128 + dp <= 512 && dp <= 64 && false) BN = 128;
+  if (g_force_attn_bn == 64 || g_force_attn_bn == 128) BN = g_force_attn_bn;
+  if (BN == 128 && 2 * 128 + dp > 512) BN = 64;
+
+  AttnParams p{};
+  p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp;
+  p.nkv = ceil_div_i(Tk, BN);
+  uint32_t need = 2 * BN + dp, cols = 32;
+  while (cols < need) cols <<= 1;
+  p.tmem_cols = cols;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__half*>(out);
+  p.osb = out_stride_b; p.osh = out_stride_h; p.ost = out_stride_t;
+
+  const size_t q_bytes = (size_t)BQ * dp * 2, k_bytes = (size_t)BN * dp * 2, p_bytes = (size_t)BQ * BN * 2;
+  const size_t budget = (cols <= 256 ? 113 : 227) * 1024 - 2048;
+  int stages = (int)((budget - q_bytes - p_bytes) / (2 * k_bytes));
+  if (stages > 4) stages = 4;
+  if (stages > p.nkv) stages = p.nkv < 1 ? 1 : p.nkv;
+  TF_CHECK_ARG(stages >= 1, "tf_attention_f16: head dim %d does not fit shared memory", dp);
+  p.stages = stages;
+  const size_t smem = q_bytes + p_bytes + (size_t)stages * 2 * k_bytes + 2048;
+
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {16, (uint64_t)B * Tq, (uint64_t)(ldq / 16)};
+    uint64_t strides[2] = {(uint64_t)ldq * 2, 32};
+    uint32_t box[3] = {16, BQ, (uint32_t)(dp / 16)};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = tf_encode_tmap(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {16, (uint64_t)B * Tk_pad, (uint64_t)(ldk / 16)};
+    uint64_t strides[2] = {(uint64_t)ldk * 2, 32};
+    uint32_t box[3] = {16, (uint32_t)BN, (uint32_t)(dp / 16)};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = tf_encode_tmap(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, k, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)B * Tk_pad, (uint64_t)NH * dp};
+    uint64_t strides[1] = {(uint64_t)ldvt * 2};
+    uint32_t box[2] = {64, (uint32_t)dp};
+    uint32_t es[2] = {1, 1};
+    int rc = tf_encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  dim3 grid(ceil_div_i(Tq, BQ), NH, B);
+  if (BN == 64) {
+    static bool set64 = false;
+    if (!set64) {
+      TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set64 = true;
+    }
+    tf_attention_kernel<64><<<grid, kAttThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    static bool set128 = false;
+    if (!set128) {
+      TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      set128 = true;
+    }
+    tf_attention_kernel<128><<<grid, kAttThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  }
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}

@@ -1,0 +1,313 @@
+// tinyfusers_b200 — the small HBM/launch-bound pieces of the UNet step:
+//   timestep embedding, the M=1 time-MLP / ResBlock emb projections (GEMV), the Cin=4 input conv,
+//   nearest x2 upsample, NCHW<->NHWC edge conversions and the fused CFG-combine + DDIM update.
+#include "tf_common.cuh"
+#include "tinyfusers_b200.h"
+
+namespace {
+
+// reference: tinyfusers/vision/unet.py:92-97. Angles are formed in fp64 like the reference
+// (int64 timestep * float promotes to float64 in CuPy), the result is fp32.
+__global__ void timestep_embedding_kernel(const float* __restrict__ t_dev, const int* __restrict__ idx_dev,
+                                          int dim, float max_period, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= half) return;
+  const double t = (double)t_dev[idx_dev ? *idx_dev : 0];
+  const double f = exp(-log((double)max_period) * (double)i / (double)half);
+  const double a = t * f;
+  out[i] = (float)cos(a);
+  out[half + i] = (float)sin(a);
+}
+
+// out[n] = sum_k act(x[k]) * W[n,k] + bias[n] (+ bias2[n]); one warp per output row, fp16 weights.
+// reference: Linear at M=1 — UNet time_embed (vision/unet.py:11,54) and ResBlock.emb_layers
+// (vision/resnet.py:13-16,27). All 22 ResBlock projections are served by ONE launch over the
+// row-concatenated weight matrix.
+__global__ void gemv_kernel(const float* __restrict__ x, const __half* __restrict__ W, const float* __restrict__ bias,
+                            const float* __restrict__ bias2, float* __restrict__ out, int N, int K, int silu_in) {
+  extern __shared__ float xs[];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float v = x[k];
+    xs[k] = silu_in ? tf::silu_f(v) : v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= N) return;
+  const __half* w = W + (size_t)n * K;
+  float acc = 0.f;
+  for (int k = lane * 8; k < K; k += 32 * 8) {
+    tf::Pack16 pk;
+    pk.v = __ldg(reinterpret_cast<const uint4*>(w + k));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(pk.h2[j]);
+      acc += f.x * xs[k + 2 * j] + f.y * xs[k + 2 * j + 1];
+    }
+  }
+  acc = tf::warp_sum(acc);
+  if (lane == 0) out[n] = acc + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f);
+}
+
+// 3x3 pad-1 conv with a tiny input-channel count, fp32 NCHW in -> fp16 NHWC out.
+// reference: UNetModel.input_blocks[0] = Conv2d(4, 320, 3x3, pad 1) (vision/unet.py:13).
+// w: fp32 (Cout, Cin, 3, 3) exactly as the reference stores it. Each thread: one pixel x 8 output channels.
+template <int CIN>
+__global__ void conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ bias, __half* __restrict__ out, int NI, int H,
+                                        int W_, int Cout, int out_stride) {
+  extern __shared__ float ws[];  // [Cout][CIN*9]
+  for (int i = threadIdx.x; i < Cout * CIN * 9; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long total = (long)NI * H * W_ * groups;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long pix = idx / groups;
+    const int xo = (int)(pix % W_);
+    const int yo = (int)((pix / W_) % H);
+    const int n = (int)(pix / ((long)W_ * H));
+    float in[CIN * 9];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int yy = yo + r - 1, xx = xo + s - 1;
+          in[c * 9 + r * 3 + s] =
+              (yy >= 0 && yy < H && xx >= 0 && xx < W_) ? x[(((size_t)n * CIN + c) * H + yy) * W_ + xx] : 0.f;
+        }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wr = ws + (g * 8 + j) * CIN * 9;
+      float a = bias ? bias[g * 8 + j] : 0.f;
+#pragma unroll
+      for (int k = 0; k < CIN * 9; ++k) a += in[k] * wr[k];
+      acc[j] = a;
+    }
+    tf::Pack16 pk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pk.h2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + (size_t)pix * out_stride + g * 8) = pk.v;
+  }
+}
+
+// nearest-neighbour x2 (reference: Upsample.__call__ broadcast+reshape, vision/unet.py:81-83)
+__global__ void upsample2x_kernel(const __half* __restrict__ x, int x_stride, __half* __restrict__ out,
+                                  int out_stride, int NI, int H, int W_, int C) {
+  const int nvec = C / 8;
+  const long total = (long)NI * 2 * H * 2 * W_ * nvec;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    const long pix = idx / nvec;
+    const int xo = (int)(pix % (2 * W_));
+    const int yo = (int)((pix / (2 * W_)) % (2 * H));
+    const int n = (int)(pix / ((long)4 * W_ * H));
+    const size_t src = (((size_t)n * H + (yo >> 1)) * W_ + (xo >> 1)) * x_stride + v * 8;
+    *reinterpret_cast<uint4*>(out + (size_t)pix * out_stride + v * 8) = *reinterpret_cast<const uint4*>(x + src);
+  }
+}
+
+// fp32/fp16 NCHW -> fp16 NHWC (API edge: per-op wrappers keep the reference's NCHW signatures)
+template <typename TIn>
+__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, __half* __restrict__ out, int C, int HW,
+                                    int out_stride) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? (float)x[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) out[((size_t)n * HW + p) * out_stride + c] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename TOut>
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int x_stride, TOut* __restrict__ out, int C,
+                                    int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? __half2float(x[((size_t)n * HW + p) * x_stride + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = (TOut)tile[threadIdx.x][i];
+  }
+}
+
+// fp32 (rows, C) -> fp16 (rows_pad, C) with zero rows appended per batch (prompt context 77 -> 80 tokens)
+__global__ void pad_tokens_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int T, int Tpad,
+                                  int C) {
+  const long total = (long)B * Tpad * C;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int t = (int)((idx / C) % Tpad);
+    const int b = (int)(idx / ((long)C * Tpad));
+    out[idx] = t < T ? __float2half_rn(x[((size_t)b * T + t) * C + c]) : __float2half_rn(0.f);
+  }
+}
+
+// CFG combine + DDIM (eta = 0) update, fused.
+// reference: variants/sd.py:44-45 (e_t = u + g (c - u)) and sd.py:14-25 (x_prev).
+// eps: fp32 NHWC, pixel stride eps_stride, images [0,B) = unconditional, [B,2B) = conditional
+// (order [uncond ; cond], sd.py:32). latent in/out: fp32 NCHW (B, C, H, W).
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps, int eps_stride, const float* __restrict__ latent,
+                                float* __restrict__ latent_out, float* __restrict__ e_t_out,
+                                const float* __restrict__ a_t_tab, const float* __restrict__ a_prev_tab,
+                                const int* __restrict__ idx_dev, float guidance, int B, int C, int HW) {
+  const int idx = idx_dev ? *idx_dev : 0;
+  const float a_t = a_t_tab[idx], a_prev = a_prev_tab[idx];
+  const float sqrt_one_minus_at = sqrtf(1.f - a_t);
+  const float inv_sqrt_at = 1.f / sqrtf(a_t);
+  const float sqrt_aprev = sqrtf(a_prev);
+  const float dir_coef = sqrtf(1.f - a_prev);
+  const long total = (long)B * C * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int b = (int)(i / ((long)HW * C));
+    const float u = eps[((size_t)b * HW + p) * eps_stride + c];
+    const float cnd = eps[((size_t)(B + b) * HW + p) * eps_stride + c];
+    const float e = u + guidance * (cnd - u);
+    const float x = latent[i];
+    const float pred_x0 = (x - sqrt_one_minus_at * e) * inv_sqrt_at;
+    latent_out[i] = sqrt_aprev * pred_x0 + dir_coef * e;
+    if (e_t_out) e_t_out[i] = e;
+  }
+}
+
+// latent (B,C,H,W) fp32 -> (2B,C,H,W) fp32 duplicated (reference: broadcast_to in sd.py:31); trivial copy
+__global__ void add_int_kernel(int* p, int delta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *p += delta;
+}
+
+static int ew_blocks(long total, int threads) {
+  long b = (total + threads - 1) / threads;
+  const long cap = (long)tf_num_sms() * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int tf_timestep_embedding_f32(const float* timesteps_dev, const int* index_dev, int dim,
+                                         float max_period, float* out, void* stream) {
+  TF_CHECK_ARG(timesteps_dev && out && dim > 0 && dim % 2 == 0, "tf_timestep_embedding_f32: bad arguments");
+  const int half = dim / 2;
+  timestep_embedding_kernel<<<ceil_div_i(half, 128), 128, 0, (cudaStream_t)stream>>>(timesteps_dev, index_dev, dim,
+                                                                                    max_period, out);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_gemv_f16w(const float* x, const void* W, const float* bias, const float* bias2, float* out, int N,
+                            int K, int silu_input, void* stream) {
+  TF_CHECK_ARG(x && W && out && N > 0 && K > 0 && K % 8 == 0, "tf_gemv_f16w: bad arguments (N=%d K=%d)", N, K);
+  TF_CHECK_ARG(K * sizeof(float) <= 48 * 1024, "tf_gemv_f16w: K too large (%d)", K);
+  const int threads = 256;
+  gemv_kernel<<<ceil_div_i(N, threads / 32), threads, K * sizeof(float), (cudaStream_t)stream>>>(
+      x, (const __half*)W, bias, bias2, out, N, K, silu_input);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, const float* w, const float* bias, void* out, int NI,
+                                           int Cin, int H, int W, int Cout, int out_pixel_stride, void* stream) {
+  TF_CHECK_ARG(x && w && out, "tf_conv3x3_smallcin_f32nchw: null pointer");
+  TF_CHECK_ARG(Cin == 4, "tf_conv3x3_smallcin_f32nchw: only Cin == 4 is built (got %d)", Cin);
+  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && Cout * Cin * 9 * 4 <= 48 * 1024,
+               "tf_conv3x3_smallcin_f32nchw: bad Cout %d", Cout);
+  const long total = (long)NI * H * W * (Cout / 8);
+  conv3x3_smallcin_kernel<4><<<ew_blocks(total, 256), 256, Cout * Cin * 9 * sizeof(float), (cudaStream_t)stream>>>(
+      x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_upsample_nearest2x_nhwc_f16(const void* x, int x_pixel_stride, void* out, int out_pixel_stride,
+                                              int NI, int H, int W, int C, void* stream) {
+  TF_CHECK_ARG(x && out && C % 8 == 0 && x_pixel_stride % 8 == 0 && out_pixel_stride % 8 == 0,
+               "tf_upsample_nearest2x_nhwc_f16: bad arguments");
+  const long total = (long)NI * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, x_pixel_stride,
+                                                                            (__half*)out, out_pixel_stride, NI, H, W, C);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_nchw_to_nhwc_f16(const void* x, int x_is_f32, void* out, int NI, int C, int HW,
+                                   int out_pixel_stride, void* stream) {
+  TF_CHECK_ARG(x && out && NI > 0 && C > 0 && HW > 0 && out_pixel_stride >= C, "tf_nchw_to_nhwc_f16: bad arguments");
+  dim3 grid(ceil_div_i(HW, 32), ceil_div_i(C, 32), NI), block(32, 8);
+  if (x_is_f32)
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, (__half*)out, C, HW,
+                                                                         out_pixel_stride);
+  else
+    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, C, HW,
+                                                                          out_pixel_stride);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_nhwc_to_nchw(const void* x, int x_pixel_stride, void* out, int out_is_f32, int NI, int C, int HW,
+                               void* stream) {
+  TF_CHECK_ARG(x && out && NI > 0 && C > 0 && HW > 0 && x_pixel_stride >= C, "tf_nhwc_to_nchw: bad arguments");
+  dim3 grid(ceil_div_i(HW, 32), ceil_div_i(C, 32), NI), block(32, 8);
+  if (out_is_f32)
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, x_pixel_stride, (float*)out,
+                                                                         C, HW);
+  else
+    nhwc_to_nchw_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, x_pixel_stride,
+                                                                          (__half*)out, C, HW);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_pad_tokens_f32_to_f16(const float* x, void* out, int B, int T, int Tpad, int C, void* stream) {
+  TF_CHECK_ARG(x && out && B > 0 && T > 0 && Tpad >= T && C > 0, "tf_pad_tokens_f32_to_f16: bad arguments");
+  const long total = (long)B * Tpad * C;
+  pad_tokens_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)out, B, T, Tpad, C);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride, const float* latent,
+                                    float* latent_out, float* e_t_out, const float* alphas_dev,
+                                    const float* alphas_prev_dev, const int* index_dev, float guidance, int B, int C,
+                                    int HW, void* stream) {
+  TF_CHECK_ARG(eps_nhwc && latent && latent_out && alphas_dev && alphas_prev_dev,
+               "tf_cfg_ddim_step_f32: null pointer");
+  TF_CHECK_ARG(B > 0 && C > 0 && HW > 0 && eps_pixel_stride >= C, "tf_cfg_ddim_step_f32: bad dims");
+  const long total = (long)B * C * HW;
+  cfg_ddim_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      eps_nhwc, eps_pixel_stride, latent, latent_out, e_t_out, alphas_dev, alphas_prev_dev, index_dev, guidance, B, C,
+      HW);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_add_int(int* p_dev, int delta, void* stream) {
+  TF_CHECK_ARG(p_dev, "tf_add_int: null pointer");
+  add_int_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p_dev, delta);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}

@@ -1,0 +1,325 @@
+// tinyfusers_b200 — GroupNorm(+SiLU) and LayerNorm for NHWC / (B,T,C) fp16 activations (HBM-bound).
+//
+// GroupNorm (reference: tinyfusers/ff/group_norm.py:3-21, followed by Tensor.silu in
+// vision/resnet.py:8-10,17-19 and vision/unet.py:45-47): the reference runs >= 8 CuPy elementwise /
+// reduction launches and >= 6 full read+write passes. Here: one statistics pass (128-bit loads, register
+// partials per channel, shared-memory group bins, one global atomic per group per block) and one
+// apply pass that fuses normalise + affine + SiLU and writes the fp16 NHWC tensor the following
+// implicit-GEMM conv reads through TMA. Both passes accept a channel slice of a wider tensor
+// (pixel stride != C), which is how the UNet's skip concatenation is consumed without a copy.
+//
+// LayerNorm (reference: tinyfusers/ff/layer_norm.py:8-49, cuDNN graph rebuilt per call): one warp per
+// row, row cached in registers, exact two-pass statistics. `interleave` > 1 reproduces the reference's
+// NHWC-stride declaration at batch > 1 (SURVEY.md §8 parity note 1): the buffer is viewed as
+// (T, C, B) and normalised over C for each (t, b).
+#include "tf_common.cuh"
+#include "tinyfusers_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics: stats[(n*G + g)*2 + {0,1}] += {sum, sumsq}
+// block = nvec * k threads (nvec = Cs/8), so a thread always sees the same 8 channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, int x_stride, int c_off,
+                                int cpg, int G, int pix_per_block, float* __restrict__ stats) {
+  __shared__ float bins[2 * 64];
+  const int n = blockIdx.y;
+  const int nvec = Cs >> 3;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int npl = blockDim.x / nvec;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) bins[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const __half* base = x + (size_t)n * HW * x_stride + v * 8;
+  for (int p = p0 + pl; p < p1; p += npl) {
+    tf::Pack16 pk;
+    pk.v = *reinterpret_cast<const uint4*>(base + (size_t)p * x_stride);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(pk.h2[j]);
+      s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+      s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+    }
+  }
+  // fold the 8 channels into their (at most two) groups before touching shared memory
+  const int c0 = c_off + v * 8;
+  const int g0 = c0 / cpg;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+  bool two = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    if (g == g0) { s0 += s[j]; q0 += q[j]; }
+    else if (g == g0 + 1) { s1 += s[j]; q1 += q[j]; two = true; }
+    else { atomicAdd(&bins[2 * g], s[j]); atomicAdd(&bins[2 * g + 1], q[j]); }  // cpg < 4: rare path
+  }
+  atomicAdd(&bins[2 * g0], s0);
+  atomicAdd(&bins[2 * g0 + 1], q0);
+  if (two) { atomicAdd(&bins[2 * (g0 + 1)], s1); atomicAdd(&bins[2 * (g0 + 1) + 1], q1); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    const float val = bins[i];
+    if (val != 0.f) atomicAdd(&stats[(size_t)n * 2 * G + i], val);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply: out = act((x - mean) * rstd * gamma + beta), act = SiLU or identity
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, int x_stride, int c_off,
+                                int cpg, int G, int pix_per_block, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                float inv_count, int silu, __half* __restrict__ out, int out_stride) {
+  const int n = blockIdx.y;
+  const int nvec = Cs >> 3;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int npl = blockDim.x / nvec;
+  const int c0 = c_off + v * 8;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    const float sum = stats[((size_t)n * G + g) * 2];
+    const float sq = stats[((size_t)n * G + g) * 2 + 1];
+    const float mean = sum * inv_count;
+    const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    a[j] = rstd * ga;
+    b[j] = be - mean * rstd * ga;
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const __half* xin = x + (size_t)n * HW * x_stride + v * 8;
+  __half* o = out + (size_t)n * HW * out_stride + c0;
+  for (int p = p0 + pl; p < p1; p += npl) {
+    tf::Pack16 pk;
+    pk.v = *reinterpret_cast<const uint4*>(xin + (size_t)p * x_stride);
+    tf::Pack16 r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(pk.h2[j]);
+      float y0 = f.x * a[2 * j] + b[2 * j];
+      float y1 = f.y * a[2 * j + 1] + b[2 * j + 1];
+      if (silu) { y0 = tf::silu_f(y0); y1 = tf::silu_f(y1); }
+      r.h2[j] = __floats2half2_rn(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(o + (size_t)p * out_stride) = r.v;
+  }
+}
+
+static int gn_block_threads(int Cs) {
+  const int nvec = Cs / 8;
+  int k = 512 / nvec;
+  if (k < 1) k = 1;
+  return nvec * k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row; IL = interleave factor (1 canonical; >1 reference stride quirk)
+// memory index of logical element (row r = (t, b), channel c):  t*C*IL + c*IL + b
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>  // max 8-half vectors per lane
+__global__ void ln_rows_kernel(const __half* __restrict__ x, __half* __restrict__ out, int rows, int C,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const __half* xr = x + (size_t)warp * C;
+  tf::Pack16 pk[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      pk[i].v = *reinterpret_cast<const uint4*>(xr + v * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(pk[i].h2[j]);
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = tf::warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(pk[i].h2[j]);
+        sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+  }
+  const float rstd = rsqrtf(tf::warp_sum(sq) / (float)C + eps);
+  __half* orow = out + (size_t)warp * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      tf::Pack16 r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(pk[i].h2[j]);
+        r.h2[j] = __floats2half2_rn((f.x - mean) * rstd * g[2 * j] + b[2 * j],
+                                    (f.y - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
+      }
+      *reinterpret_cast<uint4*>(orow + v * 8) = r.v;
+    }
+  }
+}
+
+// interleave == 2: one warp per chunk-row t; each half2 holds (b=0, b=1) of one channel.
+template <int MAXE>  // max half2 elements per lane
+__global__ void ln_il2_kernel(const __half* __restrict__ x, __half* __restrict__ out, int trow, int C,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= trow) return;
+  const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)warp * C * 2);
+  float2 e[MAXE];
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      e[i] = __half22float2(xr[c]);
+      s0 += e[i].x;
+      s1 += e[i].y;
+    }
+  }
+  const float m0 = tf::warp_sum(s0) / (float)C, m1 = tf::warp_sum(s1) / (float)C;
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      q0 += (e[i].x - m0) * (e[i].x - m0);
+      q1 += (e[i].y - m1) * (e[i].y - m1);
+    }
+  }
+  const float r0 = rsqrtf(tf::warp_sum(q0) / (float)C + eps), r1 = rsqrtf(tf::warp_sum(q1) / (float)C + eps);
+  __half2* orow = reinterpret_cast<__half2*>(out + (size_t)warp * C * 2);
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      const float g = __ldg(gamma + c), b = __ldg(beta + c);
+      orow[c] = __floats2half2_rn((e[i].x - m0) * r0 * g + b, (e[i].y - m1) * r1 * g + b);
+    }
+  }
+}
+
+// generic interleave: one warp per (t, b); strided scalar access (correct for any IL, not tuned)
+__global__ void ln_il_generic_kernel(const __half* __restrict__ x, __half* __restrict__ out, int trow, int C,
+                                     int IL, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= trow * IL) return;
+  const int t = warp / IL, b = warp % IL;
+  const __half* xr = x + (size_t)t * C * IL + b;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __half2float(xr[(size_t)c * IL]);
+  const float mean = tf::warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = __half2float(xr[(size_t)c * IL]) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(tf::warp_sum(q) / (float)C + eps);
+  __half* orow = out + (size_t)t * C * IL + b;
+  for (int c = lane; c < C; c += 32)
+    orow[(size_t)c * IL] = __float2half_rn((__half2float(xr[(size_t)c * IL]) - mean) * rstd * gamma[c] + beta[c]);
+}
+
+}  // namespace
+
+extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void* x2,
+                                     int x2_pixel_stride, int Cx2, void* out, int out_pixel_stride, int NI,
+                                     int HW, int groups, const float* gamma, const float* beta, float eps,
+                                     int apply_silu, float* stats_ws, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TF_CHECK_ARG(x && out && stats_ws, "tf_groupnorm_nhwc_f16: null pointer");
+  const int C = Cx + (x2 ? Cx2 : 0);
+  TF_CHECK_ARG(NI > 0 && HW > 0 && groups > 0 && groups <= 64 && C % groups == 0,
+               "tf_groupnorm_nhwc_f16: bad dims (C=%d groups=%d)", C, groups);
+  TF_CHECK_ARG(Cx % 8 == 0 && (!x2 || Cx2 % 8 == 0) && x_pixel_stride % 8 == 0 && out_pixel_stride % 8 == 0 &&
+                   (!x2 || x2_pixel_stride % 8 == 0),
+               "tf_groupnorm_nhwc_f16: channels and strides must be multiples of 8");
+  TF_CHECK_ARG(Cx / 8 <= 1024 && (!x2 || Cx2 / 8 <= 1024), "tf_groupnorm_nhwc_f16: too many channels");
+  const int cpg = C / groups;
+  TF_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * NI, stream));
+  const int sms = tf_num_sms();
+  int chunks = (2 * sms + NI - 1) / NI;
+  if (chunks > HW) chunks = HW;
+  const int ppb = ceil_div_i(HW, chunks);
+  chunks = ceil_div_i(HW, ppb);
+  const dim3 grid(chunks, NI);
+  const float inv_count = 1.0f / ((float)cpg * (float)HW);
+  const __half* xs[2] = {reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x2)};
+  const int cs[2] = {Cx, Cx2}, st[2] = {x_pixel_stride, x2_pixel_stride}, off[2] = {0, Cx};
+  const int nsrc = x2 ? 2 : 1;
+  for (int i = 0; i < nsrc; ++i) {
+    gn_stats_kernel<<<grid, gn_block_threads(cs[i]), 0, stream>>>(xs[i], HW, cs[i], st[i], off[i], cpg, groups,
+                                                                ppb, stats_ws);
+    TF_LAUNCH_CHECK();
+  }
+  for (int i = 0; i < nsrc; ++i) {
+    gn_apply_kernel<<<grid, gn_block_threads(cs[i]), 0, stream>>>(
+        xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, stats_ws, gamma, beta, eps, inv_count, apply_silu,
+        reinterpret_cast<__half*>(out), out_pixel_stride);
+    TF_LAUNCH_CHECK();
+  }
+  tf_launch_count_add(2 * nsrc);
+  return TF_OK;
+}
+
+extern "C" int tf_layernorm_f16(const void* x, void* out, int rows, int C, const float* gamma, const float* beta,
+                                float eps, int interleave, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TF_CHECK_ARG(x && out && gamma && beta, "tf_layernorm_f16: null pointer");
+  TF_CHECK_ARG(rows > 0 && C > 0 && interleave >= 1 && rows % interleave == 0,
+               "tf_layernorm_f16: bad dims rows=%d C=%d interleave=%d", rows, C, interleave);
+  const int threads = 256, wpb = threads / 32;
+  if (interleave == 1) {
+    TF_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "tf_layernorm_f16: C must be a multiple of 8 and <= 2048");
+    const int blocks = ceil_div_i(rows, wpb);
+    const int nv = ceil_div_i(C / 8, 32);
+    if (nv <= 2) ln_rows_kernel<2><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows, C, gamma, beta, eps);
+    else if (nv <= 5) ln_rows_kernel<5><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows, C, gamma, beta, eps);
+    else ln_rows_kernel<8><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows, C, gamma, beta, eps);
+  } else if (interleave == 2 && C <= 32 * 40) {
+    const int trow = rows / 2;
+    const int blocks = ceil_div_i(trow, wpb);
+    const int ne = ceil_div_i(C, 32);
+    if (ne <= 10) ln_il2_kernel<10><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, trow, C, gamma, beta, eps);
+    else if (ne <= 20) ln_il2_kernel<20><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, trow, C, gamma, beta, eps);
+    else ln_il2_kernel<40><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, trow, C, gamma, beta, eps);
+  } else {
+    const int blocks = ceil_div_i(rows, wpb);
+    ln_il_generic_kernel<<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows / interleave, C,
+                                                         interleave, gamma, beta, eps);
+  }
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
