@@ -74,7 +74,9 @@ int tf_gemm_set_tuning(int force_bn, int force_splits);
  * The input may be given as TWO channel slices (x: Cx channels, x2: Cx2 channels, each with its own pixel
  * stride) that are normalised as their channel concatenation — this is how
  * `cp.concatenate((x, saved_inputs.pop()), axis=1)` (vision/unet.py:72) is consumed without a copy.
- * x2 may be NULL. gamma/beta: fp32 (C) or NULL. stats_ws: fp32 scratch, 2*groups*NI floats. */
+ * x2 may be NULL. gamma/beta: fp32 (C) or NULL. stats_ws: scratch of tf_groupnorm_workspace_bytes(NI, groups)
+ * bytes. Statistics are reduced in a fixed order (no atomics): results are bit-reproducible. */
+size_t tf_groupnorm_workspace_bytes(int NI, int groups);
 int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void* x2, int x2_pixel_stride,
                           int Cx2, void* out, int out_pixel_stride, int NI, int HW, int groups,
                           const float* gamma, const float* beta, float eps, int apply_silu, float* stats_ws,
@@ -93,7 +95,8 @@ int tf_layernorm_f16(const void* x, void* out, int rows, int C, const float* gam
  * Replaces: scaled_dot_product_attention (2 cuBLAS batched SGEMMs + softmax_kernel)
  *           tinyfusers/attention/sdpa.py:53-77, tinyfusers/native/cuda/softmax.cu:24-112.
  * q: (B*Tq, ldq), k: (B*Tk_pad, ldk): head h at columns [h*dp, (h+1)*dp), dp = d padded to 16 with zeros;
- * vt: (NH*dp, ldvt >= B*Tk_pad) = V transposed; keys [Tk, Tk_pad) of each batch are padding (ignored).
+ * vt: (NH*dp, ldvt >= B*Tk_pad) = V transposed, ldvt % 8 == 0; batch b owns key rows/columns
+ * [b*Tk_pad, b*Tk_pad + Tk); keys [Tk, Tk_pad) of each batch are padding (ignored).
  * out element (b,h,t,j<d) at b*out_stride_b + h*out_stride_h + t*out_stride_t + j — the strides select
  * the reference's head-major reshape (attention/attention.py:39) or the canonical head merge. */
 int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
@@ -113,9 +116,11 @@ int tf_timestep_embedding_f32(const float* timesteps_dev, const int* index_dev, 
 int tf_gemv_f16w(const float* x, const void* W, const float* bias, const float* bias2, float* out, int N, int K,
                  int silu_input, void* stream);
 /* 3x3 pad-1 conv, Cin = 4, fp32 NCHW in, fp32 OIHW weights, fp16 NHWC out.
+ * Output image n reads input image n % x_images: the CFG batch [latent ; latent] (variants/sd.py:31,
+ * cp.broadcast_to) is formed without materialising the copy.
  * Replaces: UNetModel.input_blocks[0] Conv2d(4,320)  tinyfusers/vision/unet.py:13. */
-int tf_conv3x3_smallcin_f32nchw(const float* x, const float* w, const float* bias, void* out, int NI, int Cin,
-                                int H, int W, int Cout, int out_pixel_stride, void* stream);
+int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out, int NI,
+                                int Cin, int H, int W, int Cout, int out_pixel_stride, void* stream);
 /* nearest x2. Replaces: Upsample.__call__ broadcast/reshape  tinyfusers/vision/unet.py:81-83. */
 int tf_upsample_nearest2x_nhwc_f16(const void* x, int x_pixel_stride, void* out, int out_pixel_stride, int NI,
                                    int H, int W, int C, void* stream);
@@ -135,6 +140,15 @@ int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride, const floa
                          const int* index_dev, float guidance, int B, int C, int HW, void* stream);
 /* *p_dev += delta (device-resident sampler step counter, so a captured graph can be replayed) */
 int tf_add_int(int* p_dev, int delta, void* stream);
+/* elementwise activation, op: 0 sigmoid, 1 silu/swish, 2 gelu (tanh approx), 3 quick_gelu; fp32 or fp16.
+ * Replaces: Tensor.sigmoid/silu/gelu/quick_gelu static methods  tinyfusers/storage/tensor.py:64-86. */
+int tf_unary(const void* x, void* out, long long n, int op, int is_f32, void* stream);
+/* fp32 NHWC (pixel stride >= C) -> fp32 NCHW: returns the UNet's eps in the reference layout */
+int tf_nhwc_f32_to_nchw_f32(const float* x, int x_pixel_stride, float* out, int NI, int C, int HW, void* stream);
+/* DDIM eta=0 update on its own; a_t / a_prev are device scalars; pred_x0 may be NULL.
+ * Replaces: StableDiffusion.get_x_prev_and_pred_x0  tinyfusers/variants/sd.py:14-25. */
+int tf_ddim_step_f32(const float* x, const float* e_t, const float* a_t_dev, const float* a_prev_dev, float* x_prev,
+                     float* pred_x0, long long n, void* stream);
 
 #ifdef __cplusplus
 }

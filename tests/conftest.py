@@ -1,0 +1,50 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| — the per-op metric of BASELINE.json's north_star (<= 1e-2 in fp16)."""
+    import torch
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import ref_ops
+    return ref_ops
+
+
+@pytest.fixture(scope="session")
+def unet_sd(oracle):
+    """Seeded synthetic UNet weights with the reference's checkpoint keys (fp32, CPU)."""
+    return oracle.make_unet_state_dict(seed=1234)
+
+
+@pytest.fixture(scope="session")
+def sd_model(unet_sd):
+    """tinyfusers_b200 StableDiffusion with the synthetic weights injected through update_state."""
+    import contextlib
+    import io
+    import torch
+    from tinyfusers_b200.storage.state import update_state
+    from tinyfusers_b200.variants.sd import StableDiffusion
+    assert torch.cuda.is_available()
+    m = StableDiffusion()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        update_state(m, unet_sd)
+    skipped = [l for l in buf.getvalue().splitlines() if l.startswith("skipped")]
+    # the only keys the synthetic dict does not carry are the bias-less attention projections
+    assert all(k.endswith((".to_q.bias", ".to_k.bias", ".to_v.bias")) for k in skipped), skipped[:5]
+    return m

@@ -1,0 +1,104 @@
+"""Block-level parity (the reference has no such tests — SURVEY.md §4): ResBlock, CrossAttention with the
+head-major reshape quirk, BasicTransformerBlock with the LayerNorm stride quirk, SpatialTransformer,
+Up/Downsample, all against the oracle on seeded weights/inputs. fp16 tolerance 1e-2 (max-normalised)."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _load(obj, sd, prefix):
+    from tinyfusers_b200.storage.state import update_state
+    with contextlib.redirect_stdout(io.StringIO()):
+        update_state(obj, sd, prefix)
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(320, 320, 16), (320, 640, 16), (2560, 1280, 8), (960, 640, 12)])
+def test_resblock(oracle, cin, cout, hw):
+    from tinyfusers_b200.vision.resnet import ResBlock
+    sd = {}
+    oracle.add_res_block(sd, "rb", cin, cout, seed=11)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, cin, hw, hw, generator=g)
+    emb = torch.randn(1, 1280, generator=g)
+    rb = ResBlock(cin, 1280, cout)
+    _load(rb, sd, "rb")
+    out = rb(x.cuda(), emb.cuda())
+    assert rel_err(out, oracle.res_block(sd, "rb", x, emb)) < TOL
+
+
+@pytest.mark.parametrize("quirks", [True, False])
+@pytest.mark.parametrize("c,d,T,B", [(320, 40, 256, 2), (640, 80, 64, 2), (1280, 160, 64, 1)])
+def test_cross_attention_self_and_cross(oracle, quirks, c, d, T, B):
+    import tinyfusers_b200
+    from tinyfusers_b200.attention.attention import CrossAttention
+    sd = {}
+    oracle.add_spatial_transformer(sd, "st", c, 768, seed=12)
+    p = "st.transformer_blocks.0"
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, T, c, generator=g)
+    ctx = torch.randn(B, 77, 768, generator=g)
+    tinyfusers_b200.set_quirks(quirks)
+    try:
+        a1 = CrossAttention(c, c, 8, d)
+        _load(a1, sd, p + ".attn1")
+        assert rel_err(a1(x.cuda()), oracle.cross_attention(sd, p + ".attn1", x, None, 8, d, quirks)) < TOL
+        a2 = CrossAttention(c, 768, 8, d)
+        _load(a2, sd, p + ".attn2")
+        assert rel_err(a2(x.cuda(), ctx.cuda()), oracle.cross_attention(sd, p + ".attn2", x, ctx, 8, d, quirks)) < TOL
+    finally:
+        tinyfusers_b200.set_quirks(True)
+
+
+@pytest.mark.parametrize("quirks", [True, False])
+def test_basic_transformer_block(oracle, quirks):
+    import tinyfusers_b200
+    from tinyfusers_b200.attention.attention import BasicTransformerBlock
+    c, d = 320, 40
+    sd = {}
+    oracle.add_spatial_transformer(sd, "st", c, 768, seed=13)
+    p = "st.transformer_blocks.0"
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 256, c, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    tinyfusers_b200.set_quirks(quirks)
+    try:
+        blk = BasicTransformerBlock(c, 768, 8, d)
+        _load(blk, sd, p)
+        out = blk(x.cuda(), ctx.cuda())
+    finally:
+        tinyfusers_b200.set_quirks(True)
+    assert rel_err(out, oracle.basic_transformer_block(sd, p, x, ctx, 8, d, quirks)) < TOL
+
+
+@pytest.mark.parametrize("c,d,hw", [(320, 40, 16), (640, 80, 8), (1280, 160, 8)])
+def test_spatial_transformer(oracle, c, d, hw):
+    from tinyfusers_b200.attention.attention import SpatialTransformer
+    sd = {}
+    oracle.add_spatial_transformer(sd, "st", c, 768, seed=14)
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, c, hw, hw, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    st = SpatialTransformer(c, 768, 8, d)
+    _load(st, sd, "st")
+    assert rel_err(st(x.cuda(), ctx.cuda()), oracle.spatial_transformer(sd, "st", x, ctx, 8, d, True)) < TOL
+
+
+def test_up_down_sample(oracle):
+    from tinyfusers_b200.vision.unet import Downsample, Upsample
+    sd = {}
+    oracle._add_conv(sd, "u.conv", 640, 640, 3, 15)
+    oracle._add_conv(sd, "d.op", 320, 320, 3, 15)
+    g = torch.Generator().manual_seed(15)
+    xu, xd = torch.randn(2, 640, 8, 8, generator=g), torch.randn(2, 320, 16, 16, generator=g)
+    up, down = Upsample(640), Downsample(320)
+    _load(up, sd, "u")
+    _load(down, sd, "d")
+    assert rel_err(up(xu.cuda()), oracle.upsample(sd, "u", xu)) < TOL
+    assert rel_err(down(xd.cuda()), oracle.downsample(sd, "d", xd)) < TOL

@@ -1,0 +1,176 @@
+"""SpatialTransformer / BasicTransformerBlock / CrossAttention with the reference's signatures
+(reference: tinyfusers/attention/attention.py:26-76).
+
+Fast path per transformer block (reference: 9 cuBLAS GEMMs, 2 materialised-score SDPAs, 3 cuDNN
+LayerNorm graph builds, ~25 elementwise launches):
+  LN -> [QK proj GEMM, V^T proj GEMM (operands swapped so V arrives transposed)] -> fused attention
+     -> out-proj GEMM (+bias +residual, in place)           x2 (self, cross)
+  LN -> GEGLU GEMM (fused gate) -> out GEMM (+bias +residual, in place)
+In NHWC the reference's (B,C,HW)->(B,HW,C) transposes (attention.py:70,73) are free reinterpretations,
+and the 1x1 proj_in / proj_out convs are plain GEMMs with bias / residual epilogues."""
+import torch
+
+from .. import get_quirks, packing
+from ..ff.group_norm import GroupNorm
+from ..ff.layer_norm import LayerNorm
+from ..ff.linear import Linear
+from ..ff.nn import FeedForward
+from ..runtime import (F16, F32, Act, act_to_nchw, nchw_to_act, new_act_tensor, require_cuda, standalone_context,
+                       tokens_to_act)
+from ..vision.conv2d import Conv2d
+from .sdpa import scaled_dot_product_attention  # noqa: F401  (re-exported like the reference)
+
+
+def _pad16(d):
+    return (d + 15) // 16 * 16
+
+
+class CrossAttention:
+    def __init__(self, query_dim, context_dim, n_heads, d_head):
+        self.to_q = Linear(query_dim, n_heads * d_head, bias=False)
+        self.to_k = Linear(context_dim, n_heads * d_head, bias=False)
+        self.to_v = Linear(context_dim, n_heads * d_head, bias=False)
+        self.num_heads = n_heads
+        self.head_size = d_head
+        self.to_out = [Linear(n_heads * d_head, query_dim)]
+
+    def _packed(self):
+        nh, d = self.num_heads, self.head_size
+        dp = _pad16(d)
+        def build():
+            wq = packing.head_pad(self.to_q.weight, nh, d, dp)
+            wk = packing.head_pad(self.to_k.weight, nh, d, dp)
+            wv = packing.head_pad(self.to_v.weight, nh, d, dp)
+            wqk = torch.cat((wq, wk), dim=0).contiguous() if wq.shape[1] == wk.shape[1] else None
+            return wq, wk, wv, wqk
+        return packing.cached(self, "attn", (self.to_q.weight, self.to_k.weight, self.to_v.weight), build)
+
+    def __call__(self, x, context=None):
+        require_cuda(x, "x")
+        ctx = standalone_context(get_quirks())
+        ctx.arena.reset()
+        xa = tokens_to_act(x)
+        ca = None if context is None else _pad_context(ctx, context)
+        B, T, C = x.shape
+        out = torch.zeros((B, T, self.to_out[0].weight.shape[0]), dtype=F16, device=x.device)
+        self._run(ctx, xa.ptr, B, T, C, out.data_ptr(), context=ca, residual=False)
+        return out.to(F32)
+
+    # h_ptr (B*T, C) is updated:  h <- to_out(attention(...)) (+ h if residual);  xn_ptr = normalised input
+    def _run(self, ctx, xn_ptr, B, T, C, h_ptr, context=None, residual=True):
+        nh, d = self.num_heads, self.head_size
+        dp = _pad16(d)
+        wq, wk, wv, wqk = self._packed()
+        mark = ctx.arena.mark()
+        M = B * T
+        if context is None:
+            # self-attention: one GEMM for [Q | K], one swapped GEMM for V^T
+            qk_ptr = ctx.arena.alloc(2 * M * 2 * nh * dp)
+            ctx.gemm(xn_ptr, C, M, C, wqk.data_ptr(), 2 * nh * dp, qk_ptr, 2 * nh * dp)
+            if T % 8 != 0:
+                raise RuntimeError(f"tinyfusers_b200 self-attention: {T} tokens per image; the B200 kernel needs a "
+                                   "multiple of 8 (latent height*width at every UNet level)")
+            vt_ptr = ctx.arena.alloc(2 * nh * dp * M)
+            ctx.gemm(wv.data_ptr(), C, nh * dp, C, xn_ptr, M, vt_ptr, M, ldw=C)
+            q_ptr, ldq, k_ptr, ldk = qk_ptr, 2 * nh * dp, qk_ptr + 2 * nh * dp, 2 * nh * dp
+            Tk, Tkp, ldvt = T, T, M
+        else:
+            Tkp, Cc = context.h, context.c
+            Tk = context.valid if context.valid is not None else context.h
+            Mc = B * Tkp
+            q_ptr = ctx.arena.alloc(2 * M * nh * dp)
+            ctx.gemm(xn_ptr, C, M, C, wq.data_ptr(), nh * dp, q_ptr, nh * dp)
+            k_ptr = ctx.arena.alloc(2 * Mc * nh * dp)
+            ctx.gemm(context.ptr, context.stride, Mc, Cc, wk.data_ptr(), nh * dp, k_ptr, nh * dp)
+            vt_ptr = ctx.arena.alloc(2 * nh * dp * Mc)
+            ctx.gemm(wv.data_ptr(), Cc, nh * dp, Cc, context.ptr, Mc, vt_ptr, Mc, ldw=context.stride)
+            ldq = ldk = nh * dp
+            ldvt = Mc
+        a_ptr = ctx.arena.alloc(2 * M * nh * d)
+        ctx.attention(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, a_ptr, B, nh, T, Tk, Tkp, d, dp, head_major=ctx.quirks)
+        wo, bo = self.to_out[0]._packed()
+        ctx.gemm(a_ptr, nh * d, M, nh * d, wo.data_ptr(), wo.shape[0], h_ptr, wo.shape[0],
+                 bias=bo.data_ptr() if bo is not None else None, residual_ptr=h_ptr if residual else None,
+                 ldr=wo.shape[0])
+        ctx.arena.release(mark)
+
+
+class BasicTransformerBlock:
+    def __init__(self, dim, context_dim, n_heads, d_head):
+        self.attn1 = CrossAttention(dim, dim, n_heads, d_head)
+        self.ff = FeedForward(dim)
+        self.attn2 = CrossAttention(dim, context_dim, n_heads, d_head)
+        self.norm1 = LayerNorm(dim)
+        self.norm2 = LayerNorm(dim)
+        self.norm3 = LayerNorm(dim)
+
+    def __call__(self, x, context=None):
+        require_cuda(x, "x")
+        ctx = standalone_context(get_quirks())
+        ctx.arena.reset()
+        B, T, C = x.shape
+        h = x.to(F16).contiguous().clone()
+        ca = None
+        if context is not None:
+            ca = _pad_context(ctx, context)
+        self._run(ctx, h.data_ptr(), B, T, C, ca)
+        return h.to(F32)
+
+    # h (B*T, C) fp16 updated in place
+    def _run(self, ctx, h_ptr, B, T, C, context):
+        mark = ctx.arena.mark()
+        xn = ctx.arena.alloc(2 * B * T * C)
+        self.norm1._run(ctx, h_ptr, xn, B, T, C)
+        self.attn1._run(ctx, xn, B, T, C, h_ptr)
+        self.norm2._run(ctx, h_ptr, xn, B, T, C)
+        self.attn2._run(ctx, xn, B, T, C, h_ptr, context=context)
+        self.norm3._run(ctx, h_ptr, xn, B, T, C)
+        self.ff._run(ctx, xn, h_ptr, B * T, C)
+        ctx.arena.release(mark)
+
+
+def _pad_context(ctx, context):
+    """(B,Tk,C) fp32/fp16 prompt embeddings -> zero-padded fp16 Act (B, Tk_pad, C) with Tk remembered."""
+    from ..native.b200.ops import b200
+    from ..runtime import stream_ptr
+    B, Tk, Cc = context.shape
+    Tkp = (Tk + 7) // 8 * 8
+    buf = torch.empty((B, Tkp, Cc), dtype=F16, device=context.device)
+    c32 = context.to(F32).contiguous()
+    st = b200.tf_pad_tokens_f32_to_f16(c32.data_ptr(), buf.data_ptr(), B, Tk, Tkp, Cc, stream_ptr())
+    b200.check(st, "tf_pad_tokens_f32_to_f16")
+    act = Act(buf.data_ptr(), B, Tkp, 1, Cc, Cc, keep=(buf, c32))
+    act.valid = Tk
+    return act
+
+
+class SpatialTransformer:
+    def __init__(self, channels, context_dim, n_heads, d_head):
+        self.norm = GroupNorm(32, channels)
+        assert channels == n_heads * d_head
+        self.proj_in = Conv2d(channels, n_heads * d_head, kernel_size=[1, 1])
+        self.transformer_blocks = [BasicTransformerBlock(channels, context_dim, n_heads, d_head)]
+        self.proj_out = Conv2d(n_heads * d_head, channels, kernel_size=[1, 1])
+
+    def __call__(self, x, context=None):
+        require_cuda(x, "x")
+        ctx = standalone_context(get_quirks())
+        ctx.arena.reset()
+        a = nchw_to_act(x, c_pad_to=8)
+        ca = _pad_context(ctx, context) if context is not None else None
+        out = new_act_tensor(a.n, a.h, a.w, a.c, device=x.device)
+        self._run(ctx, a, ca, out)
+        return act_to_nchw(out, x.shape[1])
+
+    def _run(self, ctx, x, context, out):
+        mark = ctx.arena.mark()
+        B, T, C = x.n, x.h * x.w, x.c
+        hn = ctx.new_act(x.n, x.h, x.w, C)
+        self.norm._run(ctx, x, hn, silu=False)
+        h = ctx.new_act(x.n, x.h, x.w, C)
+        self.proj_in._run(ctx, hn, h)
+        for block in self.transformer_blocks:
+            block._run(ctx, h.ptr, B, T, C, context)
+        self.proj_out._run(ctx, h, out, residual=x)
+        ctx.arena.release(mark)
+        return out

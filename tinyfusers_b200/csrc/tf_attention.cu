@@ -290,8 +290,10 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
   TF_CHECK_ARG(B > 0 && NH > 0 && Tq > 0 && Tk > 0 && Tk_pad >= Tk, "tf_attention_f16: bad dims");
   TF_CHECK_ARG(dp % 16 == 0 && dp >= 16 && dp <= 256 && d <= dp && d % 8 == 0,
                "tf_attention_f16: head dim d=%d (padded %d) unsupported: need d %% 8 == 0, dp %% 16 == 0, dp <= 256", d, dp);
+  // Tk_pad % 8: batch b's V^T columns start at b*Tk_pad and a TMA box must start on a 16-byte boundary
   TF_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && Tk_pad % 8 == 0,
-               "tf_attention_f16: leading dims / Tk_pad must be multiples of 8");
+               "tf_attention_f16: leading dims and Tk_pad must be multiples of 8 (ldq=%d ldk=%d ldvt=%d Tk_pad=%d)", ldq,
+               ldk, ldvt, Tk_pad);
   TF_CHECK_ARG(ldq >= NH * dp && ldk >= NH * dp && ldvt >= B * Tk_pad, "tf_attention_f16: leading dims too small");
   TF_CHECK_ARG(out_stride_t % 8 == 0 && out_stride_h % 8 == 0 && out_stride_b % 8 == 0,
                "tf_attention_f16: output strides must be multiples of 8");
@@ -299,8 +301,7 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
                    ((uintptr_t)out & 15) == 0,
                "tf_attention_f16: pointers must be 16-byte aligned");
 
-  int BN = (dp <= 96) ? 64 : 64;
-  if (2 * 128 + dp <= 512 && dp <= 64 && false) BN = 128;
+  int BN = 64;  // 64-key blocks: two CTAs per SM (TMEM 2*64 + dp <= 256 columns) hide softmax latency
   if (g_force_attn_bn == 64 || g_force_attn_bn == 128) BN = g_force_attn_bn;
   if (BN == 128 && 2 * 128 + dp > 512) BN = 64;
 

@@ -56,7 +56,7 @@ __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restric
 template <int CIN>
 __global__ void conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                         const float* __restrict__ bias, __half* __restrict__ out, int NI, int H,
-                                        int W_, int Cout, int out_stride) {
+                                        int W_, int Cout, int out_stride, int x_images) {
   extern __shared__ float ws[];  // [Cout][CIN*9]
   for (int i = threadIdx.x; i < Cout * CIN * 9; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -67,7 +67,7 @@ __global__ void conv3x3_smallcin_kernel(const float* __restrict__ x, const float
     const long pix = idx / groups;
     const int xo = (int)(pix % W_);
     const int yo = (int)((pix / W_) % H);
-    const int n = (int)(pix / ((long)W_ * H));
+    const int n = (int)(pix / ((long)W_ * H)) % x_images;
     float in[CIN * 9];
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
@@ -223,15 +223,16 @@ extern "C" int tf_gemv_f16w(const float* x, const void* W, const float* bias, co
   return TF_OK;
 }
 
-extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, const float* w, const float* bias, void* out, int NI,
-                                           int Cin, int H, int W, int Cout, int out_pixel_stride, void* stream) {
-  TF_CHECK_ARG(x && w && out, "tf_conv3x3_smallcin_f32nchw: null pointer");
+extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out,
+                                           int NI, int Cin, int H, int W, int Cout, int out_pixel_stride,
+                                           void* stream) {
+  TF_CHECK_ARG(x && w && out && x_images > 0, "tf_conv3x3_smallcin_f32nchw: null pointer");
   TF_CHECK_ARG(Cin == 4, "tf_conv3x3_smallcin_f32nchw: only Cin == 4 is built (got %d)", Cin);
   TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && Cout * Cin * 9 * 4 <= 48 * 1024,
                "tf_conv3x3_smallcin_f32nchw: bad Cout %d", Cout);
   const long total = (long)NI * H * W * (Cout / 8);
   conv3x3_smallcin_kernel<4><<<ew_blocks(total, 256), 256, Cout * Cin * 9 * sizeof(float), (cudaStream_t)stream>>>(
-      x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride);
+      x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride, x_images);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
@@ -307,6 +308,89 @@ extern "C" int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride,
 extern "C" int tf_add_int(int* p_dev, int delta, void* stream) {
   TF_CHECK_ARG(p_dev, "tf_add_int: null pointer");
   add_int_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p_dev, delta);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone activations (reference: Tensor.sigmoid/silu/gelu/quick_gelu, storage/tensor.py:64-86).
+// On the UNet fast path these are fused into GroupNorm / GEMM epilogues; this entry point keeps the
+// drop-in static methods working on their own.
+// ------------------------------------------------------------------------------------------------
+namespace {
+template <typename T>
+__global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ out, long n, int op) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = (float)x[i];
+    float r;
+    switch (op) {
+      case 0: r = 1.0f / (1.0f + __expf(-v)); break;
+      case 1: r = tf::silu_f(v); break;
+      case 2: r = tf::gelu_tanh_f(v); break;
+      default: r = v / (1.0f + __expf(-1.702f * v)); break;
+    }
+    out[i] = (T)r;
+  }
+}
+}  // namespace
+
+extern "C" int tf_unary(const void* x, void* out, long long n, int op, int is_f32, void* stream) {
+  TF_CHECK_ARG(x && out && n >= 0 && op >= 0 && op <= 3, "tf_unary: bad arguments");
+  if (n == 0) return TF_OK;
+  const int threads = 256;
+  long b = (n + threads - 1) / threads;
+  const long cap = (long)tf_num_sms() * 8;
+  const int blocks = (int)(b < cap ? b : cap);
+  if (is_f32)
+    unary_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)out, n, op);
+  else
+    unary_kernel<__half><<<blocks, threads, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, n, op);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+namespace {
+__global__ void nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ x, int x_stride, float* __restrict__ out, int NI,
+                                            int C, int HW) {
+  const long total = (long)NI * C * HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int n = (int)(i / ((long)HW * C));
+    out[i] = x[((size_t)n * HW + p) * x_stride + c];
+  }
+}
+// DDIM (eta = 0) update on its own (reference: variants/sd.py:14-25)
+__global__ void ddim_kernel(const float* __restrict__ x, const float* __restrict__ e_t, const float* __restrict__ a_t_p,
+                            const float* __restrict__ a_prev_p, float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                            long n) {
+  const float a_t = *a_t_p, a_prev = *a_prev_p;
+  const float s1 = sqrtf(1.f - a_t), is = 1.f / sqrtf(a_t), sp = sqrtf(a_prev), dp = sqrtf(1.f - a_prev);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float e = e_t[i];
+    const float p0 = (x[i] - s1 * e) * is;
+    x_prev[i] = sp * p0 + dp * e;
+    if (pred_x0) pred_x0[i] = p0;
+  }
+}
+}  // namespace
+
+extern "C" int tf_nhwc_f32_to_nchw_f32(const float* x, int x_pixel_stride, float* out, int NI, int C, int HW,
+                                       void* stream) {
+  TF_CHECK_ARG(x && out && NI > 0 && C > 0 && HW > 0 && x_pixel_stride >= C, "tf_nhwc_f32_to_nchw_f32: bad arguments");
+  const long total = (long)NI * C * HW;
+  nhwc_f32_to_nchw_f32_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, out, NI, C, HW);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_ddim_step_f32(const float* x, const float* e_t, const float* a_t_dev, const float* a_prev_dev,
+                                float* x_prev, float* pred_x0, long long n, void* stream) {
+  TF_CHECK_ARG(x && e_t && a_t_dev && a_prev_dev && x_prev && n > 0, "tf_ddim_step_f32: bad arguments");
+  ddim_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, e_t, a_t_dev, a_prev_dev, x_prev, pred_x0, n);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;

@@ -3,7 +3,7 @@
 // GroupNorm (reference: tinyfusers/ff/group_norm.py:3-21, followed by Tensor.silu in
 // vision/resnet.py:8-10,17-19 and vision/unet.py:45-47): the reference runs >= 8 CuPy elementwise /
 // reduction launches and >= 6 full read+write passes. Here: one statistics pass (128-bit loads, register
-// partials per channel, shared-memory group bins, one global atomic per group per block) and one
+// partials per channel, fixed-order block and cross-block reduction - no atomics, bit-reproducible) and one
 // apply pass that fuses normalise + affine + SiLU and writes the fp16 NHWC tensor the following
 // implicit-GEMM conv reads through TMA. Both passes accept a channel slice of a wider tensor
 // (pixel stride != C), which is how the UNet's skip concatenation is consumed without a copy.
@@ -18,19 +18,19 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: stats[(n*G + g)*2 + {0,1}] += {sum, sumsq}
-// block = nvec * k threads (nvec = Cs/8), so a thread always sees the same 8 channels.
+// GroupNorm statistics, deterministic (no atomics): each block reduces its pixel chunk to per-group
+// {sum, sumsq} in a fixed order and writes partial[(chunk*NI + n)*G + g]; gn_finalize_kernel folds the
+// chunks in order and emits {mean, rstd}. block = nvec * k threads (nvec = Cs/8): a thread always sees
+// the same 8 channels.
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, int x_stride, int c_off,
-                                int cpg, int G, int pix_per_block, float* __restrict__ stats) {
-  __shared__ float bins[2 * 64];
+                                int cpg, int G, int pix_per_block, float2* __restrict__ partial) {
+  extern __shared__ float gsm[];  // [npl][Cs] sums, [npl][Cs] squares, then [Cs] x 2 channel totals
   const int n = blockIdx.y;
   const int nvec = Cs >> 3;
   const int v = threadIdx.x % nvec;
   const int pl = threadIdx.x / nvec;
   const int npl = blockDim.x / nvec;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) bins[i] = 0.f;
-  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   float s[8], q[8];
@@ -47,35 +47,57 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, in
       s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
     }
   }
-  // fold the 8 channels into their (at most two) groups before touching shared memory
-  const int c0 = c_off + v * 8;
-  const int g0 = c0 / cpg;
-  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-  bool two = false;
+  float* ps = gsm;
+  float* pq = gsm + npl * Cs;
+  float* cs = gsm + 2 * npl * Cs;
+  float* cq = cs + Cs;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
-    if (g == g0) { s0 += s[j]; q0 += q[j]; }
-    else if (g == g0 + 1) { s1 += s[j]; q1 += q[j]; two = true; }
-    else { atomicAdd(&bins[2 * g], s[j]); atomicAdd(&bins[2 * g + 1], q[j]); }  // cpg < 4: rare path
+    ps[pl * Cs + v * 8 + j] = s[j];
+    pq[pl * Cs + v * 8 + j] = q[j];
   }
-  atomicAdd(&bins[2 * g0], s0);
-  atomicAdd(&bins[2 * g0 + 1], q0);
-  if (two) { atomicAdd(&bins[2 * (g0 + 1)], s1); atomicAdd(&bins[2 * (g0 + 1) + 1], q1); }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
-    const float val = bins[i];
-    if (val != 0.f) atomicAdd(&stats[(size_t)n * 2 * G + i], val);
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < npl; ++l) { a += ps[l * Cs + c]; b += pq[l * Cs + c]; }
+    cs[c] = a;
+    cq[c] = b;
   }
+  __syncthreads();
+  // groups covered (fully or partly) by this channel slice
+  const int g_lo = c_off / cpg, g_hi = (c_off + Cs - 1) / cpg;
+  for (int g = g_lo + threadIdx.x; g <= g_hi; g += blockDim.x) {
+    const int c_begin = max(g * cpg, c_off) - c_off, c_end = min((g + 1) * cpg, c_off + Cs) - c_off;
+    float a = 0.f, b = 0.f;
+    for (int c = c_begin; c < c_end; ++c) { a += cs[c]; b += cq[c]; }
+    partial[((size_t)blockIdx.x * gridDim.y + n) * G + g] = make_float2(a, b);
+  }
+}
+
+// stats[(n*G+g)] = {mean, rstd}; one block per image, one thread per group; up to two slice partial arrays
+__global__ void gn_finalize_kernel(const float2* __restrict__ partial_a, const float2* __restrict__ partial_b, int chunks,
+                                   int NI, int G, int split_group_lo, int split_group_hi, float inv_count, float eps,
+                                   float2* __restrict__ stats) {
+  const int n = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  float a = 0.f, b = 0.f;
+  // slice A covers groups [0, split_group_hi], slice B (optional) covers [split_group_lo, G)
+  if (g <= split_group_hi)
+    for (int c = 0; c < chunks; ++c) { float2 t = partial_a[((size_t)c * NI + n) * G + g]; a += t.x; b += t.y; }
+  if (partial_b && g >= split_group_lo)
+    for (int c = 0; c < chunks; ++c) { float2 t = partial_b[((size_t)c * NI + n) * G + g]; a += t.x; b += t.y; }
+  const float mean = a * inv_count;
+  const float var = fmaxf(b * inv_count - mean * mean, 0.f);
+  stats[(size_t)n * G + g] = make_float2(mean, rsqrtf(var + eps));
 }
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm apply: out = act((x - mean) * rstd * gamma + beta), act = SiLU or identity
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, int x_stride, int c_off,
-                                int cpg, int G, int pix_per_block, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                float inv_count, int silu, __half* __restrict__ out, int out_stride) {
+                                int cpg, int G, int pix_per_block, const float2* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                __half* __restrict__ out, int out_stride) {
   const int n = blockIdx.y;
   const int nvec = Cs >> 3;
   const int v = threadIdx.x % nvec;
@@ -86,16 +108,11 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, in
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    const int g = c / cpg;
-    const float sum = stats[((size_t)n * G + g) * 2];
-    const float sq = stats[((size_t)n * G + g) * 2 + 1];
-    const float mean = sum * inv_count;
-    const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
+    const float2 mr = stats[(size_t)n * G + c / cpg];
     const float ga = gamma ? gamma[c] : 1.f;
     const float be = beta ? beta[c] : 0.f;
-    a[j] = rstd * ga;
-    b[j] = be - mean * rstd * ga;
+    a[j] = mr.y * ga;
+    b[j] = be - mr.x * mr.y * ga;
   }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
@@ -120,6 +137,8 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, in
 static int gn_block_threads(int Cs) {
   const int nvec = Cs / 8;
   int k = 512 / nvec;
+  const int k_smem = (40 * 1024 / 4 - 2 * Cs) / (2 * Cs);  // statistics kernel shared-memory budget
+  if (k > k_smem) k = k_smem;
   if (k < 1) k = 1;
   return nvec * k;
 }
@@ -253,6 +272,12 @@ __global__ void ln_il_generic_kernel(const __half* __restrict__ x, __half* __res
 
 }  // namespace
 
+extern "C" size_t tf_groupnorm_workspace_bytes(int NI, int groups) {
+  // 2 slices x chunks x NI x G float2 partials + NI x G float2 {mean, rstd}; chunks <= 2*SMs + 1
+  const size_t chunks = (size_t)2 * tf_num_sms() + 1;
+  return sizeof(float2) * ((size_t)2 * chunks * NI * groups + (size_t)NI * groups);
+}
+
 extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void* x2,
                                      int x2_pixel_stride, int Cx2, void* out, int out_pixel_stride, int NI,
                                      int HW, int groups, const float* gamma, const float* beta, float eps,
@@ -267,7 +292,6 @@ extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, 
                "tf_groupnorm_nhwc_f16: channels and strides must be multiples of 8");
   TF_CHECK_ARG(Cx / 8 <= 1024 && (!x2 || Cx2 / 8 <= 1024), "tf_groupnorm_nhwc_f16: too many channels");
   const int cpg = C / groups;
-  TF_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * NI, stream));
   const int sms = tf_num_sms();
   int chunks = (2 * sms + NI - 1) / NI;
   if (chunks > HW) chunks = HW;
@@ -278,18 +302,28 @@ extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, 
   const __half* xs[2] = {reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x2)};
   const int cs[2] = {Cx, Cx2}, st[2] = {x_pixel_stride, x2_pixel_stride}, off[2] = {0, Cx};
   const int nsrc = x2 ? 2 : 1;
+  float2* partial[2];
+  partial[0] = reinterpret_cast<float2*>(stats_ws);
+  partial[1] = partial[0] + (size_t)chunks * NI * groups;
+  float2* stats = partial[1] + (size_t)chunks * NI * groups;
   for (int i = 0; i < nsrc; ++i) {
-    gn_stats_kernel<<<grid, gn_block_threads(cs[i]), 0, stream>>>(xs[i], HW, cs[i], st[i], off[i], cpg, groups,
-                                                                ppb, stats_ws);
+    const int threads = gn_block_threads(cs[i]);
+    const int npl = threads / (cs[i] / 8);
+    const size_t smem = sizeof(float) * ((size_t)2 * npl * cs[i] + 2 * cs[i]);
+    TF_CHECK_ARG(smem <= 48 * 1024, "tf_groupnorm_nhwc_f16: channel slice of %d too wide for the statistics kernel", cs[i]);
+    gn_stats_kernel<<<grid, threads, smem, stream>>>(xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, partial[i]);
     TF_LAUNCH_CHECK();
   }
+  gn_finalize_kernel<<<NI, 64, 0, stream>>>(partial[0], nsrc == 2 ? partial[1] : nullptr, chunks, NI, groups,
+                                            nsrc == 2 ? Cx / cpg : 0, (Cx - 1) / cpg, inv_count, eps, stats);
+  TF_LAUNCH_CHECK();
   for (int i = 0; i < nsrc; ++i) {
     gn_apply_kernel<<<grid, gn_block_threads(cs[i]), 0, stream>>>(
-        xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, stats_ws, gamma, beta, eps, inv_count, apply_silu,
+        xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, stats, gamma, beta, apply_silu,
         reinterpret_cast<__half*>(out), out_pixel_stride);
     TF_LAUNCH_CHECK();
   }
-  tf_launch_count_add(2 * nsrc);
+  tf_launch_count_add(2 * nsrc + 1);
   return TF_OK;
 }
 

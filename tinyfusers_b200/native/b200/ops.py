@@ -33,19 +33,23 @@ _SIGNATURES = {
                                    _P, _P, c_int, c_int, _P, c_size_t, _P]),
     "tf_groupnorm_nhwc_f16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P,
                                       c_float, c_int, _P, _P]),
+    "tf_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tf_layernorm_f16": (c_int, [_P, _P, c_int, c_int, _P, _P, c_float, c_int, _P]),
     "tf_attention_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "tf_attention_set_tuning": (c_int, [c_int]),
     "tf_timestep_embedding_f32": (c_int, [_P, _P, c_int, c_float, _P, _P]),
     "tf_gemv_f16w": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    "tf_conv3x3_smallcin_f32nchw": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "tf_conv3x3_smallcin_f32nchw": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "tf_upsample_nearest2x_nhwc_f16": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "tf_nchw_to_nhwc_f16": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_pad_tokens_f32_to_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_cfg_ddim_step_f32": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
     "tf_add_int": (c_int, [_P, c_int, _P]),
+    "tf_unary": (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
+    "tf_nhwc_f32_to_nchw_f32": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
+    "tf_ddim_step_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_longlong, _P]),
 }
 
 

@@ -1,0 +1,88 @@
+"""One-time weight re-layout (load time, not on the step path): the reference's fp32 OIHW / (out,in)
+tensors -> the fp16 layouts the kernels read through TMA. Pure data movement done with torch as the
+container library."""
+import torch
+
+F16, F32 = torch.float16, torch.float32
+
+
+def _key(*tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+
+
+def cached(obj, name, tensors, builder):
+    """Cache `builder()` on `obj` until any of `tensors` is replaced or modified in place."""
+    key = _key(*tensors)
+    slot = "_pk_" + name
+    hit = obj.__dict__.get(slot)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = builder()
+    obj.__dict__[slot] = (key, val)
+    return val
+
+
+def f32(t):
+    return None if t is None else t.detach().to(F32).contiguous()
+
+
+def linear_weight(w, k_pad_to=8):
+    w = w.detach()
+    out_f, in_f = w.shape
+    kp = (in_f + k_pad_to - 1) // k_pad_to * k_pad_to
+    if kp == in_f:
+        return w.to(F16).contiguous()
+    p = torch.zeros((out_f, kp), dtype=F16, device=w.device)
+    p[:, :in_f] = w
+    return p
+
+
+def pad_rows(w, mult):
+    n = w.shape[0]
+    np_ = (n + mult - 1) // mult * mult
+    if np_ == n:
+        return w
+    p = torch.zeros((np_,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+    p[:n] = w
+    return p
+
+
+def conv3x3_weight(w, cin_pad_to=64, cout_pad_to=8):
+    """OIHW fp32 -> (Cout_pad, 3, 3, Cin_pad) fp16 (OHWI), zero padded."""
+    w = w.detach()
+    O, I, kh, kw = w.shape
+    Ip = (I + cin_pad_to - 1) // cin_pad_to * cin_pad_to
+    Op = (O + cout_pad_to - 1) // cout_pad_to * cout_pad_to
+    p = torch.zeros((Op, kh, kw, Ip), dtype=F16, device=w.device)
+    p[:O, :, :, :I] = w.permute(0, 2, 3, 1)
+    return p.contiguous()
+
+
+def conv1x1_weight(w, cout_pad_to=8):
+    w = w.detach()
+    O, I = w.shape[0], w.shape[1]
+    return pad_rows(linear_weight(w.reshape(O, I)), cout_pad_to)
+
+
+def head_pad(w, n_heads, d, dp):
+    """(n_heads*d, in) -> (n_heads*dp, in): each head's rows zero-padded to dp (attention K-dim multiple of 16)."""
+    w = w.detach()
+    if dp == d:
+        return w.to(F16).contiguous()
+    inf = w.shape[1]
+    p = torch.zeros((n_heads, dp, inf), dtype=F16, device=w.device)
+    p[:, :d] = w.reshape(n_heads, d, inf)
+    return p.reshape(n_heads * dp, inf).contiguous()
+
+
+def geglu_pack(w, b):
+    """GEGLU proj (2*dout, in): rows [0,dout) = value, [dout,2dout) = gate (ff/nn.py:11 split) ->
+    blocks of 32 rows = 16 value rows followed by their 16 gate rows (TF_EPI_GEGLU layout)."""
+    w = w.detach()
+    dout = w.shape[0] // 2
+    assert dout % 16 == 0
+    idx = torch.arange(dout, device=w.device).reshape(-1, 16)
+    perm = torch.cat((idx, idx + dout), dim=1).reshape(-1)
+    wp = w[perm].to(F16).contiguous()
+    bp = None if b is None else b.detach()[perm].to(F32).contiguous()
+    return wp, bp

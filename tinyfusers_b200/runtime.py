@@ -1,0 +1,231 @@
+"""Host-side runtime shared by the drop-in module classes.
+
+PyTorch is used here strictly as a container: `torch.empty` for device memory, `data_ptr()` for raw
+pointers, `torch.cuda.current_stream()` for the stream, `torch.cuda.CUDAGraph` for capture. All
+arithmetic happens in libtinyfusers_b200.so (tinyfusers_b200/native/b200/ops.py).
+
+Activations on the fast path are fp16 NHWC views (`Act`) carved from a stack arena whose addresses are
+a deterministic function of the call sequence — so a whole UNet step can be captured into a CUDA graph
+and replayed.
+"""
+import math
+import os
+
+import torch
+
+from .native.b200.ops import b200
+
+F16 = torch.float16
+F32 = torch.float32
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA torch tensor (tinyfusers_b200 has no CPU path)")
+
+
+class Act:
+    """A (n, h, w, c) fp16 NHWC activation view: pixel p of image i starts at ptr + 2*((i*h*w + p)*stride)."""
+
+    __slots__ = ("ptr", "n", "h", "w", "c", "stride", "keep", "valid")
+
+    def __init__(self, ptr, n, h, w, c, stride=None, keep=None):
+        self.ptr, self.n, self.h, self.w, self.c = ptr, n, h, w, c
+        self.stride = c if stride is None else stride
+        self.keep = keep  # torch tensor owning the memory when not arena-backed
+        self.valid = None  # for padded token sequences: number of real tokens per batch (<= h)
+
+    @property
+    def rows(self):
+        return self.n * self.h * self.w
+
+    def channels(self, c0, c1):
+        return Act(self.ptr + 2 * c0, self.n, self.h, self.w, c1 - c0, self.stride, self.keep)
+
+    def as_tokens(self):
+        return Act(self.ptr, self.n, self.h * self.w, 1, self.c, self.stride, self.keep)
+
+    def reshaped(self, n, h, w):
+        assert n * h * w == self.rows
+        return Act(self.ptr, n, h, w, self.c, self.stride, self.keep)
+
+
+class Arena:
+    """Stack allocator over one device buffer. `dry` mode only measures the peak."""
+
+    def __init__(self):
+        self.buf = None
+        self.base = 0
+        self.top = 0
+        self.peak = 0
+        self.capacity = 0
+        self.dry = False
+
+    def reserve(self, nbytes, device):
+        if self.buf is None or self.capacity < nbytes:
+            self.buf = torch.empty(_align(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self.capacity = self.buf.numel()
+            self.base = self.buf.data_ptr()
+            assert self.base % 1024 == 0
+
+    def reset(self):
+        self.top = 0
+
+    def mark(self):
+        return self.top
+
+    def release(self, mark):
+        self.top = mark
+
+    def alloc(self, nbytes):
+        off = self.top
+        self.top = off + _align(nbytes, 1024)
+        self.peak = max(self.peak, self.top)
+        if self.dry:
+            return 1024 + off  # fake but well-aligned address; nothing is launched in dry mode
+        if self.top > self.capacity:
+            raise RuntimeError(f"tinyfusers_b200 arena exhausted ({self.top} > {self.capacity} bytes)")
+        return self.base + off
+
+
+class Context:
+    """Execution context handed down the module tree on the fast path."""
+
+    def __init__(self, device, quirks=True):
+        self.device = torch.device(device)
+        self.quirks = quirks
+        self.arena = Arena()
+        self.ws_bytes = 192 << 20
+        self.ws = None
+        self.dry = False
+        # per-forward values set by the UNet
+        self.emb_bias = None       # dict: id(ResBlock) -> device pointer of its (conv bias + emb) fp32 vector
+        self.context = None        # Act view of the zero-padded fp16 prompt context (B, Tpad, 768)
+        self.context_tokens = 0
+
+    def ensure_workspaces(self):
+        if self.ws is None:
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+
+    # -- allocation ------------------------------------------------------------------------------
+    def new_act(self, n, h, w, c, stride=None):
+        stride = c if stride is None else stride
+        ptr = self.arena.alloc(2 * n * h * w * stride)
+        return Act(ptr, n, h, w, c, stride)
+
+    def new_f32(self, numel):
+        return self.arena.alloc(4 * numel)
+
+    # -- kernel wrappers (each is one C-ABI call) ---------------------------------------------------
+    def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None):
+        if self.dry:
+            return
+        st = b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
+                              residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
+        b200.check(st, "tf_gemm_f16")
+
+    def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0):
+        if self.dry:
+            return
+        st = b200.tf_conv2d_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr, out.stride, bias,
+                                     residual.ptr if residual is not None else None,
+                                     residual.stride if residual is not None else 0, flags, self.ws.data_ptr(),
+                                     self.ws_bytes, stream_ptr())
+        b200.check(st, "tf_conv2d_nhwc_f16")
+
+    def groupnorm(self, x, out, gamma, beta, eps, silu, groups=32):
+        mark = self.arena.mark()
+        stats = self.arena.alloc(b200.tf_groupnorm_workspace_bytes(x.n, groups))   # partials + {mean, rstd}
+        self.arena.release(mark)                          # stream order keeps the reuse safe
+        if self.dry:
+            return
+        st = b200.tf_groupnorm_nhwc_f16(x.ptr, x.stride, x.c, None, 0, 0, out.ptr, out.stride, x.n, x.h * x.w, groups,
+                                        gamma, beta, eps, 1 if silu else 0, stats, stream_ptr())
+        b200.check(st, "tf_groupnorm_nhwc_f16")
+
+    def layernorm(self, x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave):
+        if self.dry:
+            return
+        st = b200.tf_layernorm_f16(x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave, stream_ptr())
+        b200.check(st, "tf_layernorm_f16")
+
+    def attention(self, q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, B, NH, Tq, Tk, Tk_pad, d, dp, head_major):
+        if self.dry:
+            return
+        if head_major:   # reference reshape quirk: (B,NH,T,d) memory read back as (B,T,NH*d)
+            osb, osh, ost = NH * Tq * d, Tq * d, d
+        else:
+            osb, osh, ost = Tq * NH * d, d, NH * d
+        st = b200.tf_attention_f16(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, osb, osh, ost, B, NH, Tq, Tk, Tk_pad,
+                                   d, dp, 1.0 / math.sqrt(d), stream_ptr())
+        b200.check(st, "tf_attention_f16")
+
+    def upsample2x(self, x, out):
+        if self.dry:
+            return
+        st = b200.tf_upsample_nearest2x_nhwc_f16(x.ptr, x.stride, out.ptr, out.stride, x.n, x.h, x.w, x.c, stream_ptr())
+        b200.check(st, "tf_upsample_nearest2x_nhwc_f16")
+
+
+# ------------------------------------------------------------------------------------------------
+# layout edges for the stand-alone (reference-signature) operator wrappers
+# ------------------------------------------------------------------------------------------------
+
+def nchw_to_act(x, c_pad_to=8):
+    """(N,C,H,W) fp32/fp16 CUDA tensor -> fp16 NHWC Act (channels zero-padded to a multiple of c_pad_to)."""
+    require_cuda(x, "x")
+    if x.dtype not in (F16, F32):
+        x = x.to(F32)
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    Cp = _align(C, c_pad_to)
+    buf = torch.zeros((N, H, W, Cp), dtype=F16, device=x.device) if Cp != C else torch.empty((N, H, W, Cp), dtype=F16, device=x.device)
+    st = b200.tf_nchw_to_nhwc_f16(x.data_ptr(), 1 if x.dtype == F32 else 0, buf.data_ptr(), N, C, H * W, Cp, stream_ptr())
+    b200.check(st, "tf_nchw_to_nhwc_f16")
+    return Act(buf.data_ptr(), N, H, W, Cp, Cp, keep=(buf, x))
+
+
+def act_to_nchw(a, C=None, dtype=F32):
+    C = a.c if C is None else C
+    out = torch.empty((a.n, C, a.h, a.w), dtype=dtype, device="cuda")
+    st = b200.tf_nhwc_to_nchw(a.ptr, a.stride, out.data_ptr(), 1 if dtype == F32 else 0, a.n, C, a.h * a.w, stream_ptr())
+    b200.check(st, "tf_nhwc_to_nchw")
+    return out
+
+
+def tokens_to_act(x):
+    """(B,T,C) CUDA tensor -> fp16 Act (n=B, h=T, w=1)."""
+    require_cuda(x, "x")
+    xh = x.to(F16).contiguous()  # dtype cast only; container-level
+    B, T, C = xh.shape
+    return Act(xh.data_ptr(), B, T, 1, C, C, keep=xh)
+
+
+def new_act_tensor(n, h, w, c, device="cuda"):
+    buf = torch.empty((n, h, w, c), dtype=F16, device=device)
+    return Act(buf.data_ptr(), n, h, w, c, c, keep=buf)
+
+
+_standalone_ctx = {}
+
+
+def standalone_context(quirks=True):
+    """Context for per-op calls outside a UNet forward (allocates from torch, not the arena)."""
+    dev = torch.cuda.current_device()
+    key = (dev, quirks)
+    ctx = _standalone_ctx.get(key)
+    if ctx is None:
+        b200.init(dev)
+        ctx = Context(torch.device("cuda", dev), quirks)
+        ctx.ensure_workspaces()
+        ctx.arena.reserve(int(os.environ.get("TINYFUSERS_B200_SCRATCH_MB", "1024")) << 20, ctx.device)
+        _standalone_ctx[key] = ctx
+    return ctx

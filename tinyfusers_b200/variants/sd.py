@@ -1,0 +1,186 @@
+"""StableDiffusion sampler object with the reference's signatures (reference: tinyfusers/variants/sd.py:7-65).
+
+One sampler step = UNet forward at batch 2B ([uncond ; cond]) + CFG combine + DDIM (eta = 0) update.
+The reference round-trips the latent batch through host memory and synchronises the device twice per
+step (sd.py:34-41); here the step is a fixed launch sequence on one stream — conv_in forms the CFG batch
+by index, one fused kernel does CFG + DDIM in place — and `sample()` captures it once into a CUDA graph
+and replays it with a device-resident step counter selecting (t, a_t, a_prev) from device tables.
+
+The VAE and the CLIP text encoder are outside the denoising hot path (SURVEY.md §8f "next" rows) and are
+not built yet: `decode` and `cond_stage_model` raise loudly instead of falling back to anything.
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from .. import get_quirks
+from ..native.b200.ops import b200
+from ..runtime import F32, require_cuda, stream_ptr
+from ..vision.unet import UNetModel
+
+
+class _NotBuilt:
+    def __init__(self, what):
+        self._what = what
+
+    def __getattr__(self, name):
+        raise RuntimeError(f"tinyfusers_b200: {self._what} is not built yet (outside the UNet hot path, SURVEY.md §8f)")
+
+    def __call__(self, *a, **k):
+        raise RuntimeError(f"tinyfusers_b200: {self._what} is not built yet (outside the UNet hot path, SURVEY.md §8f)")
+
+
+def get_alphas_cumprod(beta_start=0.00085, beta_end=0.0120, n_training_steps=1000):
+    """fp32 scaled-linear beta schedule, computed once on the host (reference: sd.py:61-65)."""
+    betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, n_training_steps, dtype=np.float32) ** 2
+    alphas = (1.0 - betas).astype(np.float32)
+    ac = torch.from_numpy(np.cumprod(alphas, axis=0).astype(np.float32))
+    return ac.cuda() if torch.cuda.is_available() else ac
+
+
+class StableDiffusion:
+    def __init__(self):
+        self.alphas_cumprod = get_alphas_cumprod()
+        self.model = namedtuple("DiffusionModel", ["diffusion_model"])(diffusion_model=UNetModel())
+        self.first_stage_model = _NotBuilt("AutoencoderKL (VAE)")
+        self.cond_stage_model = _NotBuilt("CLIPTextTransformer")
+        self._samplers = {}
+
+    # ---- reference API -------------------------------------------------------------------------
+    def get_x_prev_and_pred_x0(self, x, e_t, a_t, a_prev):
+        require_cuda(x, "x")
+        x32, e32 = x.to(F32).contiguous(), e_t.to(F32).contiguous()
+        a_t = torch.as_tensor(a_t, dtype=F32, device=x.device).reshape(-1)[:1].contiguous()
+        a_prev = torch.as_tensor(a_prev, dtype=F32, device=x.device).reshape(-1)[:1].contiguous()
+        x_prev, pred_x0 = torch.empty_like(x32), torch.empty_like(x32)
+        st = b200.tf_ddim_step_f32(x32.data_ptr(), e32.data_ptr(), a_t.data_ptr(), a_prev.data_ptr(), x_prev.data_ptr(),
+                                   pred_x0.data_ptr(), x32.numel(), stream_ptr())
+        b200.check(st, "tf_ddim_step_f32")
+        return x_prev, pred_x0
+
+    def get_model_output(self, unconditional_context, context, latent, timestep, unconditional_guidance_scale):
+        s = self._sampler(latent.shape, context.shape[1])
+        s.load(unconditional_context, context, latent)
+        s.set_scalars(timestep, 1.0, 1.0, unconditional_guidance_scale)
+        s.enqueue_step(update_latent=False)
+        return s.e_t.clone()
+
+    def decode(self, x):
+        return self.first_stage_model.decoder(x)
+
+    def __call__(self, unconditional_context, context, latent, timestep, alphas, alphas_prev, guidance):
+        s = self._sampler(latent.shape, context.shape[1])
+        s.load(unconditional_context, context, latent)
+        s.set_scalars(timestep, alphas, alphas_prev, guidance)
+        s.enqueue_step(update_latent=True)
+        return s.latent.clone()
+
+    # ---- whole sampler loop on device (graph-captured steps) -----------------------------------------
+    def sample(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance, use_graph=True):
+        """Runs len(timesteps) DDIM steps, last-to-first like example/sd1.py:68-73, and returns the final latent."""
+        s = self._sampler(latent.shape, context.shape[1])
+        s.load(unconditional_context, context, latent)
+        s.set_tables(timesteps, alphas, alphas_prev, guidance)
+        s.run(len(timesteps), use_graph=use_graph)
+        return s.latent.clone()
+
+    def _sampler(self, latent_shape, ctx_tokens):
+        B, C, H, W = latent_shape
+        key = (torch.cuda.current_device(), B, H, W, ctx_tokens, get_quirks())
+        s = self._samplers.get(key)
+        if s is None:
+            s = SamplerEngine(self.model.diffusion_model, B, H, W, ctx_tokens)
+            self._samplers[key] = s
+        return s
+
+
+def _scalar(v):
+    if isinstance(v, torch.Tensor):
+        return float(v.reshape(-1)[0].item())
+    return float(np.asarray(v).reshape(-1)[0])
+
+
+class SamplerEngine:
+    """Device-resident sampler state for B images: latent, [uncond ; cond] context, schedule tables, step index."""
+
+    def __init__(self, unet, B, H, W, ctx_tokens):
+        self.B, self.H, self.W = B, H, W
+        self.unet_engine = unet.engine(2 * B, H, W, n_src=B, ctx_tokens=ctx_tokens)
+        e = self.unet_engine
+        dev = e.latent.device
+        self.latent = e.latent                      # (B,4,H,W) fp32, updated in place every step
+        self.context = e.context                    # (2B,T,768) fp32: [uncond ; cond]  (sd.py:32)
+        self.e_t = torch.zeros((B, 4, H, W), dtype=F32, device=dev)
+        self.max_steps = 1024
+        self.t_tab = torch.zeros(self.max_steps, dtype=F32, device=dev)
+        self.a_tab = torch.ones(self.max_steps, dtype=F32, device=dev)
+        self.ap_tab = torch.ones(self.max_steps, dtype=F32, device=dev)
+        self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.guidance = 7.5
+        self.graph = None
+        self.graph_guidance = None
+
+    def load(self, unconditional_context, context, latent):
+        require_cuda(latent, "latent")
+        self.latent.copy_(latent.reshape(self.latent.shape))
+        B = self.B
+        self.context[:B].copy_(unconditional_context.reshape(B, -1, 768))
+        self.context[B:].copy_(context.reshape(B, -1, 768))
+
+    def set_scalars(self, timestep, a_t, a_prev, guidance):
+        self.t_tab[0] = _scalar(timestep)
+        self.a_tab[0] = _scalar(a_t)
+        self.ap_tab[0] = _scalar(a_prev)
+        self.idx.zero_()
+        self.guidance = _scalar(guidance)
+
+    def set_tables(self, timesteps, alphas, alphas_prev, guidance):
+        n = len(timesteps)
+        assert n <= self.max_steps
+        self.t_tab[:n].copy_(torch.as_tensor(np.asarray(timesteps, dtype=np.float32)))
+        self.a_tab[:n].copy_(torch.as_tensor(alphas, dtype=F32).reshape(-1)[:n])
+        self.ap_tab[:n].copy_(torch.as_tensor(alphas_prev, dtype=F32).reshape(-1)[:n])
+        self.idx.fill_(n - 1)   # the loop runs from the last timestep to the first
+        self.guidance = _scalar(guidance)
+
+    def enqueue_step(self, update_latent=True, advance=False):
+        """One step on the current stream: UNet(2B) -> CFG + DDIM (in place) [-> idx -= 1]."""
+        e = self.unet_engine
+        e._enqueue(t_ptr=self.t_tab.data_ptr(), idx_ptr=self.idx.data_ptr())
+        out = self.latent if update_latent else self.e_t   # when only e_t is wanted the latent is left untouched
+        scratch = self.latent.data_ptr() if update_latent else self._scratch().data_ptr()
+        st = b200.tf_cfg_ddim_step_f32(e.eps.data_ptr(), 16, self.latent.data_ptr(), scratch, self.e_t.data_ptr(),
+                                       self.a_tab.data_ptr(), self.ap_tab.data_ptr(), self.idx.data_ptr(),
+                                       float(self.guidance), self.B, 4, self.H * self.W, stream_ptr())
+        b200.check(st, "tf_cfg_ddim_step_f32")
+        if advance:
+            b200.check(b200.tf_add_int(self.idx.data_ptr(), -1, stream_ptr()), "tf_add_int")
+
+    def _scratch(self):
+        if not hasattr(self, "_scratch_buf"):
+            self._scratch_buf = torch.empty_like(self.latent)
+        return self._scratch_buf
+
+    def capture(self):
+        """Capture one step (with index advance) into a CUDA graph; replays need no host work."""
+        self.enqueue_step(advance=False)  # warm-up outside capture (lazy attribute setup, weight packing)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.enqueue_step(update_latent=True, advance=True)
+        self.graph, self.graph_guidance = g, self.guidance
+        return g
+
+    def run(self, n_steps, use_graph=True):
+        if use_graph:
+            if self.graph is None or self.graph_guidance != self.guidance:
+                lat, idx = self.latent.clone(), self.idx.clone()
+                self.capture()
+                self.latent.copy_(lat)
+                self.idx.copy_(idx)
+            for _ in range(n_steps):
+                self.graph.replay()
+        else:
+            for _ in range(n_steps):
+                self.enqueue_step(update_latent=True, advance=True)
