@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — SD1.5 512x512 UNet denoising throughput on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one CFG denoising step of one image: UNet forward at effective batch 2 ([uncond ; cond],
+64x64x4 latent, 77-token context) + CFG combine + DDIM update — the unit of the reference's sampler loop
+(example/sd1.py:68-73 -> variants/sd.py:56-59). Weights are seeded synthetic (no checkpoint offline),
+data is synthetic N(0,1) latents / prompt embeddings.
+
+  value      steps/s of the whole job with inputs resident in HBM: K CUDA-graph replays of the captured step,
+             CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e        the same metric through the public drop-in call `StableDiffusion.__call__` with HOST buffers:
+             every step copies latent + both prompt embeddings from pinned host memory to the device and
+             reads the updated latent back.
+  roofline   dominant kernel = tf_gemm_kernel (all convs + linears): algorithmic FLOPs of those launches in one
+             step / their measured duration (a graph holding ONLY those launches, timed live with CUDA
+             events), against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json.
+  cpu_baseline  the oracle (CPU restatement of the reference) timed on this box's host cores.
+
+N > 1 (torchrun, one rank per GPU): independent UNet replicas, one image trajectory each (weak scaling);
+NCCL is used once, to all-gather the final latents (inside the timed region).
+
+--impl reference: the reference's arithmetic on the host CPUs (oracle port; the reference itself needs
+CuPy + cuDNN python bindings that do not install offline and has no CPU path), bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sd15_512x512_unet_cfg_denoising_steps_per_sec"
+UNIT = "steps/s"
+WORKLOAD = ("SD1.5 full UNet single denoising step, 512^2 (64x64x4 latent), batch 1 with CFG "
+            "(effective batch 2), fp16, seeded random-init weights")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"tflops_sustained": d.get("bf16_tflops_sustained"), "tflops_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for line in fh:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        # "under load": the upper half of the samples (idle samples before/after the region are lower)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_oracle_step(R, sd, hw, repeats, threads):
+    import torch
+    torch.set_num_threads(threads)
+    lat, unc, ctx = R.make_inputs(1, hw)
+    ts, alphas, alphas_prev = R.sampler_schedule(50)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            R.sampler_step(sd, unc, ctx, lat, [ts[25]], alphas[[25]], alphas_prev[[25]], 7.5)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_flops_ratio(R, hw):
+    """algorithmic FLOPs(64x64 step) / FLOPs(hw x hw step), batch 2 — scales a bounded CPU sample to the metric."""
+    return R.unet_step_flops(2, 64, 64) / R.unet_step_flops(2, hw, hw)
+
+
+def run_reference(args, rank, world):
+    """The reference's arithmetic on the host CPUs (oracle port), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_ops as R
+    cores = os.cpu_count() or 1
+    sd = R.make_unet_state_dict(seed=1234)
+    # calibrate on a 16x16 latent, then pick the largest latent whose (K+W) steps fit the time budget
+    t16 = min(time_oracle_step(R, sd, 16, 2, cores))
+    budget = 150.0
+    n = args.steps + args.warmup
+    hw = 16
+    for cand, cost in ((64, 20.0), (32, 4.2)):  # rough CPU cost relative to 16x16
+        if t16 * cost * n <= budget:
+            hw = cand
+            break
+    ratio = cpu_flops_ratio(R, hw)
+    time_oracle_step(R, sd, hw, args.warmup, cores)
+    times = time_oracle_step(R, sd, hw, args.steps, cores)
+    total = sum(times)
+    steps_per_s = args.steps / total / ratio
+    sample = (f"{args.steps} oracle CFG steps at {hw}x{hw} latent (batch 2) on {cores} host threads, scaled to the "
+              f"64x64 step by the algorithmic FLOP ratio {ratio:.2f}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / steps_per_s, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_path": "oracle port on host CPU (reference has no CPU path and "
+                   "does not install offline: needs CuPy + cudnn-frontend + tinygrad)"},
+        "cpu_baseline": {"value": steps_per_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": steps_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from oracle import ref_ops as R  # weight/input generators + the cpu_baseline leg only (never on the GPU path)
+    from tinyfusers_b200.flops import unet_flops
+    from tinyfusers_b200.native.b200.ops import b200
+    from tinyfusers_b200.storage.state import update_state
+    from tinyfusers_b200.variants.sd import StableDiffusion
+    import contextlib
+    import io
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b200.init(local_rank)
+
+    # ---- model + synthetic weights (identical on every rank; independent replicas) ----
+    sd = R.make_unet_state_dict(seed=1234)
+    model = StableDiffusion()
+    with contextlib.redirect_stdout(io.StringIO()):
+        update_state(model, sd)
+    lat, unc, ctx = R.make_inputs(1, 64, seed=42 + rank, ctx_seed=43 + rank)
+    ts, alphas, alphas_prev = R.sampler_schedule(50)
+    guidance = 7.5
+    flops = unet_flops(model.model.diffusion_model, 2, 64, 64)
+
+    sampler = model._sampler(lat.shape, 77)
+    sampler.load(unc.to(dev), ctx.to(dev), lat.to(dev))
+    sampler.set_tables(ts, alphas, alphas_prev, guidance)
+
+    # launches per step (counted on an eager step; a graph replay re-issues exactly these)
+    b200.tf_launch_count_reset()
+    sampler.enqueue_step(update_latent=True, advance=False)
+    torch.cuda.synchronize()
+    launches_per_step = int(b200.tf_launch_count())
+    sampler._warm = True
+    graph = sampler._graph(True)
+
+    def reset_state():
+        sampler.load(unc.to(dev), ctx.to(dev), lat.to(dev))
+        sampler.set_tables(ts, alphas, alphas_prev, guidance)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: W warm-up + K timed graph replays ----
+    reset_state()
+    for _ in range(args.warmup):
+        graph.replay()
+    reset_state()
+    gathered = [torch.empty_like(sampler.latent) for _ in range(world)] if world > 1 else None
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        if i > 0 and i % 50 == 0:
+            sampler.idx.fill_(49)  # a new 50-step trajectory; keeps the schedule index in range
+        graph.replay()
+    if world > 1:
+        dist.all_gather(gathered, sampler.latent)  # final latents over NVLink (the only collective on the path)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_rec = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    finite = bool(torch.isfinite(sampler.latent).all().item())
+    value = world * args.steps / (ms / 1000.0)
+
+    # ---- end to end through the public call with host buffers ----
+    pin = lambda t: t.clone().pin_memory()
+    h_lat, h_unc, h_ctx = pin(lat), pin(unc), pin(ctx)
+    h_out = torch.empty_like(h_lat).pin_memory()
+    h2d = h_lat.numel() * 4 + h_unc.numel() * 4 + h_ctx.numel() * 4 + 3 * 4
+    d2h = h_out.numel() * 4
+    n_e2e = max(3, min(args.steps, 50))
+
+    def e2e_step(i):
+        x = model(h_unc.to(dev, non_blocking=True), h_ctx.to(dev, non_blocking=True), h_lat.to(dev, non_blocking=True),
+                  torch.tensor([ts[i % 50]]), alphas[[i % 50]], alphas_prev[[i % 50]], torch.tensor([guidance]))
+        h_out.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller owns the result only after the read-back
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(n_e2e):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)  # device-timed, host gaps between steps included by construction
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * n_e2e / (e2e_ms / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel-class device time inside the step (graphs holding only that class), rank 0 ----
+    peaks = measured_peaks()
+    eng = sampler.unet_engine
+
+    def class_ms(kinds, reps=10):
+        eng.ctx.only = set(kinds)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sampler.enqueue_step(update_latent=True, advance=False)
+        finally:
+            eng.ctx.only = None
+        for _ in range(3):
+            g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reset_state()
+    breakdown = {k: class_ms([k]) for k in ("gemm", "attention", "norm", "misc")}
+    gemm_tflops = flops["gemm"] / (breakdown["gemm"] / 1000.0) / 1e12
+    attn_tflops = flops["attention"] / (breakdown["attention"] / 1000.0) / 1e12
+    peak = peaks["tflops_sustained"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_step")
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
+    cores = os.cpu_count() or 1
+    t16 = min(time_oracle_step(R, sd, 16, 2, cores))
+    hw = 64 if t16 * 20.0 <= 30.0 else (32 if t16 * 4.2 <= 30.0 else 16)
+    tcpu = min(time_oracle_step(R, sd, hw, 1, cores))
+    ratio = cpu_flops_ratio(R, hw)
+    cpu_value = 1.0 / (tcpu * ratio)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (independent replicas, final-latent all_gather)",
+                   "images_per_s_50step": value / 50.0,
+                   "l2": "working set > L2: 1.72 GB of fp16 weights streamed every step (126 MB L2)",
+                   "semantics": "reference-literal (LayerNorm stride + head-merge quirks on)",
+                   "cuda_graph": True, "output_finite": finite},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "api": "StableDiffusion.__call__ (pinned host tensors in, host latent out)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "clocks": clock_rec,
+        "roofline": {"bound": "tensor", "kernel": "tf_gemm_kernel (convs + linears, all launches of one step)",
+                     "achieved": gemm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": gemm_tflops / peak,
+                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                     "traffic": traffic, "algorithmic_flops_per_step": flops["gemm"], "ms_per_step": breakdown["gemm"]},
+        "breakdown_ms": breakdown,
+        "attention": {"achieved": attn_tflops, "unit": "TFLOP/s", "algorithmic_flops_per_step": flops["attention"]},
+        "whole_step_tflops": flops["total"] / (ms / args.steps / 1000.0) / 1e12,
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"one oracle CFG step at {hw}x{hw} latent (batch 2), scaled to 64x64 by the "
+                                   f"algorithmic FLOP ratio {ratio:.2f}"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,8 @@ int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel
 
 /* test / tuning hook: force the N tile and split-K factor of the next GEMM/conv calls (0 = auto) */
 int tf_gemm_set_tuning(int force_bn, int force_splits);
+/* debug hook: per-CTA clock64 stamps of the next GEMM/conv launches ([grid][8] int64; NULL = off) */
+int tf_gemm_set_timeline(long long* dev_buf);
 
 /* ---- normalisation -------------------------------------------------------------------------------- */
 /* GroupNorm (+ optional SiLU), NHWC fp16 -> NHWC fp16, statistics fp32, biased variance.

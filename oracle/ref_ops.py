@@ -450,3 +450,46 @@ def make_inputs(batch=1, latent_hw=64, seed=42, ctx_seed=43):
     ctx = torch.from_numpy(g2.standard_normal((batch, 77, CONTEXT_DIM), dtype=np.float32))
     unc = torch.from_numpy(g2.standard_normal((batch, 77, CONTEXT_DIM), dtype=np.float32))
     return latent, unc, ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic FLOPs from the structure tables (used to scale a bounded CPU sample to the 64x64 step)
+# ------------------------------------------------------------------------------------------------
+
+
+def unet_step_flops(n, H, W, ctx_tokens=77):
+    """2*M*N*K per conv/linear + 4*B*NH*Tq*Tk*d per attention for one UNet forward at batch n."""
+    total = 2.0 * (320 * 1280 + 1280 * 1280)
+    h, w = H, W
+
+    def layer_flops(layer, h, w):
+        kind = layer[0]
+        if kind == "conv":
+            return 2.0 * n * h * w * layer[2] * layer[1] * 9
+        if kind == "res":
+            cin, cout = layer[1], layer[2]
+            f = 2.0 * n * h * w * cout * (cin + cout) * 9 + 2.0 * EMB_CHANNELS * cout
+            return f + (2.0 * n * h * w * cin * cout if cin != cout else 0.0)
+        if kind == "st":
+            c, nh, d = layer[1], layer[2], layer[3]
+            T = h * w
+            f = 2 * 2.0 * n * T * c * c                                   # proj_in / proj_out
+            f += 4 * 2.0 * n * T * c * c + 4.0 * n * nh * T * T * d       # self-attention
+            f += 2 * 2.0 * n * T * c * c + 2 * 2.0 * n * ctx_tokens * CONTEXT_DIM * c + 4.0 * n * nh * T * ctx_tokens * d
+            f += 2.0 * n * T * c * 8 * c + 2.0 * n * T * 4 * c * c        # GEGLU feed-forward
+            return f
+        return 0.0
+
+    for group in (UNET_INPUT_BLOCKS, [UNET_MIDDLE_BLOCK], UNET_OUTPUT_BLOCKS):
+        for block in group:
+            for layer in block:
+                if layer[0] == "down":
+                    h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+                    total += 2.0 * n * h * w * layer[1] * layer[1] * 9
+                elif layer[0] == "up":
+                    h, w = 2 * h, 2 * w
+                    total += 2.0 * n * h * w * layer[1] * layer[1] * 9
+                else:
+                    total += layer_flops(layer, h, w)
+    total += 2.0 * n * h * w * 4 * 320 * 9
+    return total

@@ -90,8 +90,8 @@ int tf_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const voi
     tf_set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old or no GPU)");
     return TF_ERR_DEVICE;
   }
-  cuuint64_t d[5], s[4];
-  cuuint32_t b[5], e[5];
+  cuuint64_t d[5] = {0, 0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+  cuuint32_t b[5] = {0, 0, 0, 0, 0}, e[5] = {0, 0, 0, 0, 0};
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides[i]; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,

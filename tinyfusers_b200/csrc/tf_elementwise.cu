@@ -52,38 +52,43 @@ __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restric
 
 // 3x3 pad-1 conv with a tiny input-channel count, fp32 NCHW in -> fp16 NHWC out.
 // reference: UNetModel.input_blocks[0] = Conv2d(4, 320, 3x3, pad 1) (vision/unet.py:13).
-// w: fp32 (Cout, Cin, 3, 3) exactly as the reference stores it. Each thread: one pixel x 8 output channels.
+// w: fp32 (Cout, Cin, 3, 3) exactly as the reference stores it. Block = 32 pixels x 4 warps: lane = pixel (its
+// 36 inputs stay in registers), warp = a quarter of the output-channel groups, so weight reads are
+// warp-uniform shared-memory broadcasts.
 template <int CIN>
-__global__ void conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                        const float* __restrict__ bias, __half* __restrict__ out, int NI, int H,
-                                        int W_, int Cout, int out_stride, int x_images) {
-  extern __shared__ float ws[];  // [Cout][CIN*9]
+__global__ void __launch_bounds__(128)
+conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                        __half* __restrict__ out, int NI, int H, int W_, int Cout, int out_stride, int x_images) {
+  extern __shared__ float ws[];  // [Cout][CIN*9] then [Cout] bias
+  float* bs = ws + Cout * CIN * 9;
   for (int i = threadIdx.x; i < Cout * CIN * 9; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long npix = (long)NI * H * W_;
+  const long pix = (long)blockIdx.x * 32 + lane;
+  if (pix >= npix) return;
+  const int xo = (int)(pix % W_);
+  const int yo = (int)((pix / W_) % H);
+  const int n = (int)(pix / ((long)W_ * H)) % x_images;
+  float in[CIN * 9];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int yy = yo + r - 1, xx = xo + s - 1;
+        in[c * 9 + r * 3 + s] =
+            (yy >= 0 && yy < H && xx >= 0 && xx < W_) ? x[(((size_t)n * CIN + c) * H + yy) * W_ + xx] : 0.f;
+      }
   const int groups = Cout / 8;
-  const long total = (long)NI * H * W_ * groups;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const long pix = idx / groups;
-    const int xo = (int)(pix % W_);
-    const int yo = (int)((pix / W_) % H);
-    const int n = (int)(pix / ((long)W_ * H)) % x_images;
-    float in[CIN * 9];
-#pragma unroll
-    for (int c = 0; c < CIN; ++c)
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int yy = yo + r - 1, xx = xo + s - 1;
-          in[c * 9 + r * 3 + s] =
-              (yy >= 0 && yy < H && xx >= 0 && xx < W_) ? x[(((size_t)n * CIN + c) * H + yy) * W_ + xx] : 0.f;
-        }
+  for (int g = warp; g < groups; g += 4) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float* wr = ws + (g * 8 + j) * CIN * 9;
-      float a = bias ? bias[g * 8 + j] : 0.f;
+      float a = bs[g * 8 + j];
 #pragma unroll
       for (int k = 0; k < CIN * 9; ++k) a += in[k] * wr[k];
       acc[j] = a;
@@ -228,10 +233,16 @@ extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const f
                                            void* stream) {
   TF_CHECK_ARG(x && w && out && x_images > 0, "tf_conv3x3_smallcin_f32nchw: null pointer");
   TF_CHECK_ARG(Cin == 4, "tf_conv3x3_smallcin_f32nchw: only Cin == 4 is built (got %d)", Cin);
-  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && Cout * Cin * 9 * 4 <= 48 * 1024,
+  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && (Cout * Cin * 9 + Cout) * 4 <= 64 * 1024,
                "tf_conv3x3_smallcin_f32nchw: bad Cout %d", Cout);
-  const long total = (long)NI * H * W * (Cout / 8);
-  conv3x3_smallcin_kernel<4><<<ew_blocks(total, 256), 256, Cout * Cin * 9 * sizeof(float), (cudaStream_t)stream>>>(
+  const long npix = (long)NI * H * W;
+  const size_t smem = (size_t)(Cout * Cin * 9 + Cout) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    TF_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  conv3x3_smallcin_kernel<4><<<(unsigned)((npix + 31) / 32), 128, smem, (cudaStream_t)stream>>>(
       x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride, x_images);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);

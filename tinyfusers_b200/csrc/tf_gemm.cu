@@ -25,6 +25,12 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccStride = 256;  // columns between the two accumulator buffers
+// epilogue staging: each epilogue warp owns one 32-row x 32-column block (<= 128 B per row, fp32 worst case)
+// written thread-per-row in the TMA swizzle pattern and shipped with one TMA store per chunk, plus a copy of
+// the tile's bias slice.
+constexpr int kEpiStageBytes = 32 * 128;                    // per warp, 1024-aligned (swizzle atom)
+constexpr int kEpiBiasFloats = 256;
+constexpr int kEpiBytes = 4 * kEpiStageBytes + 4 * kEpiBiasFloats * 4;  // 20480
 
 struct ConvGeom {
   int H, W, NI;          // OUTPUT height/width, images
@@ -34,6 +40,7 @@ struct ConvGeom {
   int cscale;            // input coord = output coord * cscale + tap offset (1: stride 1, 2: stride 2)
   int pad;               // 1 for 3x3
   int ksize;             // 3
+  int sbw, sbh;          // store box of one epilogue warp (32 tile rows): sbw x sbh x (32/(sbw*sbh)) pixels
 };
 
 struct GemmParams {
@@ -48,6 +55,7 @@ struct GemmParams {
   int ldr;
   float* partial;
   int flags;
+  long long* timeline;  // optional debug: per-CTA clock stamps [grid][8] (tf_gemm_set_timeline)
 };
 
 // tile-local row (0..127) -> global output row (pixel index for conv), or -1 if padding
@@ -70,48 +78,11 @@ __device__ __forceinline__ int tile_row_to_m(const GemmParams& p, int mt, int r)
   return (n * g.H + y) * g.W + x;
 }
 
-__device__ __forceinline__ void store8(const GemmParams& p, int m, int n, const float* f) {
-  if (p.flags & TF_EPI_OUT_F32) {
-    float* o = reinterpret_cast<float*>(p.out) + (size_t)m * p.ldc + n;
-    reinterpret_cast<float4*>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
-    reinterpret_cast<float4*>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
-  } else {
-    tf::Pack16 pk;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) pk.h2[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-    __half* o = reinterpret_cast<__half*>(p.out) + (size_t)m * p.ldc + n;
-    *reinterpret_cast<uint4*>(o) = pk.v;
-  }
-}
-
-// bias + residual + store for 8 consecutive columns starting at n (n % 8 == 0)
-__device__ __forceinline__ void epilogue8(const GemmParams& p, int m, int n, const uint32_t* acc) {
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[j]);
-  if (p.bias) {
-    float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-    float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-  }
-  if (p.residual) {
-    tf::Pack16 r;
-    r.v = *reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ldr + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 t = __half22float2(r.h2[j]);
-      f[2 * j] += t.x;
-      f[2 * j + 1] += t.y;
-    }
-  }
-  store8(p, m, n, f);
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  const long long t_entry = clock64();
   const uint32_t raw_u32 = tf::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -120,7 +91,8 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_stage_bytes = (uint32_t)p.bn * 128u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + p.stages * A_STAGE_BYTES;
-  const uint32_t bar_base = smem_b + p.stages * b_stage_bytes;
+  const uint32_t epi_base = smem_b + p.stages * b_stage_bytes;
+  const uint32_t bar_base = epi_base + kEpiBytes;
   const int S = p.stages;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
@@ -133,6 +105,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tf::tma_prefetch_desc(&tmA);
     tf::tma_prefetch_desc(&tmB);
+    tf::tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
@@ -155,6 +128,9 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 16 : nullptr;
+#define TF_STAMP(i) do { if (tl) tl[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) { TF_STAMP(0); if (tl) tl[7] = t_entry; }   // setup done (barriers, TMEM alloc)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -210,10 +186,12 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         tf::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        if (t == blockIdx.x) TF_STAMP(1);
         tf::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
           tf::mbar_wait(full_bar(stage), phase);
+          if (t == blockIdx.x && kb == kb0) TF_STAMP(2);   // first operands landed
           tf::tcgen05_fence_after();
           const uint64_t adesc = tf::umma_desc_sw128_kmajor(smem_a + stage * A_STAGE_BYTES);
           const uint64_t bdesc = tf::umma_desc_sw128_kmajor(smem_b + stage * b_stage_bytes);
@@ -226,6 +204,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tf::umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs have read it
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        if (t == blockIdx.x) TF_STAMP(3);   // all MMAs of the first tile issued
         tf::umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         as ^= 1;
         if (as == 0) aphase ^= 1u;
@@ -233,8 +212,26 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // Thread = accumulator row (the 32x32b TMEM load hands every lane its own row). Everything that does not
+    // depend on the accumulator is fetched while the main loop runs: the tile's bias slice (-> shared
+    // memory, read back as broadcasts) and the first residual chunk (64 contiguous bytes of the thread's
+    // row). The accumulator is drained 32 columns at a time: + bias + residual in registers, convert, write
+    // the row chunk into this warp's staging block in the TMA swizzle pattern (conflict-free 16-byte
+    // stores), then ONE TMA store ships the 32x32 block; rows / columns outside the tensor are clipped by
+    // the TMA unit, so there is no per-element address or bounds arithmetic at all.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    const uint32_t stg = epi_base + q * kEpiStageBytes;
+    float* bsm = reinterpret_cast<float*>(smem_raw + (epi_base + 4 * kEpiStageBytes - raw_u32)) + q * kEpiBiasFloats;
+    const bool partial = p.partial != nullptr;
+    const bool geglu = (p.flags & TF_EPI_GEGLU) != 0 && !partial;
+    const bool out_f32 = (p.flags & TF_EPI_OUT_F32) != 0 || partial;
+    const bool use_bias = p.bias != nullptr && !partial;
+    const bool use_res = p.residual != nullptr && !partial;
+    // swizzle of 16-byte chunk j in row r (row = lane): fp32 rows are 128 B (SW128), fp16 64 B (SW64), GEGLU 32 B (SW32)
+    const uint32_t row_bytes = out_f32 ? 128u : (geglu ? 32u : 64u);
+    const uint32_t swz = out_f32 ? (uint32_t)(lane & 7) : (geglu ? (uint32_t)((lane >> 2) & 1) : (uint32_t)((lane >> 1) & 3));
+    const uint32_t srow = stg + lane * row_bytes;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -242,56 +239,130 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t1 = t / p.splits;
       const int nt = t1 % p.n_tiles;
       const int mt = t1 / p.n_tiles;
-      const int m = tile_row_to_m(p, mt, row);
+      const int n_tile = nt * p.bn;
+      const int m_own = tile_row_to_m(p, mt, row);
+      // store coordinates of this warp's 32-row block
+      int sc1, sc2 = 0, sc3 = 0;
+      if (p.is_conv) {
+        const ConvGeom& g = p.g;
+        const int tx = mt % g.tiles_x, t2 = mt / g.tiles_x;
+        const int r0 = q * 32;
+        sc1 = tx * g.TW + r0 % g.TW;
+        sc2 = (t2 % g.tiles_y) * g.TH + (r0 / g.TW) % g.TH;
+        sc3 = (t2 / g.tiles_y) * g.TN + r0 / (g.TW * g.TH);
+      } else {
+        sc1 = mt * BM + q * 32;
+      }
+      // bias slice of this tile -> shared memory (zeros where absent / beyond N)
+#pragma unroll
+      for (int j = 0; j < kEpiBiasFloats / 32; ++j) {
+        const int nn = n_tile + j * 32 + lane;
+        bsm[j * 32 + lane] = (use_bias && j * 32 < p.bn && nn < p.N) ? __ldg(p.bias + nn) : 0.f;
+      }
+      // residual chunk: 32 halfs of this thread's row (zeros outside the tensor), prefetched one chunk ahead
+      const __half* res_row = (use_res && m_own >= 0) ? p.residual + (size_t)m_own * p.ldr + n_tile : nullptr;
+      auto load_res = [&](int c, uint4* rr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rr[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (res_row != nullptr && c < p.bn && n_tile + c + j * 8 < p.N)
+            rr[j] = *reinterpret_cast<const uint4*>(res_row + c + j * 8);
+        }
+      };
+      uint4 rr[4];
+      load_res(0, rr);
+      __syncwarp();
       tf::mbar_wait(tfull_bar(as), aphase);
+      if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(4);   // accumulator of the first tile complete
       tf::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
       for (int c = 0; c < p.bn; c += 32) {
         uint32_t v[32];
         tf::tmem_ld_x16(taddr + c, v);
-        const bool second = (c + 16 < p.bn);
-        if (second) tf::tmem_ld_x16(taddr + c + 16, v + 16);
+        tf::tmem_ld_x16(taddr + c + 16, v + 16);   // BN is a multiple of 32 (TMA store granularity)
+        uint4 rn[4];
+        load_res(c + 32, rn);            // next chunk's residual goes in flight now
         tf::tmem_ld_wait();
-        const int n = nt * p.bn + c;
-        if (m < 0) continue;
-        if (p.partial) {
-          float* dst = p.partial + ((size_t)split * p.M + m) * p.N + n;
+        if (c + 32 >= p.bn) {            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tf::tcgen05_fence_before();
+          tf::mbar_arrive(tempty_bar(as));
+        }
+        // the previous chunk's TMA store must have finished reading the staging block
+        if (lane == 0) tf::tma_store_wait_read<0>();
+        __syncwarp();
+        if (geglu) {
+          // packed columns: [c, c+16) = value, [c+16, c+32) = gate  (tinyfusers_b200/packing.py: geglu_pack)
+          uint32_t h[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j < p.N && (j < 16 || second))
-              *reinterpret_cast<float4*>(dst + j) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 16; j += 2) {
+            float f[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float val = __uint_as_float(v[j + i]) + bsm[c + j + i];
+              const float gate = __uint_as_float(v[16 + j + i]) + bsm[c + 16 + j + i];
+              f[i] = val * tf::gelu_tanh_f(gate);
+            }
+            __half2 hh = __floats2half2_rn(f[0], f[1]);
+            h[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           }
-        } else if (p.flags & TF_EPI_GEGLU) {
-          // packed columns: [n, n+16) = value, [n+16, n+32) = gate  (see tf_pack_geglu_weight)
-          if (n < p.N) {
-            float f[16];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ swz) << 4)), "r"(h[4 * j]),
+                         "r"(h[4 * j + 1]), "r"(h[4 * j + 2]), "r"(h[4 * j + 3])
+                         : "memory");
+        } else {
+          float f[32];
+          const __half2* r2 = reinterpret_cast<const __half2*>(rr);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 rv = __half22float2(r2[j >> 1]);
+            f[j] = __uint_as_float(v[j]) + bsm[c + j] + rv.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + bsm[c + j + 1] + rv.y;
+          }
+          if (out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ swz) << 4)),
+                           "r"(__float_as_uint(f[4 * j])), "r"(__float_as_uint(f[4 * j + 1])),
+                           "r"(__float_as_uint(f[4 * j + 2])), "r"(__float_as_uint(f[4 * j + 3]))
+                           : "memory");
+          } else {
+            uint32_t h[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float val = __uint_as_float(v[j]);
-              float gate = __uint_as_float(v[16 + j]);
-              if (p.bias) {
-                val += __ldg(p.bias + n + j);
-                gate += __ldg(p.bias + n + 16 + j);
-              }
-              f[j] = val * tf::gelu_tanh_f(gate);
+              __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+              h[j] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            store8(p, m, n / 2, f);
-            store8(p, m, n / 2 + 8, f + 8);
-          }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j < p.N && (j < 16 || second)) epilogue8(p, m, n + j, v + j);
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ swz) << 4)), "r"(h[4 * j]),
+                           "r"(h[4 * j + 1]), "r"(h[4 * j + 2]), "r"(h[4 * j + 3])
+                           : "memory");
           }
         }
+        tf::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          const int col = geglu ? ((n_tile + c) >> 1) : (n_tile + c);
+          // split-K partials live in a tensor with one extra (split) dimension, so a tile's overhang is clipped
+          // per split instead of spilling into the next split's slab
+          if (p.is_conv) {
+            if (partial) tf::tma_store_5d(&tmC, stg, col, sc1, sc2, sc3, split);
+            else tf::tma_store_4d(&tmC, stg, col, sc1, sc2, sc3);
+          } else {
+            if (partial) tf::tma_store_3d(&tmC, stg, col, sc1, split);
+            else tf::tma_store_2d(&tmC, stg, col, sc1);
+          }
+          tf::tma_store_commit();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = rn[j];
       }
-      tf::tcgen05_fence_before();
-      tf::mbar_arrive(tempty_bar(as));
+      if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(5);   // first tile stored (issued)
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if (lane == 0) tf::tma_store_wait<0>();   // all bulk stores complete before the CTA retires
   }
 
   tf::tcgen05_fence_before();
@@ -300,6 +371,8 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tf::tcgen05_fence_after();
     tf::tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) TF_STAMP(6);
+#undef TF_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -351,13 +424,14 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
   const int sms = tf_num_sms();
   TileChoice best{128, 1};
   double best_cost = 1e30;
-  const int step = (flags & TF_EPI_GEGLU) ? 32 : 16;
+  (void)flags;
+  const int step = 32;  // epilogue ships 32-column blocks
   for (int bn = step; bn <= 256; bn += step) {
     if (force_bn > 0 && bn != force_bn) continue;
     const int n_tiles = ceil_div_i(N, bn);
     // avoid heavily padded N tiles
     const double n_eff = (double)N / (n_tiles * bn);
-    if (n_eff < 0.8 && force_bn <= 0) continue;
+    if (n_eff < 0.8 && force_bn <= 0 && bn > step) continue;
     const int max_split = allow_split ? 16 : 1;
     for (int sp = 1; sp <= max_split; ++sp) {
       if (force_splits > 0 && sp != force_splits) continue;
@@ -382,9 +456,10 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
 }
 
 static int g_force_bn = 0, g_force_splits = 0;
+static long long* g_timeline = nullptr;
 
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p,
-                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams& p,
+                       cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -392,7 +467,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     attr_set = true;
   }
   const int stage_bytes = A_STAGE_BYTES + p.bn * 128;
-  int stages = (kSmemBudget - 2048) / stage_bytes;
+  int stages = (kSmemBudget - 2048 - kEpiBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
     tf_set_error("gemm: tile too large for shared memory");
@@ -401,16 +476,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.stages = stages;
   // always carve > half of the SM's shared memory: one CTA per SM, so the 512-column TMEM
   // allocation can never contend with a co-resident CTA.
-  size_t smem = (size_t)stages * stage_bytes + 2048;
+  size_t smem = (size_t)stages * stage_bytes + kEpiBytes + 2048;
   if (smem < 120 * 1024) smem = 120 * 1024;
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
-  if (p.splits > 1) {
-    p.partial = reinterpret_cast<float*>(workspace);
-  } else {
-    p.partial = nullptr;
-  }
-  tf_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  p.timeline = g_timeline;
+  tf_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, p);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   if (p.splits > 1) {
@@ -427,6 +498,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
 }
 
 }  // namespace
+
+extern "C" int tf_gemm_set_timeline(long long* dev_buf) {
+  g_timeline = dev_buf;  // >= 148*8 int64; debug only
+  return TF_OK;
+}
 
 extern "C" int tf_gemm_set_tuning(int force_bn, int force_splits) {
   g_force_bn = force_bn;
@@ -481,7 +557,25 @@ extern "C" int tf_gemm_f16(const void* A, int lda, const void* W, int ldw, void*
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  return launch_gemm(tmA, tmB, p, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+  CUtensorMap tmC;
+  {
+    const bool geglu = (flags & TF_EPI_GEGLU) != 0;
+    const bool f32 = (flags & TF_EPI_OUT_F32) != 0 || p.splits > 1;
+    p.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+    const void* base = p.splits > 1 ? workspace : out;
+    const uint64_t cols = geglu ? (uint64_t)N / 2 : (uint64_t)N;
+    const bool part = p.splits > 1;
+    const uint64_t ld = part ? (uint64_t)N : (uint64_t)ldc;
+    uint64_t dims[3] = {cols, (uint64_t)M, (uint64_t)p.splits};
+    uint64_t strides[2] = {ld * (f32 ? 4 : 2), (uint64_t)M * ld * (f32 ? 4 : 2)};
+    uint32_t box[3] = {geglu ? 16u : 32u, 32u, 1u};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = tf_encode_tmap(&tmC, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, part ? 3 : 2, base,
+                            dims, strides, box, es,
+                            f32 ? CU_TENSOR_MAP_SWIZZLE_128B : (geglu ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B));
+    if (rc) return rc;
+  }
+  return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride,
@@ -529,8 +623,11 @@ extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, 
   g.tiles_y = ceil_div_i(Ho, g.TH);
   p.m_tiles = g.tiles_x * g.tiles_y * ceil_div_i(NI, g.TN);
   p.k_blocks = 9 * g.cblocks;
-  TileChoice tc = choose_tiles(p.m_tiles, Cout, p.k_blocks, flags, workspace != nullptr, ws_bytes, p.M,
-                               g_force_bn, g_force_splits);
+  // store box of one epilogue warp = 32 consecutive tile rows (x fastest, then y, then image)
+  g.sbw = g.TW >= 32 ? 32 : g.TW;
+  g.sbh = g.TW >= 32 ? 1 : (g.TW * g.TH >= 32 ? 32 / g.TW : g.TH);
+  TileChoice tc = choose_tiles(p.m_tiles, Cout, p.k_blocks, flags, workspace != nullptr, ws_bytes, p.M, g_force_bn,
+                               g_force_splits);
   p.bn = tc.bn;
   p.splits = tc.splits;
   p.n_tiles = ceil_div_i(Cout, p.bn);
@@ -559,5 +656,22 @@ extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, 
                             CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  return launch_gemm(tmA, tmB, p, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+  CUtensorMap tmC;
+  {
+    const bool part = p.splits > 1;
+    const bool f32 = (flags & TF_EPI_OUT_F32) != 0 || part;
+    p.partial = part ? reinterpret_cast<float*>(workspace) : nullptr;
+    const void* base = part ? workspace : out;
+    const uint64_t ld = part ? (uint64_t)Cout : (uint64_t)ldc;
+    const uint64_t es_b = f32 ? 4 : 2;
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NI, (uint64_t)p.splits};
+    uint64_t strides[4] = {ld * es_b, (uint64_t)Wo * ld * es_b, (uint64_t)Ho * Wo * ld * es_b,
+                           (uint64_t)NI * Ho * Wo * ld * es_b};
+    uint32_t box[5] = {32u, (uint32_t)g.sbw, (uint32_t)g.sbh, (uint32_t)(32 / (g.sbw * g.sbh)), 1u};
+    uint32_t es[5] = {1, 1, 1, 1, 1};
+    int rc = tf_encode_tmap(&tmC, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, part ? 5 : 4, base,
+                            dims, strides, box, es, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -74,21 +74,26 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, in
   }
 }
 
-// stats[(n*G+g)] = {mean, rstd}; one block per image, one thread per group; up to two slice partial arrays
+// stats[(n*G+g)] = {mean, rstd}; one block per image, one WARP per group: lanes stride over the chunk
+// partials, then a fixed-pattern xor-shuffle reduction (deterministic). Up to two slice partial arrays.
 __global__ void gn_finalize_kernel(const float2* __restrict__ partial_a, const float2* __restrict__ partial_b, int chunks,
                                    int NI, int G, int split_group_lo, int split_group_hi, float inv_count, float eps,
                                    float2* __restrict__ stats) {
-  const int n = blockIdx.x, g = threadIdx.x;
+  const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
   float a = 0.f, b = 0.f;
   // slice A covers groups [0, split_group_hi], slice B (optional) covers [split_group_lo, G)
   if (g <= split_group_hi)
-    for (int c = 0; c < chunks; ++c) { float2 t = partial_a[((size_t)c * NI + n) * G + g]; a += t.x; b += t.y; }
+    for (int c = lane; c < chunks; c += 32) { float2 t = partial_a[((size_t)c * NI + n) * G + g]; a += t.x; b += t.y; }
   if (partial_b && g >= split_group_lo)
-    for (int c = 0; c < chunks; ++c) { float2 t = partial_b[((size_t)c * NI + n) * G + g]; a += t.x; b += t.y; }
-  const float mean = a * inv_count;
-  const float var = fmaxf(b * inv_count - mean * mean, 0.f);
-  stats[(size_t)n * G + g] = make_float2(mean, rsqrtf(var + eps));
+    for (int c = lane; c < chunks; c += 32) { float2 t = partial_b[((size_t)c * NI + n) * G + g]; a += t.x; b += t.y; }
+  a = tf::warp_sum(a);
+  b = tf::warp_sum(b);
+  if (lane == 0) {
+    const float mean = a * inv_count;
+    const float var = fmaxf(b * inv_count - mean * mean, 0.f);
+    stats[(size_t)n * G + g] = make_float2(mean, rsqrtf(var + eps));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -206,45 +211,100 @@ __global__ void ln_rows_kernel(const __half* __restrict__ x, __half* __restrict_
   }
 }
 
-// interleave == 2: one warp per chunk-row t; each half2 holds (b=0, b=1) of one channel.
-template <int MAXE>  // max half2 elements per lane
-__global__ void ln_il2_kernel(const __half* __restrict__ x, __half* __restrict__ out, int trow, int C,
-                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= trow) return;
-  const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)warp * C * 2);
-  float2 e[MAXE];
-  float s0 = 0.f, s1 = 0.f;
+// Block-per-chunk-row LayerNorm for interleave IL in {1,2,4,8}: the chunk row is C*IL contiguous halfs; element
+// p belongs to group (p % IL) and channel (p / IL). 128-bit loads, the row stays in registers, exact two-pass
+// statistics, fixed-order block reduction. Used when rows are long or few (one warp per row is latency-bound).
+template <int IL, int THREADS, int MAXV>
+__global__ void __launch_bounds__(THREADS)
+ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps) {
+  __shared__ float red[2][THREADS / 32][IL];
+  const int nvec = (C * IL) >> 3;
+  const __half* xr = x + (size_t)blockIdx.x * C * IL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tf::Pack16 pk[MAXV];
+  float s[IL];
 #pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int c = lane + i * 32;
-    if (c < C) {
-      e[i] = __half22float2(xr[c]);
-      s0 += e[i].x;
-      s1 += e[i].y;
+  for (int b = 0; b < IL; ++b) s[b] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = threadIdx.x + i * THREADS;
+    if (v < nvec) {
+      pk[i].v = *reinterpret_cast<const uint4*>(xr + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j % IL] += __half2float(pk[i].h[j]);
     }
   }
-  const float m0 = tf::warp_sum(s0) / (float)C, m1 = tf::warp_sum(s1) / (float)C;
-  float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int c = lane + i * 32;
-    if (c < C) {
-      q0 += (e[i].x - m0) * (e[i].x - m0);
-      q1 += (e[i].y - m1) * (e[i].y - m1);
+  for (int b = 0; b < IL; ++b) {
+    const float w = tf::warp_sum(s[b]);
+    if (lane == 0) red[0][warp][b] = w;
+  }
+  __syncthreads();
+  float mean[IL];
+#pragma unroll
+  for (int b = 0; b < IL; ++b) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) t += red[0][w][b];
+    mean[b] = t / (float)C;
+    s[b] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = threadIdx.x + i * THREADS;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = __half2float(pk[i].h[j]) - mean[j % IL];
+        s[j % IL] += d * d;
+      }
     }
   }
-  const float r0 = rsqrtf(tf::warp_sum(q0) / (float)C + eps), r1 = rsqrtf(tf::warp_sum(q1) / (float)C + eps);
-  __half2* orow = reinterpret_cast<__half2*>(out + (size_t)warp * C * 2);
 #pragma unroll
-  for (int i = 0; i < MAXE; ++i) {
-    const int c = lane + i * 32;
-    if (c < C) {
-      const float g = __ldg(gamma + c), b = __ldg(beta + c);
-      orow[c] = __floats2half2_rn((e[i].x - m0) * r0 * g + b, (e[i].y - m1) * r1 * g + b);
+  for (int b = 0; b < IL; ++b) {
+    const float w = tf::warp_sum(s[b]);
+    if (lane == 0) red[1][warp][b] = w;
+  }
+  __syncthreads();
+  float rstd[IL];
+#pragma unroll
+  for (int b = 0; b < IL; ++b) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) t += red[1][w][b];
+    rstd[b] = rsqrtf(t / (float)C + eps);
+  }
+  __half* orow = out + (size_t)blockIdx.x * C * IL;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = threadIdx.x + i * THREADS;
+    if (v < nvec) {
+      tf::Pack16 r;
+      const int c0 = (v * 8) / IL;  // first channel covered by this vector (8 / IL channels)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j / IL;
+        const float y = (__half2float(pk[i].h[j]) - mean[j % IL]) * rstd[j % IL] * __ldg(gamma + c) + __ldg(beta + c);
+        r.h[j] = __float2half_rn(y);
+      }
+      *reinterpret_cast<uint4*>(orow + v * 8) = r.v;
     }
   }
+}
+
+template <int IL>
+static bool launch_ln_block(const __half* x, __half* out, int chunk_rows, int C, const float* gamma, const float* beta,
+                            float eps, cudaStream_t stream) {
+  const int nvec = C * IL / 8;
+  if ((C * IL) % 8 != 0) return false;
+  if (nvec <= 64) ln_block_kernel<IL, 32, 2><<<chunk_rows, 32, 0, stream>>>(x, out, C, gamma, beta, eps);
+  else if (nvec <= 128) ln_block_kernel<IL, 64, 2><<<chunk_rows, 64, 0, stream>>>(x, out, C, gamma, beta, eps);
+  else if (nvec <= 256) ln_block_kernel<IL, 128, 2><<<chunk_rows, 128, 0, stream>>>(x, out, C, gamma, beta, eps);
+  else if (nvec <= 512) ln_block_kernel<IL, 128, 4><<<chunk_rows, 128, 0, stream>>>(x, out, C, gamma, beta, eps);
+  else if (nvec <= 1024) ln_block_kernel<IL, 256, 4><<<chunk_rows, 256, 0, stream>>>(x, out, C, gamma, beta, eps);
+  else return false;
+  return true;
 }
 
 // generic interleave: one warp per (t, b); strided scalar access (correct for any IL, not tuned)
@@ -285,7 +345,7 @@ extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TF_CHECK_ARG(x && out && stats_ws, "tf_groupnorm_nhwc_f16: null pointer");
   const int C = Cx + (x2 ? Cx2 : 0);
-  TF_CHECK_ARG(NI > 0 && HW > 0 && groups > 0 && groups <= 64 && C % groups == 0,
+  TF_CHECK_ARG(NI > 0 && HW > 0 && groups > 0 && groups <= 32 && C % groups == 0,
                "tf_groupnorm_nhwc_f16: bad dims (C=%d groups=%d)", C, groups);
   TF_CHECK_ARG(Cx % 8 == 0 && (!x2 || Cx2 % 8 == 0) && x_pixel_stride % 8 == 0 && out_pixel_stride % 8 == 0 &&
                    (!x2 || x2_pixel_stride % 8 == 0),
@@ -314,7 +374,7 @@ extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, 
     gn_stats_kernel<<<grid, threads, smem, stream>>>(xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, partial[i]);
     TF_LAUNCH_CHECK();
   }
-  gn_finalize_kernel<<<NI, 64, 0, stream>>>(partial[0], nsrc == 2 ? partial[1] : nullptr, chunks, NI, groups,
+  gn_finalize_kernel<<<NI, 32 * groups, 0, stream>>>(partial[0], nsrc == 2 ? partial[1] : nullptr, chunks, NI, groups,
                                             nsrc == 2 ? Cx / cpg : 0, (Cx - 1) / cpg, inv_count, eps, stats);
   TF_LAUNCH_CHECK();
   for (int i = 0; i < nsrc; ++i) {
@@ -334,24 +394,22 @@ extern "C" int tf_layernorm_f16(const void* x, void* out, int rows, int C, const
   TF_CHECK_ARG(rows > 0 && C > 0 && interleave >= 1 && rows % interleave == 0,
                "tf_layernorm_f16: bad dims rows=%d C=%d interleave=%d", rows, C, interleave);
   const int threads = 256, wpb = threads / 32;
-  if (interleave == 1) {
-    TF_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "tf_layernorm_f16: C must be a multiple of 8 and <= 2048");
-    const int blocks = ceil_div_i(rows, wpb);
-    const int nv = ceil_div_i(C / 8, 32);
-    if (nv <= 2) ln_rows_kernel<2><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows, C, gamma, beta, eps);
-    else if (nv <= 5) ln_rows_kernel<5><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows, C, gamma, beta, eps);
-    else ln_rows_kernel<8><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows, C, gamma, beta, eps);
-  } else if (interleave == 2 && C <= 32 * 40) {
-    const int trow = rows / 2;
-    const int blocks = ceil_div_i(trow, wpb);
-    const int ne = ceil_div_i(C, 32);
-    if (ne <= 10) ln_il2_kernel<10><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, trow, C, gamma, beta, eps);
-    else if (ne <= 20) ln_il2_kernel<20><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, trow, C, gamma, beta, eps);
-    else ln_il2_kernel<40><<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, trow, C, gamma, beta, eps);
-  } else {
-    const int blocks = ceil_div_i(rows, wpb);
-    ln_il_generic_kernel<<<blocks, threads, 0, stream>>>((const __half*)x, (__half*)out, rows / interleave, C,
-                                                         interleave, gamma, beta, eps);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  __half* oh = reinterpret_cast<__half*>(out);
+  const int chunk_rows = rows / interleave;
+  bool done = false;
+  if (interleave == 1) done = launch_ln_block<1>(xh, oh, chunk_rows, C, gamma, beta, eps, stream);
+  else if (interleave == 2) done = launch_ln_block<2>(xh, oh, chunk_rows, C, gamma, beta, eps, stream);
+  else if (interleave == 4) done = launch_ln_block<4>(xh, oh, chunk_rows, C, gamma, beta, eps, stream);
+  else if (interleave == 8) done = launch_ln_block<8>(xh, oh, chunk_rows, C, gamma, beta, eps, stream);
+  if (!done) {
+    if (interleave == 1) {
+      TF_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "tf_layernorm_f16: C must be a multiple of 8 and <= 2048");
+      ln_rows_kernel<8><<<ceil_div_i(rows, wpb), threads, 0, stream>>>(xh, oh, rows, C, gamma, beta, eps);
+    } else {
+      ln_il_generic_kernel<<<ceil_div_i(rows, wpb), threads, 0, stream>>>(xh, oh, chunk_rows, C, interleave, gamma,
+                                                                         beta, eps);
+    }
   }
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);

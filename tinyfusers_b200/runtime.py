@@ -106,6 +106,7 @@ class Context:
         self.ws_bytes = 192 << 20
         self.ws = None
         self.dry = False
+        self.only = None           # bench instrumentation: if a set, only kernels of these kinds are launched
         # per-forward values set by the UNet
         self.emb_bias = None       # dict: id(ResBlock) -> device pointer of its (conv bias + emb) fp32 vector
         self.context = None        # Act view of the zero-padded fp16 prompt context (B, Tpad, 768)
@@ -125,15 +126,19 @@ class Context:
         return self.arena.alloc(4 * numel)
 
     # -- kernel wrappers (each is one C-ABI call) ---------------------------------------------------
+    def skip(self, kind):
+        """True when the kernel must not be launched (arena dry run, or bench's per-class timing filter)."""
+        return self.dry or (self.only is not None and kind not in self.only)
+
     def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None):
-        if self.dry:
+        if self.skip("gemm"):
             return
         st = b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
                               residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
         b200.check(st, "tf_gemm_f16")
 
     def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0):
-        if self.dry:
+        if self.skip("gemm"):
             return
         st = b200.tf_conv2d_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr, out.stride, bias,
                                      residual.ptr if residual is not None else None,
@@ -145,20 +150,20 @@ class Context:
         mark = self.arena.mark()
         stats = self.arena.alloc(b200.tf_groupnorm_workspace_bytes(x.n, groups))   # partials + {mean, rstd}
         self.arena.release(mark)                          # stream order keeps the reuse safe
-        if self.dry:
+        if self.skip("norm"):
             return
         st = b200.tf_groupnorm_nhwc_f16(x.ptr, x.stride, x.c, None, 0, 0, out.ptr, out.stride, x.n, x.h * x.w, groups,
                                         gamma, beta, eps, 1 if silu else 0, stats, stream_ptr())
         b200.check(st, "tf_groupnorm_nhwc_f16")
 
     def layernorm(self, x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave):
-        if self.dry:
+        if self.skip("norm"):
             return
         st = b200.tf_layernorm_f16(x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave, stream_ptr())
         b200.check(st, "tf_layernorm_f16")
 
     def attention(self, q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, B, NH, Tq, Tk, Tk_pad, d, dp, head_major):
-        if self.dry:
+        if self.skip("attention"):
             return
         if head_major:   # reference reshape quirk: (B,NH,T,d) memory read back as (B,T,NH*d)
             osb, osh, ost = NH * Tq * d, Tq * d, d
@@ -169,7 +174,7 @@ class Context:
         b200.check(st, "tf_attention_f16")
 
     def upsample2x(self, x, out):
-        if self.dry:
+        if self.skip("misc"):
             return
         st = b200.tf_upsample_nearest2x_nhwc_f16(x.ptr, x.stride, out.ptr, out.stride, x.n, x.h, x.w, x.c, stream_ptr())
         b200.check(st, "tf_upsample_nearest2x_nhwc_f16")

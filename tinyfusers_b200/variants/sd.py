@@ -73,7 +73,7 @@ class StableDiffusion:
         s = self._sampler(latent.shape, context.shape[1])
         s.load(unconditional_context, context, latent)
         s.set_scalars(timestep, alphas, alphas_prev, guidance)
-        s.enqueue_step(update_latent=True)
+        s.step_once()
         return s.latent.clone()
 
     # ---- whole sampler loop on device (graph-captured steps) -----------------------------------------
@@ -118,8 +118,6 @@ class SamplerEngine:
         self.ap_tab = torch.ones(self.max_steps, dtype=F32, device=dev)
         self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
         self.guidance = 7.5
-        self.graph = None
-        self.graph_guidance = None
 
     def load(self, unconditional_context, context, latent):
         require_cuda(latent, "latent")
@@ -148,9 +146,11 @@ class SamplerEngine:
         """One step on the current stream: UNet(2B) -> CFG + DDIM (in place) [-> idx -= 1]."""
         e = self.unet_engine
         e._enqueue(t_ptr=self.t_tab.data_ptr(), idx_ptr=self.idx.data_ptr())
-        out = self.latent if update_latent else self.e_t   # when only e_t is wanted the latent is left untouched
-        scratch = self.latent.data_ptr() if update_latent else self._scratch().data_ptr()
-        st = b200.tf_cfg_ddim_step_f32(e.eps.data_ptr(), 16, self.latent.data_ptr(), scratch, self.e_t.data_ptr(),
+        if e.ctx.skip("misc"):
+            return
+        # when only e_t is wanted (get_model_output) the latent is left untouched
+        dst = self.latent.data_ptr() if update_latent else self._scratch().data_ptr()
+        st = b200.tf_cfg_ddim_step_f32(e.eps.data_ptr(), 16, self.latent.data_ptr(), dst, self.e_t.data_ptr(),
                                        self.a_tab.data_ptr(), self.ap_tab.data_ptr(), self.idx.data_ptr(),
                                        float(self.guidance), self.B, 4, self.H * self.W, stream_ptr())
         b200.check(st, "tf_cfg_ddim_step_f32")
@@ -162,25 +162,43 @@ class SamplerEngine:
             self._scratch_buf = torch.empty_like(self.latent)
         return self._scratch_buf
 
-    def capture(self):
-        """Capture one step (with index advance) into a CUDA graph; replays need no host work."""
-        self.enqueue_step(advance=False)  # warm-up outside capture (lazy attribute setup, weight packing)
-        torch.cuda.synchronize()
+    def capture(self, advance=True):
+        """Capture one step into a CUDA graph; replays need no host work. advance=True also decrements the
+        device step index (sampler loop); advance=False is the graph behind the drop-in __call__."""
+        if not getattr(self, "_warm", False):
+            lat, idx = self.latent.clone(), self.idx.clone()
+            self.enqueue_step(advance=False)  # eager warm-up: lazy attribute setup, weight packing
+            torch.cuda.synchronize()
+            self.latent.copy_(lat)
+            self.idx.copy_(idx)
+            self._warm = True
+        lat = self.latent.clone()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.enqueue_step(update_latent=True, advance=True)
-        self.graph, self.graph_guidance = g, self.guidance
+            self.enqueue_step(update_latent=True, advance=advance)
+        self.latent.copy_(lat)
         return g
+
+    def _graph(self, advance):
+        key = (advance, self.guidance)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = self.capture(advance)
+        return g
+
+    def step_once(self, use_graph=True):
+        if use_graph:
+            self._graph(False).replay()
+        else:
+            self.enqueue_step(update_latent=True, advance=False)
 
     def run(self, n_steps, use_graph=True):
         if use_graph:
-            if self.graph is None or self.graph_guidance != self.guidance:
-                lat, idx = self.latent.clone(), self.idx.clone()
-                self.capture()
-                self.latent.copy_(lat)
-                self.idx.copy_(idx)
+            g = self._graph(True)
             for _ in range(n_steps):
-                self.graph.replay()
+                g.replay()
         else:
             for _ in range(n_steps):
                 self.enqueue_step(update_latent=True, advance=True)

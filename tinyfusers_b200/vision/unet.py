@@ -163,13 +163,14 @@ class UNetModel:
         ar = ctx.arena
         ar.reset()
         S = stream_ptr() if not ctx.dry else None
+        misc = not ctx.skip("misc")
         # --- time embedding MLP and all ResBlock emb biases (fp32, M = 1) ---
         temb, e1, emb = ctx.new_f32(320), ctx.new_f32(1280), ctx.new_f32(1280)
         wemb, bemb, cbias, offs, total = self._emb_pack()
         allb = ctx.new_f32(total)
         w0, b0 = self.time_embed[0]._packed()
         w2, b2 = self.time_embed[2]._packed()
-        if not ctx.dry:
+        if misc:
             b200.check(b200.tf_timestep_embedding_f32(t_ptr, idx_ptr, 320, 10000.0, temb, S), "tf_timestep_embedding_f32")
             b200.check(b200.tf_gemv_f16w(temb, w0.data_ptr(), b0.data_ptr(), None, e1, 1280, 320, 0, S), "tf_gemv_f16w")
             b200.check(b200.tf_gemv_f16w(e1, w2.data_ptr(), b2.data_ptr(), None, emb, 1280, 1280, 1, S), "tf_gemv_f16w")
@@ -180,7 +181,7 @@ class UNetModel:
         tkp = (ctx_tokens + 7) // 8 * 8
         cact = ctx.new_act(n, tkp, 1, 768)
         cact.valid = ctx_tokens
-        if not ctx.dry:
+        if misc:
             b200.check(b200.tf_pad_tokens_f32_to_f16(context_ptr, cact.ptr, n, ctx_tokens, tkp, 768, S),
                        "tf_pad_tokens_f32_to_f16")
         # --- plan the skip/concat buffers: output block j reads [x | saved[11-j]] ---

@@ -1,0 +1,40 @@
+"""Dev: per-CTA clock stamps of the GEMM kernel for a few UNet shapes (where does a short kernel spend its time?)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tinyfusers_b200.native.b200.ops import b200
+dev = torch.device("cuda:0"); b200.init(0)
+S = lambda: torch.cuda.current_stream().cuda_stream
+ws = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+tl = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+def report(name, grid):
+    torch.cuda.synchronize()
+    t = tl.view(148, 16)[:grid].cpu().double()
+    e = t[:, 7:8]
+    names = ["setup_done", "mma_start", "first_operands", "mma_issued", "acc_ready", "stored", "exit"]
+    d = (t[:, :7] - e)
+    ex = {k: int((t[:, i] - e[:, 0]).median().item()) for k, i in (("c0_done", 12), ("c1_tmem_loaded", 8), ("c1_staged", 9), ("c1_lds_done", 10), ("c1_done", 11))}
+    print(name, "grid", grid, " median cycles since kernel entry:", {n: int(d[:, i].median().item()) for i, n in enumerate(names)}, ex)
+def gemm(M, N, K, residual=False, geglu=False, dbg=0):
+    A = torch.randn(M, K, device=dev).half(); W = (torch.randn(N, K, device=dev) / 30).half(); b = torch.randn(N, device=dev)
+    No = N // 2 if geglu else N
+    R = torch.randn(M, No, device=dev).half() if residual else None
+    out = torch.empty(M, No, dtype=torch.half, device=dev)
+    for i in range(3):
+        b200.tf_gemm_set_timeline(tl.data_ptr() if i == 2 else None)
+        b200.check(b200.tf_gemm_f16(A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), No, M, N, K, b.data_ptr(), R.data_ptr() if residual else None, No, (2 if geglu else 0) | dbg, ws.data_ptr(), ws.numel(), S()), "gemm")
+    b200.tf_gemm_set_timeline(None)
+    report(f"gemm {M}x{N}x{K} res={residual} geglu={geglu} dbg={hex(dbg)}", min(148, (M + 127) // 128 * max(1, N // 160)))
+def conv(NI, H, W, Cin, Cout):
+    x = torch.randn(NI, H, W, Cin, device=dev).half(); w = (torch.randn(Cout, 3, 3, Cin, device=dev) / 50).half()
+    b = torch.randn(Cout, device=dev); out = torch.empty(NI, H, W, Cout, dtype=torch.half, device=dev)
+    for i in range(3):
+        b200.tf_gemm_set_timeline(tl.data_ptr() if i == 2 else None)
+        b200.check(b200.tf_conv2d_nhwc_f16(x.data_ptr(), NI, H, W, Cin, Cin, w.data_ptr(), Cout, 3, 1, out.data_ptr(), Cout, b.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), S()), "conv")
+    b200.tf_gemm_set_timeline(None)
+    report(f"conv {NI}x{H}x{W} {Cin}->{Cout}", 128)
+gemm(8192, 320, 320, residual=True)
+gemm(8192, 320, 320)
+gemm(8192, 320, 1280, residual=True)
+gemm(8192, 2560, 320, geglu=True)
+conv(2, 64, 64, 320, 320)
+conv(2, 32, 32, 640, 640)
