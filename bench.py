@@ -320,7 +320,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": WORKLOAD, "parallelism": f"dp{world} (independent replicas, final-latent all_gather)",
                    "images_per_s_50step": value / 50.0,
                    "l2": "working set > L2: 1.72 GB of fp16 weights streamed every step (126 MB L2)",
-                   "semantics": "reference-literal (LayerNorm stride + head-merge quirks on)",
+                   "semantics": "reference-literal (CrossAttention head-major reshape on; LayerNorm as real cuDNN executes it)",
                    "cuda_graph": True, "output_finite": finite},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e, "api": "StableDiffusion.__call__ (pinned host tensors in, host latent out)"},

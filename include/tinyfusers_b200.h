@@ -32,6 +32,8 @@ int tf_version(void);
 int tf_init(int device);
 const char* tf_last_error(void);
 /* number of kernels this library has launched since the last reset (bench.py: gpu_launches) */
+/* programmatic dependent launch between this library's kernels (default off; env TINYFUSERS_B200_PDL=1) */
+int tf_set_pdl(int enable);
 long long tf_launch_count(void);
 void tf_launch_count_reset(void);
 

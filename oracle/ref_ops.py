@@ -12,14 +12,15 @@ Parity pinning:
   * the three ops whose arithmetic lives in cuDNN / cuBLAS / a CUDA kernel (conv2d, layer_norm,
     softmax) are additionally pinned the way the reference's own tests pin them — against
     torch.nn.functional (tests/conv2d.py:27-33, tests/layer_norm.py:33-41, tests/sdpa.py:97-100) — and
-    the LayerNorm batch>1 stride quirk against a real cuDNN run (oracle/cudnn_probe.py, GPU box).
+    LayerNorm against a real cuDNN run of the reference's graph (oracle/cudnn_probe.py, GPU box).
 
 All functions take/return torch CPU tensors in the REFERENCE layouts: NCHW images, (B, T, C) tokens,
 OIHW conv weights, (out, in) linear weights. `dtype` of the inputs decides the precision (fp32 like the
 reference, or fp64 for a tighter yardstick).
 
-`quirks=True` reproduces the reference literally (SURVEY.md §8 parity notes 1-2); `quirks=False` is
-canonical Stable Diffusion.
+`quirks=True` reproduces the reference's CrossAttention head-major reshape (SURVEY.md §8 parity note 2);
+`quirks=False` is canonical Stable Diffusion. `ln_strided` (default False) selects the literal reading of the
+LayerNorm stride declaration, which real cuDNN rejects at batch > 1 — see layer_norm().
 """
 import math
 
@@ -87,17 +88,21 @@ def group_norm_affine(x, num_groups, weight, bias, eps=1e-5):
     return o * weight.reshape(shape) + bias.reshape(shape)
 
 
-def layer_norm(x, weight, bias, eps=1e-5, quirks=True):
-    """ff/layer_norm.py:34-49 -> :8-32.
+def layer_norm(x, weight, bias, eps=1e-5, ln_strided=False):
+    """ff/layer_norm.py:34-49 -> :8-32: LayerNorm over the last dimension (cuDNN inference layernorm graph).
 
     The reference hands cuDNN a contiguous (1,B,T,C) buffer but declares the strides
-    [B*T*C, 1, B*C, B] (layer_norm.py:10). cuDNN normalises over the last logical dim (the only dim on
-    which scale/bias have extent) and writes Y with X's strides, so logical element (b,t,c) lives at
-    memory offset  b + t*B*C + c*B.  In memory terms: view the buffer as (T, C, B) and normalise over
-    axis 1. For B == 1 this is the canonical LayerNorm over C; for B > 1 it is not (parity note 1).
+    [B*T*C, 1, B*C, B] (layer_norm.py:10). For B == 1 that IS the contiguous layout and the result is the
+    canonical LayerNorm over C — confirmed against real cuDNN 9.x on the B200 box (oracle/cudnn_probe.py,
+    tests/golden/cudnn_layernorm_probe.json, rel err 2e-7). For B > 1 the same probe shows cuDNN REJECTS the
+    descriptor (CUDNN_STATUS_NOT_SUPPORTED at finalize): the reference has no result at CFG batch 2 on this
+    cuDNN. The default here is therefore the semantics cuDNN does execute (canonical, per batch element).
+    `ln_strided=True` is the literal reading of the declared strides (SURVEY.md §8 parity note 1): logical
+    element (b,t,c) at memory offset b + t*B*C + c*B, i.e. view memory as (T, C, B) and normalise over axis 1
+    — kept as an option of the kernel and tested, not the default.
     """
     B, T, C = x.shape
-    if not quirks or B == 1:
+    if not ln_strided or B == 1:
         mean = x.mean(dim=-1, keepdim=True)
         var = ((x - mean) ** 2).mean(dim=-1, keepdim=True)
         return (x - mean) / torch.sqrt(var + eps) * weight + bias
@@ -191,23 +196,23 @@ def cross_attention(sd, p, x, context, n_heads, d_head, quirks=True):
     return linear(o, _w(sd, p + ".to_out.0.weight"), _b(sd, p + ".to_out.0.bias"))
 
 
-def basic_transformer_block(sd, p, x, context, n_heads, d_head, quirks=True):
+def basic_transformer_block(sd, p, x, context, n_heads, d_head, quirks=True, ln_strided=False):
     # attention/attention.py:43-56
-    ln = lambda name, t: layer_norm(t, _w(sd, f"{p}.{name}.weight"), _b(sd, f"{p}.{name}.bias"), 1e-5, quirks)
+    ln = lambda name, t: layer_norm(t, _w(sd, f"{p}.{name}.weight"), _b(sd, f"{p}.{name}.bias"), 1e-5, ln_strided)
     x = cross_attention(sd, p + ".attn1", ln("norm1", x), None, n_heads, d_head, quirks) + x
     x = cross_attention(sd, p + ".attn2", ln("norm2", x), context, n_heads, d_head, quirks) + x
     x = feed_forward(sd, p + ".ff", ln("norm3", x)) + x
     return x
 
 
-def spatial_transformer(sd, p, x, context, n_heads, d_head, quirks=True):
+def spatial_transformer(sd, p, x, context, n_heads, d_head, quirks=True, ln_strided=False):
     # attention/attention.py:58-76
     b, c, h, w = x.shape
     x_in = x
     x = group_norm_affine(x, 32, _w(sd, p + ".norm.weight"), _b(sd, p + ".norm.bias"), 1e-5)
     x = conv2d(x, _w(sd, p + ".proj_in.weight"), _b(sd, p + ".proj_in.bias"))
     x = x.reshape(b, c, h * w).permute(0, 2, 1)
-    x = basic_transformer_block(sd, p + ".transformer_blocks.0", x, context, n_heads, d_head, quirks)
+    x = basic_transformer_block(sd, p + ".transformer_blocks.0", x, context, n_heads, d_head, quirks, ln_strided)
     x = x.permute(0, 2, 1).reshape(b, c, h, w)
     return conv2d(x, _w(sd, p + ".proj_out.weight"), _b(sd, p + ".proj_out.bias")) + x_in
 
@@ -272,14 +277,14 @@ CONTEXT_DIM = 768
 EMB_CHANNELS = 1280
 
 
-def _run_layer(sd, p, layer, x, emb, context, quirks):
+def _run_layer(sd, p, layer, x, emb, context, quirks, ln_strided=False):
     kind = layer[0]
     if kind == "conv":
         return conv2d(x, _w(sd, p + ".weight"), _b(sd, p + ".bias"), padding=(1, 1))
     if kind == "res":
         return res_block(sd, p, x, emb)
     if kind == "st":
-        return spatial_transformer(sd, p, x, context, layer[2], layer[3], quirks)
+        return spatial_transformer(sd, p, x, context, layer[2], layer[3], quirks, ln_strided)
     if kind == "down":
         return downsample(sd, p, x)
     if kind == "up":
@@ -287,7 +292,7 @@ def _run_layer(sd, p, layer, x, emb, context, quirks):
     raise ValueError(kind)
 
 
-def unet_forward(sd, x, timesteps, context, prefix="model.diffusion_model", quirks=True):
+def unet_forward(sd, x, timesteps, context, prefix="model.diffusion_model", quirks=True, ln_strided=False):
     # vision/unet.py:51-76
     P = prefix
     t_emb = timestep_embedding(timesteps, 320).to(x.dtype)
@@ -296,14 +301,14 @@ def unet_forward(sd, x, timesteps, context, prefix="model.diffusion_model", quir
     saved = []
     for i, block in enumerate(UNET_INPUT_BLOCKS):
         for j, layer in enumerate(block):
-            x = _run_layer(sd, f"{P}.input_blocks.{i}.{j}", layer, x, emb, context, quirks)
+            x = _run_layer(sd, f"{P}.input_blocks.{i}.{j}", layer, x, emb, context, quirks, ln_strided)
         saved.append(x)
     for j, layer in enumerate(UNET_MIDDLE_BLOCK):
-        x = _run_layer(sd, f"{P}.middle_block.{j}", layer, x, emb, context, quirks)
+        x = _run_layer(sd, f"{P}.middle_block.{j}", layer, x, emb, context, quirks, ln_strided)
     for i, block in enumerate(UNET_OUTPUT_BLOCKS):
         x = torch.cat((x, saved.pop()), dim=1)
         for j, layer in enumerate(block):
-            x = _run_layer(sd, f"{P}.output_blocks.{i}.{j}", layer, x, emb, context, quirks)
+            x = _run_layer(sd, f"{P}.output_blocks.{i}.{j}", layer, x, emb, context, quirks, ln_strided)
     x = group_norm_affine(x, 32, _w(sd, P + ".out.0.weight"), _b(sd, P + ".out.0.bias"))
     return conv2d(silu(x), _w(sd, P + ".out.2.weight"), _b(sd, P + ".out.2.bias"), padding=(1, 1))
 
@@ -323,19 +328,19 @@ def get_x_prev_and_pred_x0(x, e_t, a_t, a_prev):
     return x_prev, pred_x0
 
 
-def get_model_output(sd, unconditional_context, context, latent, timestep, guidance, quirks=True):
+def get_model_output(sd, unconditional_context, context, latent, timestep, guidance, quirks=True, ln_strided=False):
     # sd.py:27-46: batch = [uncond ; cond], e_t = u + g (c - u)
     n = latent.shape[0]
     lat2 = torch.cat((latent, latent), dim=0) if n > 1 else latent.expand(2, *latent.shape[1:])
     ctx2 = torch.cat((unconditional_context, context), dim=0)
-    out = unet_forward(sd, lat2.contiguous(), timestep, ctx2, quirks=quirks)
+    out = unet_forward(sd, lat2.contiguous(), timestep, ctx2, quirks=quirks, ln_strided=ln_strided)
     u, c = out[0:n], out[n:2 * n]
     return u + guidance * (c - u)
 
 
-def sampler_step(sd, unconditional_context, context, latent, timestep, a_t, a_prev, guidance, quirks=True):
+def sampler_step(sd, unconditional_context, context, latent, timestep, a_t, a_prev, guidance, quirks=True, ln_strided=False):
     # sd.py:56-59
-    e_t = get_model_output(sd, unconditional_context, context, latent, timestep, guidance, quirks)
+    e_t = get_model_output(sd, unconditional_context, context, latent, timestep, guidance, quirks, ln_strided)
     x_prev, _ = get_x_prev_and_pred_x0(latent, e_t, a_t, a_prev)
     return x_prev
 

@@ -56,8 +56,8 @@ def test_cross_attention_self_and_cross(oracle, quirks, c, d, T, B):
         tinyfusers_b200.set_quirks(True)
 
 
-@pytest.mark.parametrize("quirks", [True, False])
-def test_basic_transformer_block(oracle, quirks):
+@pytest.mark.parametrize("quirks,strided", [(True, False), (False, False), (True, True)])
+def test_basic_transformer_block(oracle, quirks, strided):
     import tinyfusers_b200
     from tinyfusers_b200.attention.attention import BasicTransformerBlock
     c, d = 320, 40
@@ -68,13 +68,15 @@ def test_basic_transformer_block(oracle, quirks):
     x = torch.randn(2, 256, c, generator=g)
     ctx = torch.randn(2, 77, 768, generator=g)
     tinyfusers_b200.set_quirks(quirks)
+    tinyfusers_b200.set_layernorm_strided(strided)
     try:
         blk = BasicTransformerBlock(c, 768, 8, d)
         _load(blk, sd, p)
         out = blk(x.cuda(), ctx.cuda())
     finally:
         tinyfusers_b200.set_quirks(True)
-    assert rel_err(out, oracle.basic_transformer_block(sd, p, x, ctx, 8, d, quirks)) < TOL
+        tinyfusers_b200.set_layernorm_strided(False)
+    assert rel_err(out, oracle.basic_transformer_block(sd, p, x, ctx, 8, d, quirks, strided)) < TOL
 
 
 @pytest.mark.parametrize("c,d,hw", [(320, 40, 16), (640, 80, 8), (1280, 160, 8)])
@@ -102,3 +104,32 @@ def test_up_down_sample(oracle):
     _load(down, sd, "d")
     assert rel_err(up(xu.cuda()), oracle.upsample(sd, "u", xu)) < TOL
     assert rel_err(down(xd.cuda()), oracle.downsample(sd, "d", xd)) < TOL
+
+
+def test_blocks_match_reference_goldens():
+    """CUDA path against the outputs of the reference's OWN Python (tests/golden/reference_outputs.npz)."""
+    import os
+    import numpy as np
+    from tinyfusers_b200.attention.attention import BasicTransformerBlock, SpatialTransformer
+    from tinyfusers_b200.vision.resnet import ResBlock
+    from oracle import ref_ops as R
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+
+    def rnd(seed, *shape):
+        g = np.random.Generator(np.random.Philox(seed))
+        return torch.from_numpy(g.standard_normal(shape, dtype=np.float32))
+
+    sd = {}
+    R.add_spatial_transformer(sd, "st", 320, 768, seed=501)
+    xt, ctx = rnd(502, 2, 64, 320), rnd(503, 2, 77, 768)
+    blk = BasicTransformerBlock(320, 768, 8, 40)
+    _load(blk, sd, "st.transformer_blocks.0")
+    assert rel_err(blk(xt.cuda(), ctx.cuda()), torch.from_numpy(gold["transformer_block_b2"])) < TOL
+    st = SpatialTransformer(320, 768, 8, 40)
+    _load(st, sd, "st")
+    assert rel_err(st(rnd(504, 2, 320, 8, 8).cuda(), ctx.cuda()), torch.from_numpy(gold["spatial_transformer"])) < TOL
+    sd = {}
+    R.add_res_block(sd, "rb", 320, 640, seed=601)
+    rb = ResBlock(320, 1280, 640)
+    _load(rb, sd, "rb")
+    assert rel_err(rb(rnd(602, 2, 320, 8, 8).cuda(), rnd(603, 1, 1280).cuda()), torch.from_numpy(gold["res_block"])) < TOL

@@ -88,8 +88,8 @@ def test_group_norm(oracle, shape):
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 320), (2, 256, 320), (2, 64, 1280), (4, 32, 640), (3, 16, 320)])
-@pytest.mark.parametrize("quirks", [True, False])
-def test_layer_norm(oracle, shape, quirks):
+@pytest.mark.parametrize("strided", [False, True])
+def test_layer_norm(oracle, shape, strided):
     import tinyfusers_b200
     from tinyfusers_b200.ff.layer_norm import LayerNorm
     g = _g(5)
@@ -98,12 +98,12 @@ def test_layer_norm(oracle, shape, quirks):
     gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
     ln = LayerNorm(C)
     ln.weight, ln.bias = gamma.cuda(), beta.cuda()
-    tinyfusers_b200.set_quirks(quirks)
+    tinyfusers_b200.set_layernorm_strided(strided)
     try:
         out = ln(x.cuda())
     finally:
-        tinyfusers_b200.set_quirks(True)
-    assert rel_err(out, oracle.layer_norm(x, gamma, beta, 1e-5, quirks=quirks)) < TOL
+        tinyfusers_b200.set_layernorm_strided(False)
+    assert rel_err(out, oracle.layer_norm(x, gamma, beta, 1e-5, ln_strided=strided)) < TOL
 
 
 @pytest.mark.parametrize("B,NH,Tq,Tk,HS", [(2, 8, 256, 256, 40), (2, 8, 256, 77, 40), (1, 8, 64, 64, 160),

@@ -22,18 +22,29 @@ def test_unet_forward_matches_oracle(oracle, unet_sd, sd_model):
     assert rel_err(out, ref) < 2e-2   # ~700 fp16 kernels deep; per-op bound is 1e-2
 
 
-def test_unet_forward_canonical_mode(oracle, unet_sd, sd_model):
+@pytest.mark.parametrize("quirks,strided", [(False, False), (True, True)])
+def test_unet_forward_other_modes(oracle, unet_sd, sd_model, quirks, strided):
+    """canonical head merge (real checkpoints) and the literal LayerNorm-stride reading"""
     import tinyfusers_b200
     lat, unc, ctx = oracle.make_inputs(1, 32, seed=7, ctx_seed=8)
     x2, c2 = torch.cat([lat, lat]), torch.cat([unc, ctx])
     with torch.no_grad():
-        ref = oracle.unet_forward(unet_sd, x2, [501], c2, quirks=False)
-    tinyfusers_b200.set_quirks(False)
+        ref = oracle.unet_forward(unet_sd, x2, [501], c2, quirks=quirks, ln_strided=strided)
+    tinyfusers_b200.set_quirks(quirks)
+    tinyfusers_b200.set_layernorm_strided(strided)
     try:
         out = sd_model.model.diffusion_model(x2.cuda(), torch.tensor([501]).cuda(), c2.cuda())
     finally:
         tinyfusers_b200.set_quirks(True)
+        tinyfusers_b200.set_layernorm_strided(False)
     assert rel_err(out, ref) < 2e-2
+
+
+def test_unet_matches_reference_golden(sd_model, oracle):
+    """16x16-latent UNet output of the reference's own Python (tests/golden); self-attention at the deepest
+    level has 4 tokens there, below the B200 kernel's 8-token granularity, so the golden is checked at the
+    block level (test_blocks_gpu.py) and through the oracle (tests/test_oracle_golden.py) instead."""
+    pytest.skip("covered transitively: oracle == reference golden (CPU suite), CUDA == oracle (this suite)")
 
 
 def test_sampler_step_matches_oracle(oracle, unet_sd, sd_model):

@@ -5,11 +5,14 @@ classes keep their names, constructor signatures, attribute names (== checkpoint
 signatures; every arithmetic operation runs in hand-written sm_100a CUDA kernels behind the ctypes C-ABI
 in `tinyfusers_b200.native.b200` (include/tinyfusers_b200.h). torch tensors are containers only.
 
-`set_quirks(True)` (default) reproduces the reference literally, including its LayerNorm stride
-declaration at batch > 1 and the CrossAttention head-major reshape (SURVEY.md §8 parity notes);
-`set_quirks(False)` gives canonical Stable Diffusion semantics for real checkpoints.
+`set_quirks(True)` (default) reproduces the reference's CrossAttention head-major reshape
+(attention/attention.py:39, SURVEY.md §8 parity note 2); `set_quirks(False)` gives the canonical head merge for
+real checkpoints. LayerNorm is canonical: real cuDNN executes the reference's layernorm graph only at batch 1
+(where it is canonical) and rejects its stride declaration at batch > 1 (oracle/cudnn_probe.py); the literal
+reading of those strides stays available as `set_layernorm_strided(True)`.
 """
 _QUIRKS = True
+_LN_STRIDED = False
 
 
 def set_quirks(flag: bool):
@@ -19,3 +22,12 @@ def set_quirks(flag: bool):
 
 def get_quirks() -> bool:
     return _QUIRKS
+
+
+def set_layernorm_strided(flag: bool):
+    global _LN_STRIDED
+    _LN_STRIDED = bool(flag)
+
+
+def get_layernorm_strided() -> bool:
+    return _LN_STRIDED

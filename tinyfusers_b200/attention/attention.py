@@ -47,7 +47,7 @@ class CrossAttention:
 
     def __call__(self, x, context=None):
         require_cuda(x, "x")
-        ctx = standalone_context(get_quirks())
+        ctx = standalone_context()
         ctx.arena.reset()
         xa = tokens_to_act(x)
         ca = None if context is None else _pad_context(ctx, context)
@@ -106,7 +106,7 @@ class BasicTransformerBlock:
 
     def __call__(self, x, context=None):
         require_cuda(x, "x")
-        ctx = standalone_context(get_quirks())
+        ctx = standalone_context()
         ctx.arena.reset()
         B, T, C = x.shape
         h = x.to(F16).contiguous().clone()
@@ -154,7 +154,7 @@ class SpatialTransformer:
 
     def __call__(self, x, context=None):
         require_cuda(x, "x")
-        ctx = standalone_context(get_quirks())
+        ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=8)
         ca = _pad_context(ctx, context) if context is not None else None

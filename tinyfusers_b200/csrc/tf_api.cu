@@ -1,6 +1,7 @@
 // tinyfusers_b200 — process-lifetime state of the C-ABI library: error string, device probe,
 // TMA descriptor encoding through the driver entry point, launch bookkeeping.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -30,6 +31,21 @@ int tf_launch_count_add(int n) {
 }
 extern "C" long long tf_launch_count(void) { return g_launches.load(); }
 extern "C" void tf_launch_count_reset(void) { g_launches = 0; }
+
+static int g_pdl = -1;
+int tf_pdl_enabled() {
+  if (g_pdl < 0) {
+    // measured on B200 (round 1): neutral for the UNet step (the next kernel's CTAs cannot become resident while
+    // the previous kernel's CTAs hold the SM's shared memory), so it is opt-in: TINYFUSERS_B200_PDL=1
+    const char* e = getenv("TINYFUSERS_B200_PDL");
+    g_pdl = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl;
+}
+extern "C" int tf_set_pdl(int enable) {
+  g_pdl = enable ? 1 : 0;
+  return TF_OK;
+}
 
 int tf_num_sms() {
   if (g_sms == 0) {

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kAttThreads, (BN == 64) ? 2 : 1)
 tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
+  tf::pdl_trigger();
   const uint32_t raw_u32 = tf::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -105,6 +106,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  tf::pdl_wait();
   const uint32_t tmem_s0 = tmem_base;            // S buffers: columns [0,BN) and [BN,2BN)
   const uint32_t tmem_o = tmem_base + 2 * BN;    // O: dp columns
 
@@ -359,14 +361,14 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
       TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       set64 = true;
     }
-    tf_attention_kernel<64><<<grid, kAttThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+    TF_LAUNCH((tf_attention_kernel<64>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
   } else {
     static bool set128 = false;
     if (!set128) {
       TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       set128 = true;
     }
-    tf_attention_kernel<128><<<grid, kAttThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+    TF_LAUNCH((tf_attention_kernel<128>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
   }
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);

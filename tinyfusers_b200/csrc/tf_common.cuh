@@ -62,6 +62,13 @@ int tf_launch_count_add(int n);  // bookkeeping for bench.py's gpu_launches
 
 static inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch: every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with griddepcontrol.launch_dependents (the next
+// kernel may begin launching / run its prologue) followed, before it touches any global memory, by
+// griddepcontrol.wait (all producer grids complete and visible). In a captured CUDA graph these become
+// programmatic dependency edges, hiding launch latency and kernel prologues between the ~500 launches of a step.
+int tf_pdl_enabled();
+
 // ---------------------------------------------------------------------------------------------
 // Device-side PTX wrappers
 // ---------------------------------------------------------------------------------------------
@@ -74,6 +81,13 @@ static inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
 #endif
 
 namespace tf {
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -329,4 +343,22 @@ union Pack16 {  // 8 halfs <-> one 128-bit vector
 };
 
 }  // namespace tf
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tf_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define TF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)tf_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 #endif  // __CUDACC__

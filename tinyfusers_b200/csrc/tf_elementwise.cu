@@ -10,6 +10,7 @@ namespace {
 // (int64 timestep * float promotes to float64 in CuPy), the result is fp32.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t_dev, const int* __restrict__ idx_dev,
                                           int dim, float max_period, float* __restrict__ out) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= half) return;
@@ -26,6 +27,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t_dev, const
 // row-concatenated weight matrix.
 __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restrict__ W, const float* __restrict__ bias,
                             const float* __restrict__ bias2, float* __restrict__ out, int N, int K, int silu_in) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   extern __shared__ float xs[];
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float v = x[k];
@@ -59,6 +61,7 @@ template <int CIN>
 __global__ void __launch_bounds__(128)
 conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                         __half* __restrict__ out, int NI, int H, int W_, int Cout, int out_stride, int x_images) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   extern __shared__ float ws[];  // [Cout][CIN*9] then [Cout] bias
   float* bs = ws + Cout * CIN * 9;
   for (int i = threadIdx.x; i < Cout * CIN * 9; i += blockDim.x) ws[i] = w[i];
@@ -103,6 +106,7 @@ conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w
 // nearest-neighbour x2 (reference: Upsample.__call__ broadcast+reshape, vision/unet.py:81-83)
 __global__ void upsample2x_kernel(const __half* __restrict__ x, int x_stride, __half* __restrict__ out,
                                   int out_stride, int NI, int H, int W_, int C) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int nvec = C / 8;
   const long total = (long)NI * 2 * H * 2 * W_ * nvec;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -120,6 +124,7 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, int x_stride, __
 template <typename TIn>
 __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, __half* __restrict__ out, int C, int HW,
                                     int out_stride) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -137,6 +142,7 @@ __global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, __half* __restric
 template <typename TOut>
 __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int x_stride, TOut* __restrict__ out, int C,
                                     int HW) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -154,6 +160,7 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int x_stride, 
 // fp32 (rows, C) -> fp16 (rows_pad, C) with zero rows appended per batch (prompt context 77 -> 80 tokens)
 __global__ void pad_tokens_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int T, int Tpad,
                                   int C) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const long total = (long)B * Tpad * C;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
@@ -171,6 +178,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps, int eps_stride, c
                                 float* __restrict__ latent_out, float* __restrict__ e_t_out,
                                 const float* __restrict__ a_t_tab, const float* __restrict__ a_prev_tab,
                                 const int* __restrict__ idx_dev, float guidance, int B, int C, int HW) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int idx = idx_dev ? *idx_dev : 0;
   const float a_t = a_t_tab[idx], a_prev = a_prev_tab[idx];
   const float sqrt_one_minus_at = sqrtf(1.f - a_t);
@@ -194,6 +202,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps, int eps_stride, c
 
 // latent (B,C,H,W) fp32 -> (2B,C,H,W) fp32 duplicated (reference: broadcast_to in sd.py:31); trivial copy
 __global__ void add_int_kernel(int* p, int delta) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   if (threadIdx.x == 0 && blockIdx.x == 0) *p += delta;
 }
 
@@ -209,7 +218,7 @@ extern "C" int tf_timestep_embedding_f32(const float* timesteps_dev, const int* 
                                          float max_period, float* out, void* stream) {
   TF_CHECK_ARG(timesteps_dev && out && dim > 0 && dim % 2 == 0, "tf_timestep_embedding_f32: bad arguments");
   const int half = dim / 2;
-  timestep_embedding_kernel<<<ceil_div_i(half, 128), 128, 0, (cudaStream_t)stream>>>(timesteps_dev, index_dev, dim,
+  TF_LAUNCH(timestep_embedding_kernel, ceil_div_i(half, 128), 128, 0, (cudaStream_t)stream, timesteps_dev, index_dev, dim,
                                                                                     max_period, out);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -221,7 +230,7 @@ extern "C" int tf_gemv_f16w(const float* x, const void* W, const float* bias, co
   TF_CHECK_ARG(x && W && out && N > 0 && K > 0 && K % 8 == 0, "tf_gemv_f16w: bad arguments (N=%d K=%d)", N, K);
   TF_CHECK_ARG(K * sizeof(float) <= 48 * 1024, "tf_gemv_f16w: K too large (%d)", K);
   const int threads = 256;
-  gemv_kernel<<<ceil_div_i(N, threads / 32), threads, K * sizeof(float), (cudaStream_t)stream>>>(
+  TF_LAUNCH(gemv_kernel, ceil_div_i(N, threads / 32), threads, K * sizeof(float), (cudaStream_t)stream, 
       x, (const __half*)W, bias, bias2, out, N, K, silu_input);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -242,7 +251,7 @@ extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const f
     TF_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  conv3x3_smallcin_kernel<4><<<(unsigned)((npix + 31) / 32), 128, smem, (cudaStream_t)stream>>>(
+  TF_LAUNCH((conv3x3_smallcin_kernel<4>), (unsigned)((npix + 31) / 32), 128, smem, (cudaStream_t)stream, 
       x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride, x_images);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -254,7 +263,7 @@ extern "C" int tf_upsample_nearest2x_nhwc_f16(const void* x, int x_pixel_stride,
   TF_CHECK_ARG(x && out && C % 8 == 0 && x_pixel_stride % 8 == 0 && out_pixel_stride % 8 == 0,
                "tf_upsample_nearest2x_nhwc_f16: bad arguments");
   const long total = (long)NI * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, x_pixel_stride,
+  TF_LAUNCH(upsample2x_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)x, x_pixel_stride,
                                                                             (__half*)out, out_pixel_stride, NI, H, W, C);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -266,10 +275,10 @@ extern "C" int tf_nchw_to_nhwc_f16(const void* x, int x_is_f32, void* out, int N
   TF_CHECK_ARG(x && out && NI > 0 && C > 0 && HW > 0 && out_pixel_stride >= C, "tf_nchw_to_nhwc_f16: bad arguments");
   dim3 grid(ceil_div_i(HW, 32), ceil_div_i(C, 32), NI), block(32, 8);
   if (x_is_f32)
-    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, (__half*)out, C, HW,
+    TF_LAUNCH((nchw_to_nhwc_kernel<float>), grid, block, 0, (cudaStream_t)stream, (const float*)x, (__half*)out, C, HW,
                                                                          out_pixel_stride);
   else
-    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, C, HW,
+    TF_LAUNCH((nchw_to_nhwc_kernel<__half>), grid, block, 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, C, HW,
                                                                           out_pixel_stride);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -281,10 +290,10 @@ extern "C" int tf_nhwc_to_nchw(const void* x, int x_pixel_stride, void* out, int
   TF_CHECK_ARG(x && out && NI > 0 && C > 0 && HW > 0 && x_pixel_stride >= C, "tf_nhwc_to_nchw: bad arguments");
   dim3 grid(ceil_div_i(HW, 32), ceil_div_i(C, 32), NI), block(32, 8);
   if (out_is_f32)
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, x_pixel_stride, (float*)out,
+    TF_LAUNCH((nhwc_to_nchw_kernel<float>), grid, block, 0, (cudaStream_t)stream, (const __half*)x, x_pixel_stride, (float*)out,
                                                                          C, HW);
   else
-    nhwc_to_nchw_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, x_pixel_stride,
+    TF_LAUNCH((nhwc_to_nchw_kernel<__half>), grid, block, 0, (cudaStream_t)stream, (const __half*)x, x_pixel_stride,
                                                                           (__half*)out, C, HW);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -294,7 +303,7 @@ extern "C" int tf_nhwc_to_nchw(const void* x, int x_pixel_stride, void* out, int
 extern "C" int tf_pad_tokens_f32_to_f16(const float* x, void* out, int B, int T, int Tpad, int C, void* stream) {
   TF_CHECK_ARG(x && out && B > 0 && T > 0 && Tpad >= T && C > 0, "tf_pad_tokens_f32_to_f16: bad arguments");
   const long total = (long)B * Tpad * C;
-  pad_tokens_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__half*)out, B, T, Tpad, C);
+  TF_LAUNCH(pad_tokens_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, x, (__half*)out, B, T, Tpad, C);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
@@ -308,7 +317,7 @@ extern "C" int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride,
                "tf_cfg_ddim_step_f32: null pointer");
   TF_CHECK_ARG(B > 0 && C > 0 && HW > 0 && eps_pixel_stride >= C, "tf_cfg_ddim_step_f32: bad dims");
   const long total = (long)B * C * HW;
-  cfg_ddim_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  TF_LAUNCH(cfg_ddim_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, 
       eps_nhwc, eps_pixel_stride, latent, latent_out, e_t_out, alphas_dev, alphas_prev_dev, index_dev, guidance, B, C,
       HW);
   TF_LAUNCH_CHECK();
@@ -318,7 +327,7 @@ extern "C" int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride,
 
 extern "C" int tf_add_int(int* p_dev, int delta, void* stream) {
   TF_CHECK_ARG(p_dev, "tf_add_int: null pointer");
-  add_int_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p_dev, delta);
+  TF_LAUNCH(add_int_kernel, 1, 32, 0, (cudaStream_t)stream, p_dev, delta);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
@@ -332,6 +341,7 @@ extern "C" int tf_add_int(int* p_dev, int delta, void* stream) {
 namespace {
 template <typename T>
 __global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ out, long n, int op) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float v = (float)x[i];
     float r;
@@ -354,9 +364,9 @@ extern "C" int tf_unary(const void* x, void* out, long long n, int op, int is_f3
   const long cap = (long)tf_num_sms() * 8;
   const int blocks = (int)(b < cap ? b : cap);
   if (is_f32)
-    unary_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>((const float*)x, (float*)out, n, op);
+    TF_LAUNCH((unary_kernel<float>), blocks, threads, 0, (cudaStream_t)stream, (const float*)x, (float*)out, n, op);
   else
-    unary_kernel<__half><<<blocks, threads, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)out, n, op);
+    TF_LAUNCH((unary_kernel<__half>), blocks, threads, 0, (cudaStream_t)stream, (const __half*)x, (__half*)out, n, op);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
@@ -365,6 +375,7 @@ extern "C" int tf_unary(const void* x, void* out, long long n, int op, int is_f3
 namespace {
 __global__ void nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ x, int x_stride, float* __restrict__ out, int NI,
                                             int C, int HW) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const long total = (long)NI * C * HW;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int p = (int)(i % HW);
@@ -377,6 +388,7 @@ __global__ void nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ x, int x_s
 __global__ void ddim_kernel(const float* __restrict__ x, const float* __restrict__ e_t, const float* __restrict__ a_t_p,
                             const float* __restrict__ a_prev_p, float* __restrict__ x_prev, float* __restrict__ pred_x0,
                             long n) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const float a_t = *a_t_p, a_prev = *a_prev_p;
   const float s1 = sqrtf(1.f - a_t), is = 1.f / sqrtf(a_t), sp = sqrtf(a_prev), dp = sqrtf(1.f - a_prev);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -392,7 +404,7 @@ extern "C" int tf_nhwc_f32_to_nchw_f32(const float* x, int x_pixel_stride, float
                                        void* stream) {
   TF_CHECK_ARG(x && out && NI > 0 && C > 0 && HW > 0 && x_pixel_stride >= C, "tf_nhwc_f32_to_nchw_f32: bad arguments");
   const long total = (long)NI * C * HW;
-  nhwc_f32_to_nchw_f32_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, out, NI, C, HW);
+  TF_LAUNCH(nhwc_f32_to_nchw_f32_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, x, x_pixel_stride, out, NI, C, HW);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
@@ -401,7 +413,7 @@ extern "C" int tf_nhwc_f32_to_nchw_f32(const float* x, int x_pixel_stride, float
 extern "C" int tf_ddim_step_f32(const float* x, const float* e_t, const float* a_t_dev, const float* a_prev_dev,
                                 float* x_prev, float* pred_x0, long long n, void* stream) {
   TF_CHECK_ARG(x && e_t && a_t_dev && a_prev_dev && x_prev && n > 0, "tf_ddim_step_f32: bad arguments");
-  ddim_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, e_t, a_t_dev, a_prev_dev, x_prev, pred_x0, n);
+  TF_LAUNCH(ddim_kernel, ew_blocks(n, 256), 256, 0, (cudaStream_t)stream, x, e_t, a_t_dev, a_prev_dev, x_prev, pred_x0, n);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  tf::pdl_trigger();
   const long long t_entry = clock64();
   const uint32_t raw_u32 = tf::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
@@ -126,6 +127,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  tf::pdl_wait();   // barriers / TMEM / descriptors were set up while the producer kernels drained
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 16 : nullptr;
@@ -231,7 +233,6 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // swizzle of 16-byte chunk j in row r (row = lane): fp32 rows are 128 B (SW128), fp16 64 B (SW64), GEGLU 32 B (SW32)
     const uint32_t row_bytes = out_f32 ? 128u : (geglu ? 32u : 64u);
     const uint32_t swz = out_f32 ? (uint32_t)(lane & 7) : (geglu ? (uint32_t)((lane >> 2) & 1) : (uint32_t)((lane >> 1) & 3));
-    const uint32_t srow = stg + lane * row_bytes;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -287,8 +288,14 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tf::tcgen05_fence_before();
           tf::mbar_arrive(tempty_bar(as));
         }
-        // the previous chunk's TMA store must have finished reading the staging block
-        if (lane == 0) tf::tma_store_wait_read<0>();
+        // fp16 / GEGLU blocks are <= 2 KB: two staging halves alternate, so only the store issued two chunks
+        // ago must have finished reading shared memory; fp32 blocks use the whole 4 KB
+        const uint32_t stg_c = stg + (out_f32 ? 0u : (uint32_t)((c >> 5) & 1) * 2048u);
+        const uint32_t srow = stg_c + lane * row_bytes;
+        if (lane == 0) {
+          if (out_f32) tf::tma_store_wait_read<0>();
+          else tf::tma_store_wait_read<1>();
+        }
         __syncwarp();
         if (geglu) {
           // packed columns: [c, c+16) = value, [c+16, c+32) = gate  (tinyfusers_b200/packing.py: geglu_pack)
@@ -347,11 +354,11 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // split-K partials live in a tensor with one extra (split) dimension, so a tile's overhang is clipped
           // per split instead of spilling into the next split's slab
           if (p.is_conv) {
-            if (partial) tf::tma_store_5d(&tmC, stg, col, sc1, sc2, sc3, split);
-            else tf::tma_store_4d(&tmC, stg, col, sc1, sc2, sc3);
+            if (partial) tf::tma_store_5d(&tmC, stg_c, col, sc1, sc2, sc3, split);
+            else tf::tma_store_4d(&tmC, stg_c, col, sc1, sc2, sc3);
           } else {
-            if (partial) tf::tma_store_3d(&tmC, stg, col, sc1, split);
-            else tf::tma_store_2d(&tmC, stg, col, sc1);
+            if (partial) tf::tma_store_3d(&tmC, stg_c, col, sc1, split);
+            else tf::tma_store_2d(&tmC, stg_c, col, sc1);
           }
           tf::tma_store_commit();
         }
@@ -382,6 +389,7 @@ __global__ void tf_splitk_reduce_kernel(const float* __restrict__ partial, int s
                                         const float* __restrict__ bias,
                                         const __half* __restrict__ residual, int ldr, void* out,
                                         int ldc, int out_f32) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const size_t total = (size_t)M * N;
   if (idx >= total) return;
@@ -481,14 +489,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
   p.timeline = g_timeline;
-  tf_gemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, p);
+  TF_LAUNCH(tf_gemm_kernel, grid, kThreads, smem, stream, tmA, tmB, tmC, p);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   if (p.splits > 1) {
     const size_t total = (size_t)p.M * p.N;
     const int threads = 256;
     const int blocks = (int)((total / 4 + threads - 1) / threads);
-    tf_splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(
+    TF_LAUNCH(tf_splitk_reduce_kernel, blocks, threads, 0, stream, 
         p.partial, p.splits, p.M, p.N, p.bias, p.residual, p.ldr, p.out, p.ldc,
         (p.flags & TF_EPI_OUT_F32) ? 1 : 0);
     TF_LAUNCH_CHECK();

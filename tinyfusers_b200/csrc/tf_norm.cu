@@ -25,6 +25,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, int x_stride, int c_off,
                                 int cpg, int G, int pix_per_block, float2* __restrict__ partial) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   extern __shared__ float gsm[];  // [npl][Cs] sums, [npl][Cs] squares, then [Cs] x 2 channel totals
   const int n = blockIdx.y;
   const int nvec = Cs >> 3;
@@ -79,6 +80,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, in
 __global__ void gn_finalize_kernel(const float2* __restrict__ partial_a, const float2* __restrict__ partial_b, int chunks,
                                    int NI, int G, int split_group_lo, int split_group_hi, float inv_count, float eps,
                                    float2* __restrict__ stats) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int n = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (g >= G) return;
   float a = 0.f, b = 0.f;
@@ -103,6 +105,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, in
                                 int cpg, int G, int pix_per_block, const float2* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 __half* __restrict__ out, int out_stride) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int n = blockIdx.y;
   const int nvec = Cs >> 3;
   const int v = threadIdx.x % nvec;
@@ -155,6 +158,7 @@ static int gn_block_threads(int Cs) {
 template <int MAXV>  // max 8-half vectors per lane
 __global__ void ln_rows_kernel(const __half* __restrict__ x, __half* __restrict__ out, int rows, int C,
                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -218,6 +222,7 @@ template <int IL, int THREADS, int MAXV>
 __global__ void __launch_bounds__(THREADS)
 ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   __shared__ float red[2][THREADS / 32][IL];
   const int nvec = (C * IL) >> 3;
   const __half* xr = x + (size_t)blockIdx.x * C * IL;
@@ -298,11 +303,11 @@ static bool launch_ln_block(const __half* x, __half* out, int chunk_rows, int C,
                             float eps, cudaStream_t stream) {
   const int nvec = C * IL / 8;
   if ((C * IL) % 8 != 0) return false;
-  if (nvec <= 64) ln_block_kernel<IL, 32, 2><<<chunk_rows, 32, 0, stream>>>(x, out, C, gamma, beta, eps);
-  else if (nvec <= 128) ln_block_kernel<IL, 64, 2><<<chunk_rows, 64, 0, stream>>>(x, out, C, gamma, beta, eps);
-  else if (nvec <= 256) ln_block_kernel<IL, 128, 2><<<chunk_rows, 128, 0, stream>>>(x, out, C, gamma, beta, eps);
-  else if (nvec <= 512) ln_block_kernel<IL, 128, 4><<<chunk_rows, 128, 0, stream>>>(x, out, C, gamma, beta, eps);
-  else if (nvec <= 1024) ln_block_kernel<IL, 256, 4><<<chunk_rows, 256, 0, stream>>>(x, out, C, gamma, beta, eps);
+  if (nvec <= 64) TF_LAUNCH((ln_block_kernel<IL, 32, 2>), chunk_rows, 32, 0, stream, x, out, C, gamma, beta, eps);
+  else if (nvec <= 128) TF_LAUNCH((ln_block_kernel<IL, 64, 2>), chunk_rows, 64, 0, stream, x, out, C, gamma, beta, eps);
+  else if (nvec <= 256) TF_LAUNCH((ln_block_kernel<IL, 128, 2>), chunk_rows, 128, 0, stream, x, out, C, gamma, beta, eps);
+  else if (nvec <= 512) TF_LAUNCH((ln_block_kernel<IL, 128, 4>), chunk_rows, 128, 0, stream, x, out, C, gamma, beta, eps);
+  else if (nvec <= 1024) TF_LAUNCH((ln_block_kernel<IL, 256, 4>), chunk_rows, 256, 0, stream, x, out, C, gamma, beta, eps);
   else return false;
   return true;
 }
@@ -311,6 +316,7 @@ static bool launch_ln_block(const __half* x, __half* out, int chunk_rows, int C,
 __global__ void ln_il_generic_kernel(const __half* __restrict__ x, __half* __restrict__ out, int trow, int C,
                                      int IL, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float eps) {
+  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= trow * IL) return;
@@ -371,14 +377,14 @@ extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, 
     const int npl = threads / (cs[i] / 8);
     const size_t smem = sizeof(float) * ((size_t)2 * npl * cs[i] + 2 * cs[i]);
     TF_CHECK_ARG(smem <= 48 * 1024, "tf_groupnorm_nhwc_f16: channel slice of %d too wide for the statistics kernel", cs[i]);
-    gn_stats_kernel<<<grid, threads, smem, stream>>>(xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, partial[i]);
+    TF_LAUNCH(gn_stats_kernel, grid, threads, smem, stream, xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, partial[i]);
     TF_LAUNCH_CHECK();
   }
-  gn_finalize_kernel<<<NI, 32 * groups, 0, stream>>>(partial[0], nsrc == 2 ? partial[1] : nullptr, chunks, NI, groups,
+  TF_LAUNCH(gn_finalize_kernel, NI, 32 * groups, 0, stream, partial[0], nsrc == 2 ? partial[1] : nullptr, chunks, NI, groups,
                                             nsrc == 2 ? Cx / cpg : 0, (Cx - 1) / cpg, inv_count, eps, stats);
   TF_LAUNCH_CHECK();
   for (int i = 0; i < nsrc; ++i) {
-    gn_apply_kernel<<<grid, gn_block_threads(cs[i]), 0, stream>>>(
+    TF_LAUNCH(gn_apply_kernel, grid, gn_block_threads(cs[i]), 0, stream, 
         xs[i], HW, cs[i], st[i], off[i], cpg, groups, ppb, stats, gamma, beta, apply_silu,
         reinterpret_cast<__half*>(out), out_pixel_stride);
     TF_LAUNCH_CHECK();
@@ -405,9 +411,9 @@ extern "C" int tf_layernorm_f16(const void* x, void* out, int rows, int C, const
   if (!done) {
     if (interleave == 1) {
       TF_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "tf_layernorm_f16: C must be a multiple of 8 and <= 2048");
-      ln_rows_kernel<8><<<ceil_div_i(rows, wpb), threads, 0, stream>>>(xh, oh, rows, C, gamma, beta, eps);
+      TF_LAUNCH((ln_rows_kernel<8>), ceil_div_i(rows, wpb), threads, 0, stream, xh, oh, rows, C, gamma, beta, eps);
     } else {
-      ln_il_generic_kernel<<<ceil_div_i(rows, wpb), threads, 0, stream>>>(xh, oh, chunk_rows, C, interleave, gamma,
+      TF_LAUNCH(ln_il_generic_kernel, ceil_div_i(rows, wpb), threads, 0, stream, xh, oh, chunk_rows, C, interleave, gamma,
                                                                          beta, eps);
     }
   }

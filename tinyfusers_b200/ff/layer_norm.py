@@ -1,15 +1,16 @@
 """LayerNorm with the reference's signatures (reference: tinyfusers/ff/layer_norm.py:8-49).
 
-The reference declares NHWC-style strides [B*T*C, 1, B*C, B] for its contiguous (1,B,T,C) buffer
-(layer_norm.py:10), so at batch B > 1 cuDNN normalises the buffer viewed as (T, C, B) over C. With
-quirks enabled (default) the kernel is launched with interleave = B to reproduce that; with quirks off
-it is the canonical LayerNorm over the last dimension."""
+Canonical LayerNorm over the last dimension: that is what real cuDNN computes for the reference's graph at
+batch 1, the only case it executes — at batch > 1 it rejects the reference's stride declaration
+[B*T*C, 1, B*C, B] (layer_norm.py:10) with CUDNN_STATUS_NOT_SUPPORTED (oracle/cudnn_probe.py). The literal
+reading of those strides (view the buffer as (T, C, B), normalise over C) is available through
+`tinyfusers_b200.set_layernorm_strided(True)` and runs the same kernel with interleave = B."""
 from typing import Tuple, Union
 
 import numpy as np
 import torch
 
-from .. import get_quirks, packing
+from .. import get_layernorm_strided, packing
 from ..runtime import F16, F32, require_cuda, standalone_context
 from ..storage.state import _default_device
 
@@ -23,7 +24,7 @@ def layer_norm(x_gpu, scale_gpu, bias_gpu, epsilon_cpu):
     out = torch.empty_like(xh)
     g = scale_gpu.reshape(-1).to(F32).contiguous()
     b = bias_gpu.reshape(-1).to(F32).contiguous()
-    il = B if get_quirks() else 1
+    il = B if get_layernorm_strided() else 1
     ctx.layernorm(xh.data_ptr(), out.data_ptr(), B * T, C, g.data_ptr(), b.data_ptr(), float(np.asarray(epsilon_cpu).reshape(-1)[0]), il)
     return out.to(F32)
 
@@ -54,4 +55,4 @@ class LayerNorm:
     def _run(self, ctx, x_ptr, out_ptr, B, T, C):
         g, b = self._packed()
         ctx.layernorm(x_ptr, out_ptr, B * T, C, g.data_ptr(), b.data_ptr(), float(self.eps.reshape(-1)[0]),
-                      B if ctx.quirks else 1)
+                      B if ctx.ln_strided else 1)

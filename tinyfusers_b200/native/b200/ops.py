@@ -24,6 +24,7 @@ _SIGNATURES = {
     "tf_version": (c_int, []),
     "tf_init": (c_int, [c_int]),
     "tf_last_error": (ctypes.c_char_p, []),
+    "tf_set_pdl": (c_int, [c_int]),
     "tf_launch_count": (c_longlong, []),
     "tf_launch_count_reset": (None, []),
     "tf_gemm_set_tuning": (c_int, [c_int, c_int]),

@@ -99,14 +99,16 @@ class Arena:
 class Context:
     """Execution context handed down the module tree on the fast path."""
 
-    def __init__(self, device, quirks=True):
+    def __init__(self, device, quirks=True, ln_strided=False):
         self.device = torch.device(device)
-        self.quirks = quirks
+        self.quirks = quirks            # CrossAttention head-major reshape (reference attention.py:39)
+        self.ln_strided = ln_strided    # literal reading of the reference's LayerNorm stride declaration
         self.arena = Arena()
         self.ws_bytes = 192 << 20
         self.ws = None
         self.dry = False
         self.only = None           # bench instrumentation: if a set, only kernels of these kinds are launched
+        self.prof = None           # dev instrumentation: list of (key, start_event, end_event) per kernel call
         # per-forward values set by the UNet
         self.emb_bias = None       # dict: id(ResBlock) -> device pointer of its (conv bias + emb) fp32 vector
         self.context = None        # Act view of the zero-padded fp16 prompt context (B, Tpad, 768)
@@ -126,6 +128,16 @@ class Context:
         return self.arena.alloc(4 * numel)
 
     # -- kernel wrappers (each is one C-ABI call) ---------------------------------------------------
+    def _timed(self, key, fn):
+        if self.prof is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.prof.append((key, e0, e1))
+        return r
+
     def skip(self, kind):
         """True when the kernel must not be launched (arena dry run, or bench's per-class timing filter)."""
         return self.dry or (self.only is not None and kind not in self.only)
@@ -133,17 +145,19 @@ class Context:
     def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None):
         if self.skip("gemm"):
             return
-        st = b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
-                              residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
+        st = self._timed(("gemm", M, N, K, flags, residual_ptr is not None),
+                         lambda: b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
+                                                  residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr()))
         b200.check(st, "tf_gemm_f16")
 
     def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0):
         if self.skip("gemm"):
             return
-        st = b200.tf_conv2d_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr, out.stride, bias,
-                                     residual.ptr if residual is not None else None,
-                                     residual.stride if residual is not None else 0, flags, self.ws.data_ptr(),
-                                     self.ws_bytes, stream_ptr())
+        st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None),
+                         lambda: b200.tf_conv2d_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr,
+                                                         out.stride, bias, residual.ptr if residual is not None else None,
+                                                         residual.stride if residual is not None else 0, flags,
+                                                         self.ws.data_ptr(), self.ws_bytes, stream_ptr()))
         b200.check(st, "tf_conv2d_nhwc_f16")
 
     def groupnorm(self, x, out, gamma, beta, eps, silu, groups=32):
@@ -152,14 +166,17 @@ class Context:
         self.arena.release(mark)                          # stream order keeps the reuse safe
         if self.skip("norm"):
             return
-        st = b200.tf_groupnorm_nhwc_f16(x.ptr, x.stride, x.c, None, 0, 0, out.ptr, out.stride, x.n, x.h * x.w, groups,
-                                        gamma, beta, eps, 1 if silu else 0, stats, stream_ptr())
+        st = self._timed(("groupnorm", x.n, x.h * x.w, x.c),
+                         lambda: b200.tf_groupnorm_nhwc_f16(x.ptr, x.stride, x.c, None, 0, 0, out.ptr, out.stride, x.n,
+                                                            x.h * x.w, groups, gamma, beta, eps, 1 if silu else 0, stats,
+                                                            stream_ptr()))
         b200.check(st, "tf_groupnorm_nhwc_f16")
 
     def layernorm(self, x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave):
         if self.skip("norm"):
             return
-        st = b200.tf_layernorm_f16(x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave, stream_ptr())
+        st = self._timed(("layernorm", rows, C, interleave),
+                         lambda: b200.tf_layernorm_f16(x_ptr, out_ptr, rows, C, gamma, beta, eps, interleave, stream_ptr()))
         b200.check(st, "tf_layernorm_f16")
 
     def attention(self, q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, B, NH, Tq, Tk, Tk_pad, d, dp, head_major):
@@ -169,8 +186,9 @@ class Context:
             osb, osh, ost = NH * Tq * d, Tq * d, d
         else:
             osb, osh, ost = Tq * NH * d, d, NH * d
-        st = b200.tf_attention_f16(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, osb, osh, ost, B, NH, Tq, Tk, Tk_pad,
-                                   d, dp, 1.0 / math.sqrt(d), stream_ptr())
+        st = self._timed(("attention", B, NH, Tq, Tk, d),
+                         lambda: b200.tf_attention_f16(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, osb, osh, ost, B, NH, Tq,
+                                                       Tk, Tk_pad, d, dp, 1.0 / math.sqrt(d), stream_ptr()))
         b200.check(st, "tf_attention_f16")
 
     def upsample2x(self, x, out):
@@ -222,14 +240,16 @@ def new_act_tensor(n, h, w, c, device="cuda"):
 _standalone_ctx = {}
 
 
-def standalone_context(quirks=True):
+def standalone_context(quirks=None):
     """Context for per-op calls outside a UNet forward (allocates from torch, not the arena)."""
+    from . import get_layernorm_strided, get_quirks
     dev = torch.cuda.current_device()
-    key = (dev, quirks)
+    quirks = get_quirks() if quirks is None else quirks
+    key = (dev, quirks, get_layernorm_strided())
     ctx = _standalone_ctx.get(key)
     if ctx is None:
         b200.init(dev)
-        ctx = Context(torch.device("cuda", dev), quirks)
+        ctx = Context(torch.device("cuda", dev), quirks, get_layernorm_strided())
         ctx.ensure_workspaces()
         ctx.arena.reserve(int(os.environ.get("TINYFUSERS_B200_SCRATCH_MB", "1024")) << 20, ctx.device)
         _standalone_ctx[key] = ctx

@@ -14,7 +14,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from .. import get_quirks
+from .. import get_layernorm_strided, get_quirks
 from ..native.b200.ops import b200
 from ..runtime import F32, require_cuda, stream_ptr
 from ..vision.unet import UNetModel
@@ -87,7 +87,7 @@ class StableDiffusion:
 
     def _sampler(self, latent_shape, ctx_tokens):
         B, C, H, W = latent_shape
-        key = (torch.cuda.current_device(), B, H, W, ctx_tokens, get_quirks())
+        key = (torch.cuda.current_device(), B, H, W, ctx_tokens, get_quirks(), get_layernorm_strided())
         s = self._samplers.get(key)
         if s is None:
             s = SamplerEngine(self.model.diffusion_model, B, H, W, ctx_tokens)

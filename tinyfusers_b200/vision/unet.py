@@ -13,7 +13,7 @@ Fast path of one forward (batch 2B for CFG):
 import numpy as np
 import torch
 
-from .. import get_quirks, packing
+from .. import get_layernorm_strided, get_quirks, packing
 from ..attention.attention import SpatialTransformer
 from ..ff.group_norm import GroupNorm
 from ..ff.linear import Linear
@@ -123,10 +123,10 @@ class UNetModel:
 
     def engine(self, n_images, H, W, n_src=None, ctx_tokens=77):
         n_src = n_images if n_src is None else n_src
-        key = (torch.cuda.current_device(), n_images, H, W, n_src, ctx_tokens, get_quirks())
+        key = (torch.cuda.current_device(), n_images, H, W, n_src, ctx_tokens, get_quirks(), get_layernorm_strided())
         eng = self._engines.get(key)
         if eng is None:
-            eng = UNetEngine(self, n_images, H, W, n_src, ctx_tokens, get_quirks())
+            eng = UNetEngine(self, n_images, H, W, n_src, ctx_tokens, get_quirks(), get_layernorm_strided())
             self._engines[key] = eng
         return eng
 
@@ -271,11 +271,11 @@ class _LatentView:
 class UNetEngine:
     """Static buffers + arena + (optionally) a captured CUDA graph for one (batch, H, W) configuration."""
 
-    def __init__(self, model, n, H, W, n_src, ctx_tokens, quirks):
+    def __init__(self, model, n, H, W, n_src, ctx_tokens, quirks, ln_strided=False):
         dev = torch.device("cuda", torch.cuda.current_device())
         b200.init(dev.index)
         self.model, self.n, self.H, self.W, self.n_src, self.ctx_tokens = model, n, H, W, n_src, ctx_tokens
-        self.ctx = Context(dev, quirks)
+        self.ctx = Context(dev, quirks, ln_strided)
         self.ctx.ensure_workspaces()
         self.latent = torch.zeros((n_src, 4, H, W), dtype=F32, device=dev)
         self.context = torch.zeros((n, ctx_tokens, 768), dtype=F32, device=dev)
