@@ -65,6 +65,22 @@ int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel
                        const void* residual, int ldr, int flags, void* workspace, size_t ws_bytes,
                        void* stream);
 
+/* Same as tf_gemm_f16 / tf_conv2d_nhwc_f16, and additionally leaves the GroupNorm statistics of the fp16 OUTPUT in
+ * gn_stats[image][slot][unit] = {sum, sumsq} (float2; slot = 32 consecutive rows of one image, unit = gn_unit
+ * consecutive channels), computed in the epilogue from the rounded values, so that the GroupNorm that consumes
+ * this tensor (tf_groupnorm_fused_nhwc_f16) is ONE launch instead of statistics + finalize + apply.
+ * Replaces the same reference calls as the plain versions; the statistics replace the mean / var passes of
+ * group_norm (tinyfusers/ff/group_norm.py:5-10). gn_stats: NI * (rows_per_image/32) * (N/gn_unit) float2.
+ * Needs rows_per_image % 32 == 0, N % gn_unit == 0, lcm(32, gn_unit) <= 256 and the plain fp16 epilogue;
+ * tf_gn_stats_supported() answers whether a geometry qualifies (TF_ERR_UNSUPPORTED otherwise). */
+int tf_gemm_gn_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M, int N, int K,
+                   const float* bias, const void* residual, int ldr, int flags, void* workspace, size_t ws_bytes,
+                   void* gn_stats, int gn_unit, int rows_per_image, void* stream);
+int tf_conv2d_nhwc_gn_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w, int Cout,
+                          int ksize, int stride, void* out, int ldc, const float* bias, const void* residual, int ldr,
+                          int flags, void* workspace, size_t ws_bytes, void* gn_stats, int gn_unit, void* stream);
+int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_conv3x3);
+
 /* test / tuning hook: force the N tile and split-K factor of the next GEMM/conv calls (0 = auto) */
 int tf_gemm_set_tuning(int force_bn, int force_splits);
 /* debug hook: per-CTA clock64 stamps of the next GEMM/conv launches ([grid][8] int64; NULL = off) */
@@ -85,6 +101,16 @@ int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void*
                           int Cx2, void* out, int out_pixel_stride, int NI, int HW, int groups,
                           const float* gamma, const float* beta, float eps, int apply_silu, float* stats_ws,
                           void* stream);
+
+/* GroupNorm (+ optional SiLU) in ONE launch for inputs whose producer left statistics (tf_gemm_gn_f16 /
+ * tf_conv2d_nhwc_gn_f16): folds the slots, finalises mean / rstd per (image, group) and normalises. Same
+ * two-source concatenation semantics as tf_groupnorm_nhwc_f16; each source has its own unit size, and unit
+ * boundaries must coincide with group and source boundaries ((C/groups) % unit == 0, Cx % x2_unit == 0).
+ * Replaces: group_norm / GroupNorm.__call__ + Tensor.silu (tinyfusers/ff/group_norm.py:3-21). */
+int tf_groupnorm_fused_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void* x_stats, int x_unit,
+                                const void* x2, int x2_pixel_stride, int Cx2, const void* x2_stats, int x2_unit,
+                                void* out, int out_pixel_stride, int NI, int HW, int groups, const float* gamma,
+                                const float* beta, float eps, int apply_silu, void* stream);
 
 /* LayerNorm over the last dim of a (rows, C) fp16 matrix; gamma/beta fp32.
  * Replaces: layer_norm / LayerNorm.__call__ (cuDNN layernorm graph, rebuilt per call)

@@ -174,3 +174,78 @@ def test_ddim_and_alphas(oracle):
     xp, p0 = StableDiffusion.get_x_prev_and_pred_x0(sd, x.cuda(), e.cuda(), a_t.cuda(), a_prev.cuda())
     rxp, rp0 = oracle.get_x_prev_and_pred_x0(x, e, a_t, a_prev)
     assert rel_err(xp, rxp) < 1e-5 and rel_err(p0, rp0) < 1e-5
+
+
+@pytest.mark.parametrize("kind,n,h,w,cin,cout,splits", [
+    ("conv3", 2, 32, 32, 320, 320, 0), ("conv3", 2, 16, 16, 640, 1280, 0), ("conv3", 2, 8, 8, 1280, 1280, 4),
+    ("conv1", 2, 32, 32, 320, 640, 0), ("conv3s2", 2, 32, 32, 320, 320, 0), ("conv1", 2, 8, 8, 2560, 1280, 3),
+])
+def test_producer_statistics_and_fused_groupnorm(oracle, kind, n, h, w, cin, cout, splits):
+    """tf_conv2d_nhwc_gn_f16 / tf_gemm_gn_f16 leave per-slot {sum, sumsq}; tf_groupnorm_fused_nhwc_f16 consumes them.
+    Checked against (a) the sums of the produced fp16 tensor and (b) the oracle's GroupNorm + SiLU of the oracle conv."""
+    import torch.nn.functional as F
+    from tinyfusers_b200 import packing
+    from tinyfusers_b200.native.b200.ops import b200
+    from tinyfusers_b200.runtime import gn_unit, standalone_context, stream_ptr
+    ctx = standalone_context()
+    g = _g(11)
+    k = 1 if kind == "conv1" else 3
+    stride = 2 if kind == "conv3s2" else 1
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, generator=g) * 0.1
+    gamma, beta = 1 + 0.1 * torch.randn(cout, generator=g), 0.1 * torch.randn(cout, generator=g)
+    ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+    xa = x.permute(0, 2, 3, 1).contiguous().half().cuda()
+    wp = (packing.conv3x3_weight(wt.cuda(), 64, 8) if k == 3 else packing.conv1x1_weight(wt.cuda(), 8))
+    out = torch.empty(n, ho, wo, cout, dtype=torch.half, device="cuda")
+    unit = gn_unit(cout)
+    assert b200.tf_gn_stats_supported(n, ho, wo, cout, unit, 1 if k == 3 else 0)
+    slots = ho * wo // 32
+    stats = torch.full((n, slots, cout // unit, 2), float("nan"), device="cuda")
+    bc = bias.cuda()
+    b200.tf_gemm_set_tuning(0, splits)
+    try:
+        st = b200.tf_conv2d_nhwc_gn_f16(xa.data_ptr(), n, h, w, cin, cin, wp.data_ptr(), cout, k, stride, out.data_ptr(), cout,
+                                        bc.data_ptr(), None, 0, 0, ctx.ws.data_ptr(), ctx.ws_bytes, stats.data_ptr(), unit,
+                                        stream_ptr())
+    finally:
+        b200.tf_gemm_set_tuning(0, 0)
+    b200.check(st, "tf_conv2d_nhwc_gn_f16")
+    torch.cuda.synchronize()
+    o32 = out.float()
+    got = stats.sum(dim=1)                                                   # (n, units, 2)
+    want_s = o32.reshape(n, ho * wo, cout // unit, unit).sum(dim=(1, 3))
+    want_q = (o32 * o32).reshape(n, ho * wo, cout // unit, unit).sum(dim=(1, 3))
+    assert torch.isfinite(stats).all()
+    assert rel_err(got[..., 0], want_s) < 1e-4 and rel_err(got[..., 1], want_q) < 1e-4
+    y = torch.empty_like(out)
+    gc, bt = gamma.cuda(), beta.cuda()
+    st = b200.tf_groupnorm_fused_nhwc_f16(out.data_ptr(), cout, cout, stats.data_ptr(), unit, None, 0, 0, None, 1,
+                                          y.data_ptr(), cout, n, ho * wo, 32, gc.data_ptr(), bt.data_ptr(), 1e-5, 1, stream_ptr())
+    b200.check(st, "tf_groupnorm_fused_nhwc_f16")
+    ref = F.silu(F.group_norm(oracle.conv2d(x, wt, bias, stride=(stride, stride), padding=[k // 2, k // 2]), 32, gamma, beta, 1e-5))
+    assert rel_err(y.permute(0, 3, 1, 2), ref) < TOL
+
+
+def test_fused_groupnorm_two_sources(oracle):
+    """Channel concatenation of two producers (the UNet's skip connections): 640 + 320 channels, groups of 30."""
+    import torch.nn.functional as F
+    from tinyfusers_b200.native.b200.ops import b200
+    from tinyfusers_b200.runtime import standalone_context, stream_ptr
+    standalone_context()
+    g = _g(12)
+    n, hw, c1, c2 = 2, 256, 640, 320
+    cat = torch.randn(n, hw, c1 + c2, generator=g).half().cuda()
+    gamma, beta = (1 + 0.1 * torch.randn(c1 + c2, generator=g)).cuda(), (0.1 * torch.randn(c1 + c2, generator=g)).cuda()
+    def slot_stats(t, unit):
+        f = t.float().reshape(n, hw // 32, 32, t.shape[-1] // unit, unit)
+        return torch.stack((f.sum(dim=(2, 4)), (f * f).sum(dim=(2, 4))), dim=-1).contiguous()
+    s1, s2 = slot_stats(cat[..., :c1], 10), slot_stats(cat[..., c1:], 10)
+    y = torch.empty_like(cat)
+    st = b200.tf_groupnorm_fused_nhwc_f16(cat.data_ptr(), c1 + c2, c1, s1.data_ptr(), 10, cat.data_ptr() + 2 * c1, c1 + c2, c2,
+                                          s2.data_ptr(), 10, y.data_ptr(), c1 + c2, n, hw, 32, gamma.data_ptr(), beta.data_ptr(),
+                                          1e-5, 0, stream_ptr())
+    b200.check(st, "tf_groupnorm_fused_nhwc_f16")
+    ref = F.group_norm(cat.float().cpu().permute(0, 2, 1).reshape(n, c1 + c2, 16, 16), 32, gamma.cpu(), beta.cpu(), 1e-5)
+    assert rel_err(y.permute(0, 2, 1).reshape(n, c1 + c2, 16, 16), ref) < TOL

@@ -80,12 +80,16 @@ class CrossAttention:
             Mc = B * Tkp
             q_ptr = ctx.arena.alloc(2 * M * nh * dp)
             ctx.gemm(xn_ptr, C, M, C, wq.data_ptr(), nh * dp, q_ptr, nh * dp)
-            k_ptr = ctx.arena.alloc(2 * Mc * nh * dp)
-            ctx.gemm(context.ptr, context.stride, Mc, Cc, wk.data_ptr(), nh * dp, k_ptr, nh * dp)
-            vt_ptr = ctx.arena.alloc(2 * nh * dp * Mc)
-            ctx.gemm(wv.data_ptr(), Cc, nh * dp, Cc, context.ptr, Mc, vt_ptr, Mc, ldw=context.stride)
-            ldq = ldk = nh * dp
-            ldvt = Mc
+            ldq = nh * dp
+            pre = ctx.ctx_kv.get(id(self)) if ctx.ctx_kv else None
+            if pre is not None:      # projected once per step for all blocks (UNetModel._ctx_kv_pack)
+                k_ptr, ldk, vt_ptr, ldvt = pre
+            else:
+                k_ptr = ctx.arena.alloc(2 * Mc * nh * dp)
+                ctx.gemm(context.ptr, context.stride, Mc, Cc, wk.data_ptr(), nh * dp, k_ptr, nh * dp)
+                vt_ptr = ctx.arena.alloc(2 * nh * dp * Mc)
+                ctx.gemm(wv.data_ptr(), Cc, nh * dp, Cc, context.ptr, Mc, vt_ptr, Mc, ldw=context.stride)
+                ldk, ldvt = nh * dp, Mc
         a_ptr = ctx.arena.alloc(2 * M * nh * d)
         ctx.attention(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, a_ptr, B, nh, T, Tk, Tkp, d, dp, head_major=ctx.quirks)
         wo, bo = self.to_out[0]._packed()

@@ -30,7 +30,8 @@ constexpr uint32_t kAccStride = 256;  // columns between the two accumulator buf
 // the tile's bias slice.
 constexpr int kEpiStageBytes = 32 * 128;                    // per warp, 1024-aligned (swizzle atom)
 constexpr int kEpiBiasFloats = 256;
-constexpr int kEpiBytes = 4 * kEpiStageBytes + 4 * kEpiBiasFloats * 4;  // 20480
+constexpr int kEpiColsumBytes = 256 * 8;                    // per warp: {sum, sumsq} of each tile column (GroupNorm statistics)
+constexpr int kEpiBytes = 4 * kEpiStageBytes + 4 * kEpiBiasFloats * 4 + 4 * kEpiColsumBytes;  // 28672
 
 struct ConvGeom {
   int H, W, NI;          // OUTPUT height/width, images
@@ -56,6 +57,11 @@ struct GemmParams {
   float* partial;
   int flags;
   long long* timeline;  // optional debug: per-CTA clock stamps [grid][8] (tf_gemm_set_timeline)
+  // optional GroupNorm statistics of the OUTPUT (fp16 epilogue only): gn_stats[image][slot][unit] = {sum, sumsq}
+  // over one 32-row slot x gn_unit consecutive channels, computed from the rounded fp16 values.
+  float2* gn_stats;
+  int gn_unit;      // channels per statistics unit; bn % gn_unit == 0
+  int gn_hw;        // rows (pixels) per image; % 32 == 0
 };
 
 // tile-local row (0..127) -> global output row (pixel index for conv), or -1 if padding
@@ -230,6 +236,9 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool out_f32 = (p.flags & TF_EPI_OUT_F32) != 0 || partial;
     const bool use_bias = p.bias != nullptr && !partial;
     const bool use_res = p.residual != nullptr && !partial;
+    const bool gn = p.gn_stats != nullptr && !partial;
+    float2* colsum = reinterpret_cast<float2*>(smem_raw + (epi_base + 4 * kEpiStageBytes + 4 * kEpiBiasFloats * 4 - raw_u32)) +
+                     q * (kEpiColsumBytes / 8);
     // swizzle of 16-byte chunk j in row r (row = lane): fp32 rows are 128 B (SW128), fp16 64 B (SW64), GEGLU 32 B (SW32)
     const uint32_t row_bytes = out_f32 ? 128u : (geglu ? 32u : 64u);
     const uint32_t swz = out_f32 ? (uint32_t)(lane & 7) : (geglu ? (uint32_t)((lane >> 2) & 1) : (uint32_t)((lane >> 1) & 3));
@@ -339,12 +348,36 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 16; ++j) {
               __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
               h[j] = *reinterpret_cast<uint32_t*>(&hh);
+              if (gn && m_own < 0) h[j] = 0u;   // rows outside the tensor (clipped by the store) must not count
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ swz) << 4)), "r"(h[4 * j]),
                            "r"(h[4 * j + 1]), "r"(h[4 * j + 2]), "r"(h[4 * j + 3])
                            : "memory");
+            if (gn) {
+              // column sums of the staged 32x32 block: lane -> column pair (lane & 15), 16 of the 32 rows each
+              // (second half walks rows in a different parity order: conflict-free), then one xor-shuffle
+              __syncwarp();
+              const int cp = lane & 15;
+              const uint32_t jch = (uint32_t)cp >> 2, within = ((uint32_t)cp & 3u) * 4u;
+              float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t r = (lane & 16) ? (uint32_t)(16 + (i ^ 1)) : (uint32_t)i;
+                uint32_t wv;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(stg_c + r * 64u + ((jch ^ ((r >> 1) & 3u)) << 4) + within));
+                const float2 fv = __half22float2(*reinterpret_cast<__half2*>(&wv));
+                s0 += fv.x; q0 += fv.x * fv.x;
+                s1 += fv.y; q1 += fv.y * fv.y;
+              }
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              if (lane < 16) {
+                colsum[c + 2 * cp] = make_float2(s0, q0);
+                colsum[c + 2 * cp + 1] = make_float2(s1, q1);
+              }
+            }
           }
         }
         tf::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
@@ -364,6 +397,40 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) rr[j] = rn[j];
+      }
+      if (gn) {
+        // fold this warp's column sums into statistics units and publish slot (image, 32-row block)
+        __syncwarp();
+        int img, slot;
+        bool valid;
+        if (p.is_conv) {
+          const ConvGeom& g = p.g;
+          const int ppi = g.TW * g.TH;   // pixels of one image inside a tile (>= 32, exact tiling: host-checked)
+          const int tx = mt % g.tiles_x, t2 = mt / g.tiles_x;
+          img = (t2 / g.tiles_y) * g.TN + (q * 32) / ppi;
+          valid = img < g.NI;
+          slot = ((t2 % g.tiles_y) * g.tiles_x + tx) * (ppi >> 5) + ((q * 32) % ppi >> 5);
+        } else {
+          const int row0 = mt * BM + q * 32;
+          valid = row0 < p.M;
+          img = row0 / p.gn_hw;
+          slot = (row0 % p.gn_hw) >> 5;
+        }
+        if (valid) {
+          const int utot = p.N / p.gn_unit, u0 = n_tile / p.gn_unit;
+          float2* dst = p.gn_stats + ((size_t)img * (p.gn_hw >> 5) + slot) * utot;
+          for (int u = lane; u < p.bn / p.gn_unit; u += 32) {
+            if (u0 + u < utot) {
+              float a = 0.f, b = 0.f;
+              for (int k = 0; k < p.gn_unit; ++k) {
+                const float2 t2v = colsum[u * p.gn_unit + k];
+                a += t2v.x; b += t2v.y;
+              }
+              dst[u0 + u] = make_float2(a, b);
+            }
+          }
+        }
+        __syncwarp();
       }
       if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(5);   // first tile stored (issued)
       as ^= 1;
@@ -418,6 +485,69 @@ __global__ void tf_splitk_reduce_kernel(const float* __restrict__ partial, int s
   }
 }
 
+// split-K fold that also emits the GroupNorm statistics of its fp16 output (same slot/unit layout as the GEMM
+// epilogue). block = (bw/4, 32) threads over a 32-row x bw-column block: thread (tx, ty) owns columns
+// [4tx, 4tx+4) of row ty. Fixed summation order everywhere.
+__global__ void tf_splitk_reduce_stats_kernel(const float* __restrict__ partial, int splits, int M, int N,
+                                              const float* __restrict__ bias, const __half* __restrict__ residual,
+                                              int ldr, __half* __restrict__ out, int ldc, float2* __restrict__ gn_stats,
+                                              int gn_unit, int gn_hw, int bw) {
+  tf::pdl_prologue();
+  extern __shared__ float2 rsm[];   // [32][bw] per-row values' {v, v^2}... reduced in place to [bw] column totals
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * bw + 4 * tx;
+  const int row0 = blockIdx.y * 32;
+  const size_t total = (size_t)M * N;
+  const int m = row0 + ty;
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  if (m < M) {
+    const size_t idx = (size_t)m * N + col;
+    float4 acc = *reinterpret_cast<const float4*>(partial + idx);
+#pragma unroll 4
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 t = *reinterpret_cast<const float4*>(partial + (size_t)sp * total + idx);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (bias) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+    }
+    if (residual) {
+      const __half2* r = reinterpret_cast<const __half2*>(residual + (size_t)m * ldr + col);
+      const float2 r0 = __half22float2(r[0]), r1 = __half22float2(r[1]);
+      acc.x += r0.x; acc.y += r0.y; acc.z += r1.x; acc.w += r1.y;
+    }
+    const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+    __half2* o = reinterpret_cast<__half2*>(out + (size_t)m * ldc + col);
+    o[0] = h0;
+    o[1] = h1;
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rsm[ty * bw + 4 * tx + j] = make_float2(f[j], f[j] * f[j]);
+  __syncthreads();
+  const int tid = ty * blockDim.x + tx, nthreads = blockDim.x * blockDim.y;
+  // column totals over the 32 rows (fixed order), then units
+  float2* tot = rsm + 32 * bw;
+  for (int c = tid; c < bw; c += nthreads) {
+    float a = 0.f, b = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { a += rsm[r * bw + c].x; b += rsm[r * bw + c].y; }
+    tot[c] = make_float2(a, b);
+  }
+  __syncthreads();
+  if (row0 < M) {
+    const int utot = N / gn_unit, u0 = blockIdx.x * bw / gn_unit;
+    float2* dst = gn_stats + ((size_t)(row0 / gn_hw) * (gn_hw >> 5) + ((row0 % gn_hw) >> 5)) * utot;
+    for (int u = tid; u < bw / gn_unit; u += nthreads) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < gn_unit; ++k) { a += tot[u * gn_unit + k].x; b += tot[u * gn_unit + k].y; }
+      dst[u0 + u] = make_float2(a, b);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -427,13 +557,19 @@ struct TileChoice {
 
 // crude cycle model: per 64-deep k-block a CTA needs max(tensor, smem-feed) cycles; pick the
 // (BN, split-K) pair with the lowest wave-quantised estimate.
+static int lcm_i(int a, int b) {
+  int x = a, y = b;
+  while (y) { int t = x % y; x = y; y = t; }
+  return a / x * b;
+}
+
 static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool allow_split,
-                               size_t ws_bytes, int M, int force_bn, int force_splits) {
+                               size_t ws_bytes, int M, int force_bn, int force_splits, int bn_mult = 32) {
   const int sms = tf_num_sms();
   TileChoice best{128, 1};
   double best_cost = 1e30;
   (void)flags;
-  const int step = 32;  // epilogue ships 32-column blocks
+  const int step = bn_mult;  // epilogue ships 32-column blocks; GroupNorm statistics units must not straddle tiles
   for (int bn = step; bn <= 256; bn += step) {
     if (force_bn > 0 && bn != force_bn) continue;
     const int n_tiles = ceil_div_i(N, bn);
@@ -492,7 +628,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   TF_LAUNCH(tf_gemm_kernel, grid, kThreads, smem, stream, tmA, tmB, tmC, p);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
-  if (p.splits > 1) {
+  if (p.splits > 1 && p.gn_stats != nullptr) {
+    // largest block width <= 128 that is a whole number of statistics units and float4s and divides N
+    const int l = lcm_i(p.gn_unit, 4);
+    int bw = 0;
+    for (int w = (128 / l) * l; w >= l; w -= l)
+      if (p.N % w == 0) { bw = w; break; }
+    if (bw == 0) {
+      tf_set_error("gemm: no split-K reduce block width for N=%d gn_unit=%d", p.N, p.gn_unit);
+      return TF_ERR_UNSUPPORTED;
+    }
+    const dim3 grid(p.N / bw, ceil_div_i(p.M, 32)), block(bw / 4, 32);
+    TF_LAUNCH(tf_splitk_reduce_stats_kernel, grid, block, (size_t)33 * bw * sizeof(float2), stream, p.partial, p.splits, p.M,
+              p.N, p.bias, p.residual, p.ldr, reinterpret_cast<__half*>(p.out), p.ldc, p.gn_stats, p.gn_unit, p.gn_hw, bw);
+    TF_LAUNCH_CHECK();
+    tf_launch_count_add(1);
+  } else if (p.splits > 1) {
     const size_t total = (size_t)p.M * p.N;
     const int threads = 256;
     const int blocks = (int)((total / 4 + threads - 1) / threads);
@@ -518,9 +669,22 @@ extern "C" int tf_gemm_set_tuning(int force_bn, int force_splits) {
   return TF_OK;
 }
 
-extern "C" int tf_gemm_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M,
+static int gn_check(const void* gn_stats, int gn_unit, int gn_hw, int M, int N, int flags, const char* who) {
+  if (!gn_stats) return TF_OK;
+  if (flags & (TF_EPI_GEGLU | TF_EPI_OUT_F32)) {
+    tf_set_error("%s: GroupNorm statistics need the plain fp16 epilogue", who);
+    return TF_ERR_UNSUPPORTED;
+  }
+  if (gn_unit <= 0 || N % gn_unit != 0 || lcm_i(32, gn_unit) > 256 || gn_hw <= 0 || gn_hw % 32 != 0 || M % gn_hw != 0) {
+    tf_set_error("%s: GroupNorm statistics unsupported for N=%d unit=%d rows/image=%d M=%d", who, N, gn_unit, gn_hw, M);
+    return TF_ERR_UNSUPPORTED;
+  }
+  return TF_OK;
+}
+
+static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M,
                            int N, int K, const float* bias, const void* residual, int ldr, int flags,
-                           void* workspace, size_t ws_bytes, void* stream) {
+                           void* workspace, size_t ws_bytes, void* stream, void* gn_stats, int gn_unit, int gn_hw) {
   TF_CHECK_ARG(A && W && out, "tf_gemm_f16: null pointer");
   TF_CHECK_ARG(M > 0 && N > 0 && K > 0, "tf_gemm_f16: bad dims M=%d N=%d K=%d", M, N, K);
   TF_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tf_gemm_f16: K, lda, ldw must be multiples of 8");
@@ -530,14 +694,19 @@ extern "C" int tf_gemm_f16(const void* A, int lda, const void* W, int ldw, void*
   if (residual) TF_CHECK_ARG(ldr % 8 == 0 && ((uintptr_t)residual & 15) == 0, "tf_gemm_f16: residual alignment");
   if (flags & TF_EPI_GEGLU) TF_CHECK_ARG(N % 32 == 0 && !residual, "tf_gemm_f16: GEGLU needs N %% 32 == 0, no residual");
 
+  {
+    int rc = gn_check(gn_stats, gn_unit, gn_hw, M, N, flags, "tf_gemm_gn_f16");
+    if (rc) return rc;
+  }
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.is_conv = 0;
+  p.gn_stats = reinterpret_cast<float2*>(gn_stats); p.gn_unit = gn_unit; p.gn_hw = gn_hw;
   p.m_tiles = ceil_div_i(M, BM);
   p.k_blocks = ceil_div_i(K, BK);
   const bool allow_split = !(flags & TF_EPI_GEGLU) && workspace != nullptr;
   TileChoice tc = choose_tiles(p.m_tiles, N, p.k_blocks, flags, allow_split, ws_bytes, M, g_force_bn,
-                               g_force_splits);
+                               g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32);
   p.bn = tc.bn;
   p.splits = tc.splits;
   p.n_tiles = ceil_div_i(N, p.bn);
@@ -586,18 +755,31 @@ extern "C" int tf_gemm_f16(const void* A, int lda, const void* W, int ldw, void*
   return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride,
+extern "C" int tf_gemm_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M, int N, int K,
+                           const float* bias, const void* residual, int ldr, int flags, void* workspace,
+                           size_t ws_bytes, void* stream) {
+  return gemm_impl(A, lda, W, ldw, out, ldc, M, N, K, bias, residual, ldr, flags, workspace, ws_bytes, stream, nullptr, 0, 0);
+}
+
+extern "C" int tf_gemm_gn_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M, int N, int K,
+                              const float* bias, const void* residual, int ldr, int flags, void* workspace,
+                              size_t ws_bytes, void* gn_stats, int gn_unit, int rows_per_image, void* stream) {
+  return gemm_impl(A, lda, W, ldw, out, ldc, M, N, K, bias, residual, ldr, flags, workspace, ws_bytes, stream, gn_stats,
+                   gn_unit, rows_per_image);
+}
+
+static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride,
                                   const void* w, int Cout, int ksize, int stride, void* out, int ldc,
                                   const float* bias, const void* residual, int ldr, int flags,
-                                  void* workspace, size_t ws_bytes, void* stream) {
+                                  void* workspace, size_t ws_bytes, void* stream, void* gn_stats, int gn_unit) {
   TF_CHECK_ARG(x && w && out, "tf_conv2d_nhwc_f16: null pointer");
   TF_CHECK_ARG(ksize == 1 || ksize == 3, "tf_conv2d_nhwc_f16: kernel size %d unsupported (1 or 3)", ksize);
   TF_CHECK_ARG(stride == 1 || stride == 2, "tf_conv2d_nhwc_f16: stride %d unsupported (1 or 2)", stride);
   TF_CHECK_ARG(NI > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "tf_conv2d_nhwc_f16: bad dims");
   TF_CHECK_ARG(x_pixel_stride >= Cin && x_pixel_stride % 8 == 0, "tf_conv2d_nhwc_f16: bad pixel stride");
   if (ksize == 1 && stride == 1) {
-    return tf_gemm_f16(x, x_pixel_stride, w, Cin, out, ldc, NI * H * W, Cout, Cin, bias, residual, ldr,
-                       flags, workspace, ws_bytes, stream);
+    return gemm_impl(x, x_pixel_stride, w, Cin, out, ldc, NI * H * W, Cout, Cin, bias, residual, ldr,
+                     flags, workspace, ws_bytes, stream, gn_stats, gn_unit, H * W);
   }
   TF_CHECK_ARG(ksize == 3, "tf_conv2d_nhwc_f16: strided 1x1 unsupported");
   TF_CHECK_ARG(Cin % BK == 0, "tf_conv2d_nhwc_f16: Cin must be a multiple of 64 (got %d)", Cin);
@@ -609,8 +791,13 @@ extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, 
   const int Ho = (H + 2 * pad - 3) / stride + 1;
   const int Wo = (W + 2 * pad - 3) / stride + 1;
 
+  {
+    int rc = gn_check(gn_stats, gn_unit, Ho * Wo, NI * Ho * Wo, Cout, flags, "tf_conv2d_nhwc_gn_f16");
+    if (rc) return rc;
+  }
   GemmParams p{};
   p.is_conv = 1;
+  p.gn_stats = reinterpret_cast<float2*>(gn_stats); p.gn_unit = gn_unit; p.gn_hw = Ho * Wo;
   p.M = NI * Ho * Wo; p.N = Cout; p.K = 9 * Cin;
   ConvGeom& g = p.g;
   g.H = Ho; g.W = Wo; g.NI = NI; g.cblocks = Cin / BK; g.cscale = stride; g.pad = pad; g.ksize = 3;
@@ -620,12 +807,18 @@ extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, 
     for (int th = 128 / tw; th >= 1; th >>= 1) {
       int tn = 128 / (tw * th);
       if (tw * stride > 256 || th * stride > 256) continue;
+      // statistics slots are 32-row blocks inside one image: exact tiling, >= 32 pixels of an image per tile
+      if (gn_stats && (Wo % tw != 0 || Ho % th != 0 || tw * th < 32)) continue;
       long tiles = (long)ceil_div_i(Wo, tw) * ceil_div_i(Ho, th) * ceil_div_i(NI, tn);
       if (best_tiles < 0 || tiles < best_tiles) {
         best_tiles = tiles;
         g.TW = tw; g.TH = th; g.TN = tn;
       }
     }
+  }
+  if (best_tiles < 0) {
+    tf_set_error("tf_conv2d_nhwc_gn_f16: no exact 128-pixel tiling of %dx%d for GroupNorm statistics", Ho, Wo);
+    return TF_ERR_UNSUPPORTED;
   }
   g.tiles_x = ceil_div_i(Wo, g.TW);
   g.tiles_y = ceil_div_i(Ho, g.TH);
@@ -635,7 +828,7 @@ extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, 
   g.sbw = g.TW >= 32 ? 32 : g.TW;
   g.sbh = g.TW >= 32 ? 1 : (g.TW * g.TH >= 32 ? 32 / g.TW : g.TH);
   TileChoice tc = choose_tiles(p.m_tiles, Cout, p.k_blocks, flags, workspace != nullptr, ws_bytes, p.M, g_force_bn,
-                               g_force_splits);
+                               g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32);
   p.bn = tc.bn;
   p.splits = tc.splits;
   p.n_tiles = ceil_div_i(Cout, p.bn);
@@ -682,4 +875,31 @@ extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, 
     if (rc) return rc;
   }
   return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w,
+                                  int Cout, int ksize, int stride, void* out, int ldc, const float* bias,
+                                  const void* residual, int ldr, int flags, void* workspace, size_t ws_bytes,
+                                  void* stream) {
+  return conv_impl(x, NI, H, W, Cin, x_pixel_stride, w, Cout, ksize, stride, out, ldc, bias, residual, ldr, flags, workspace,
+                   ws_bytes, stream, nullptr, 0);
+}
+
+extern "C" int tf_conv2d_nhwc_gn_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w,
+                                     int Cout, int ksize, int stride, void* out, int ldc, const float* bias,
+                                     const void* residual, int ldr, int flags, void* workspace, size_t ws_bytes,
+                                     void* gn_stats, int gn_unit, void* stream) {
+  return conv_impl(x, NI, H, W, Cin, x_pixel_stride, w, Cout, ksize, stride, out, ldc, bias, residual, ldr, flags, workspace,
+                   ws_bytes, stream, gn_stats, gn_unit);
+}
+
+// 1 if tf_gemm_gn_f16 / tf_conv2d_nhwc_gn_f16 can emit statistics for this output geometry (mirrors the checks above)
+extern "C" int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_conv3x3) {
+  const int hw = Ho * Wo;
+  if (gn_unit <= 0 || C % gn_unit != 0 || lcm_i(32, gn_unit) > 256 || hw % 32 != 0 || NI <= 0) return 0;
+  if (!is_conv3x3) return 1;
+  for (int tw = 128; tw >= 1; tw >>= 1)
+    for (int th = 128 / tw; th >= 1; th >>= 1)
+      if (Wo % tw == 0 && Ho % th == 0 && tw * th >= 32 && tw <= 128 && th <= 128) return 1;
+  return 0;
 }

@@ -142,6 +142,106 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-launch GroupNorm (+SiLU) for inputs whose producer (tf_gemm_gn_f16 / tf_conv2d_nhwc_gn_f16) already left
+// per-slot statistics: stats[image][slot = 32 rows][unit] = {sum, sumsq}. Every block first folds the slots of
+// its image (one warp per unit, lanes stride over slots, fixed xor-shuffle order), then units -> groups, then
+// normalises its pixel chunk. Up to two sources (channel concatenation), each with its own unit size.
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_fused_apply_kernel(const __half* __restrict__ x1, int stride1, int C1, const float2* __restrict__ st1,
+                                      int unit1, const __half* __restrict__ x2, int stride2, int C2,
+                                      const float2* __restrict__ st2, int unit2, int HW, int cpg, int G, int pix_per_block,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      float inv_count, int silu, __half* __restrict__ out, int out_stride) {
+  tf::pdl_prologue();
+  extern __shared__ float2 fsm[];   // [units] unit totals, [G] {mean, rstd}, [SG][units] partials of the fold
+  const int n = blockIdx.y;
+  const int slots = HW >> 5;
+  const int units1 = C1 / unit1, units2 = x2 ? C2 / unit2 : 0;
+  const int units = units1 + units2;
+  // fold: thread (sg, u) sums slots sg, sg + SG, ... of unit u (independent, coalesced loads: no shuffle in the
+  // loop, so they pipeline), then thread u adds the SG partials in a fixed order
+  float2* part = fsm + units + G;
+  const int SG = min((int)blockDim.x / units, slots);
+  {
+    const int u = threadIdx.x % units, sg = threadIdx.x / units;
+    if (sg < SG) {
+      const float2* src;
+      int ld;
+      if (u < units1) { src = st1 + (size_t)n * slots * units1 + u; ld = units1; }
+      else { src = st2 + (size_t)n * slots * units2 + (u - units1); ld = units2; }
+      float a = 0.f, b = 0.f;
+#pragma unroll 4
+      for (int j = sg; j < slots; j += SG) {
+        const float2 t = __ldg(src + (size_t)j * ld);
+        a += t.x; b += t.y;
+      }
+      part[sg * units + u] = make_float2(a, b);
+    }
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int sg = 0; sg < SG; ++sg) { a += part[sg * units + u].x; b += part[sg * units + u].y; }
+    fsm[u] = make_float2(a, b);
+  }
+  __syncthreads();
+  float2* gst = fsm + units;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    int c = g * cpg;
+    const int c_end = c + cpg;
+    while (c < c_end) {           // unit boundaries are aligned with group and source boundaries (host-checked)
+      int u, step;
+      if (c < C1) { u = c / unit1; step = unit1; }
+      else { u = units1 + (c - C1) / unit2; step = unit2; }
+      a += fsm[u].x; b += fsm[u].y;
+      c += step;
+    }
+    const float mean = a * inv_count;
+    const float var = fmaxf(b * inv_count - mean * mean, 0.f);
+    gst[g] = make_float2(mean, rsqrtf(var + eps));
+  }
+  __syncthreads();
+  const int nvec = (C1 + C2) >> 3;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int npl = blockDim.x / nvec;
+  if (pl >= npl) return;
+  const int c0 = v * 8;
+  float a8[8], b8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float2 mr = gst[c / cpg];
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    a8[j] = mr.y * ga;
+    b8[j] = be - mr.x * mr.y * ga;
+  }
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const __half* xin;
+  int xs;
+  if (c0 < C1) { xin = x1 + (size_t)n * HW * stride1 + c0; xs = stride1; }
+  else { xin = x2 + (size_t)n * HW * stride2 + (c0 - C1); xs = stride2; }
+  __half* o = out + (size_t)n * HW * out_stride + c0;
+  for (int p = p0 + pl; p < p1; p += npl) {
+    tf::Pack16 pk;
+    pk.v = *reinterpret_cast<const uint4*>(xin + (size_t)p * xs);
+    tf::Pack16 r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(pk.h2[j]);
+      float y0 = f.x * a8[2 * j] + b8[2 * j];
+      float y1 = f.y * a8[2 * j + 1] + b8[2 * j + 1];
+      if (silu) { y0 = tf::silu_f(y0); y1 = tf::silu_f(y1); }
+      r.h2[j] = __floats2half2_rn(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(o + (size_t)p * out_stride) = r.v;
+  }
+}
+
 static int gn_block_threads(int Cs) {
   const int nvec = Cs / 8;
   int k = 512 / nvec;
@@ -218,23 +318,26 @@ __global__ void ln_rows_kernel(const __half* __restrict__ x, __half* __restrict_
 // Block-per-chunk-row LayerNorm for interleave IL in {1,2,4,8}: the chunk row is C*IL contiguous halfs; element
 // p belongs to group (p % IL) and channel (p / IL). 128-bit loads, the row stays in registers, exact two-pass
 // statistics, fixed-order block reduction. Used when rows are long or few (one warp per row is latency-bound).
-template <int IL, int THREADS, int MAXV>
-__global__ void __launch_bounds__(THREADS)
-ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, const float* __restrict__ gamma,
+template <int IL, int THREADS, int MAXV, int ROWS>
+__global__ void __launch_bounds__(THREADS * ROWS)
+ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int nrows, int C, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps) {
   tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
-  __shared__ float red[2][THREADS / 32][IL];
+  __shared__ float red[2][ROWS][THREADS / 32][IL];   // ROWS rows per block, THREADS threads each (whole warps)
+  const int rib = threadIdx.x / THREADS, tid = threadIdx.x % THREADS;
+  const int row = blockIdx.x * ROWS + rib;
+  const bool live = row < nrows;
   const int nvec = (C * IL) >> 3;
-  const __half* xr = x + (size_t)blockIdx.x * C * IL;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __half* xr = x + (size_t)row * C * IL;
+  const int warp = tid >> 5, lane = tid & 31;
   tf::Pack16 pk[MAXV];
   float s[IL];
 #pragma unroll
   for (int b = 0; b < IL; ++b) s[b] = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int v = threadIdx.x + i * THREADS;
-    if (v < nvec) {
+    const int v = tid + i * THREADS;
+    if (live && v < nvec) {
       pk[i].v = *reinterpret_cast<const uint4*>(xr + v * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j % IL] += __half2float(pk[i].h[j]);
@@ -243,7 +346,7 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, c
 #pragma unroll
   for (int b = 0; b < IL; ++b) {
     const float w = tf::warp_sum(s[b]);
-    if (lane == 0) red[0][warp][b] = w;
+    if (lane == 0) red[0][rib][warp][b] = w;
   }
   __syncthreads();
   float mean[IL];
@@ -251,14 +354,14 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, c
   for (int b = 0; b < IL; ++b) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) t += red[0][w][b];
+    for (int w = 0; w < THREADS / 32; ++w) t += red[0][rib][w][b];
     mean[b] = t / (float)C;
     s[b] = 0.f;
   }
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int v = threadIdx.x + i * THREADS;
-    if (v < nvec) {
+    const int v = tid + i * THREADS;
+    if (live && v < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = __half2float(pk[i].h[j]) - mean[j % IL];
@@ -269,7 +372,7 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, c
 #pragma unroll
   for (int b = 0; b < IL; ++b) {
     const float w = tf::warp_sum(s[b]);
-    if (lane == 0) red[1][warp][b] = w;
+    if (lane == 0) red[1][rib][warp][b] = w;
   }
   __syncthreads();
   float rstd[IL];
@@ -277,14 +380,14 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int C, c
   for (int b = 0; b < IL; ++b) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) t += red[1][w][b];
+    for (int w = 0; w < THREADS / 32; ++w) t += red[1][rib][w][b];
     rstd[b] = rsqrtf(t / (float)C + eps);
   }
-  __half* orow = out + (size_t)blockIdx.x * C * IL;
+  __half* orow = out + (size_t)row * C * IL;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int v = threadIdx.x + i * THREADS;
-    if (v < nvec) {
+    const int v = tid + i * THREADS;
+    if (live && v < nvec) {
       tf::Pack16 r;
       const int c0 = (v * 8) / IL;  // first channel covered by this vector (8 / IL channels)
 #pragma unroll
@@ -303,11 +406,12 @@ static bool launch_ln_block(const __half* x, __half* out, int chunk_rows, int C,
                             float eps, cudaStream_t stream) {
   const int nvec = C * IL / 8;
   if ((C * IL) % 8 != 0) return false;
-  if (nvec <= 64) TF_LAUNCH((ln_block_kernel<IL, 32, 2>), chunk_rows, 32, 0, stream, x, out, C, gamma, beta, eps);
-  else if (nvec <= 128) TF_LAUNCH((ln_block_kernel<IL, 64, 2>), chunk_rows, 64, 0, stream, x, out, C, gamma, beta, eps);
-  else if (nvec <= 256) TF_LAUNCH((ln_block_kernel<IL, 128, 2>), chunk_rows, 128, 0, stream, x, out, C, gamma, beta, eps);
-  else if (nvec <= 512) TF_LAUNCH((ln_block_kernel<IL, 128, 4>), chunk_rows, 128, 0, stream, x, out, C, gamma, beta, eps);
-  else if (nvec <= 1024) TF_LAUNCH((ln_block_kernel<IL, 256, 4>), chunk_rows, 256, 0, stream, x, out, C, gamma, beta, eps);
+  // 256-thread blocks: several short rows per block keep enough warps resident to hide the load latency
+  if (nvec <= 64) TF_LAUNCH((ln_block_kernel<IL, 32, 2, 8>), ceil_div_i(chunk_rows, 8), 256, 0, stream, x, out, chunk_rows, C, gamma, beta, eps);
+  else if (nvec <= 128) TF_LAUNCH((ln_block_kernel<IL, 64, 2, 4>), ceil_div_i(chunk_rows, 4), 256, 0, stream, x, out, chunk_rows, C, gamma, beta, eps);
+  else if (nvec <= 256) TF_LAUNCH((ln_block_kernel<IL, 128, 2, 2>), ceil_div_i(chunk_rows, 2), 256, 0, stream, x, out, chunk_rows, C, gamma, beta, eps);
+  else if (nvec <= 512) TF_LAUNCH((ln_block_kernel<IL, 128, 4, 1>), chunk_rows, 128, 0, stream, x, out, chunk_rows, C, gamma, beta, eps);
+  else if (nvec <= 1024) TF_LAUNCH((ln_block_kernel<IL, 256, 4, 1>), chunk_rows, 256, 0, stream, x, out, chunk_rows, C, gamma, beta, eps);
   else return false;
   return true;
 }
@@ -390,6 +494,42 @@ extern "C" int tf_groupnorm_nhwc_f16(const void* x, int x_pixel_stride, int Cx, 
     TF_LAUNCH_CHECK();
   }
   tf_launch_count_add(2 * nsrc + 1);
+  return TF_OK;
+}
+
+extern "C" int tf_groupnorm_fused_nhwc_f16(const void* x, int x_pixel_stride, int Cx, const void* x_stats, int x_unit,
+                                           const void* x2, int x2_pixel_stride, int Cx2, const void* x2_stats, int x2_unit,
+                                           void* out, int out_pixel_stride, int NI, int HW, int groups, const float* gamma,
+                                           const float* beta, float eps, int apply_silu, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TF_CHECK_ARG(x && out && x_stats && (!x2 || x2_stats), "tf_groupnorm_fused_nhwc_f16: null pointer");
+  if (!x2) { Cx2 = 0; x2_unit = 1; }
+  const int C = Cx + Cx2;
+  TF_CHECK_ARG(NI > 0 && HW > 0 && HW % 32 == 0 && groups > 0 && groups <= 64 && C % groups == 0,
+               "tf_groupnorm_fused_nhwc_f16: bad dims (C=%d groups=%d HW=%d)", C, groups, HW);
+  TF_CHECK_ARG(Cx % 8 == 0 && Cx2 % 8 == 0 && x_pixel_stride % 8 == 0 && out_pixel_stride % 8 == 0 &&
+                   (!x2 || x2_pixel_stride % 8 == 0) && C / 8 <= 1024,
+               "tf_groupnorm_fused_nhwc_f16: channels and strides must be multiples of 8");
+  const int cpg = C / groups;
+  TF_CHECK_ARG(x_unit > 0 && Cx % x_unit == 0 && cpg % x_unit == 0 &&
+                   (!x2 || (x2_unit > 0 && Cx2 % x2_unit == 0 && cpg % x2_unit == 0 && Cx % x2_unit == 0)),
+               "tf_groupnorm_fused_nhwc_f16: statistics units (%d, %d) do not tile groups of %d channels", x_unit, x2_unit, cpg);
+  const int sms = tf_num_sms();
+  int chunks = (2 * sms + NI - 1) / NI;
+  if (chunks > HW) chunks = HW;
+  const int ppb = ceil_div_i(HW, chunks);
+  chunks = ceil_div_i(HW, ppb);
+  int threads = gn_block_threads(C);
+  threads = (threads + 31) / 32 * 32;   // whole warps for the fold; surplus threads skip the apply loop
+  const int units = Cx / x_unit + (x2 ? Cx2 / x2_unit : 0);
+  TF_CHECK_ARG(units <= threads, "tf_groupnorm_fused_nhwc_f16: %d statistics units exceed the block size", units);
+  const size_t smem = sizeof(float2) * ((size_t)units + groups + (size_t)(threads / units) * units);
+  TF_LAUNCH(gn_fused_apply_kernel, dim3(chunks, NI), threads, smem, stream, reinterpret_cast<const __half*>(x), x_pixel_stride,
+            Cx, reinterpret_cast<const float2*>(x_stats), x_unit, reinterpret_cast<const __half*>(x2), x2_pixel_stride, Cx2,
+            reinterpret_cast<const float2*>(x2_stats), x2_unit, HW, cpg, groups, ppb, gamma, beta, eps,
+            1.0f / ((float)cpg * (float)HW), apply_silu, reinterpret_cast<__half*>(out), out_pixel_stride);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
   return TF_OK;
 }
 

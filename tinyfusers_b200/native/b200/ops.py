@@ -33,6 +33,13 @@ _SIGNATURES = {
                             _P, c_size_t, _P]),
     "tf_conv2d_nhwc_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
                                    _P, _P, c_int, c_int, _P, c_size_t, _P]),
+    "tf_gemm_gn_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
+                               _P, c_size_t, _P, c_int, c_int, _P]),
+    "tf_conv2d_nhwc_gn_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
+                                      _P, _P, c_int, c_int, _P, c_size_t, _P, c_int, _P]),
+    "tf_gn_stats_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "tf_groupnorm_fused_nhwc_f16": (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int,
+                                            c_int, c_int, _P, _P, c_float, c_int, _P]),
     "tf_groupnorm_nhwc_f16": (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P,
                                       c_float, c_int, _P, _P]),
     "tf_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),

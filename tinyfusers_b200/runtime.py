@@ -23,6 +23,16 @@ def _align(n, a=256):
     return (n + a - 1) // a * a
 
 
+def gn_unit(c, groups=32):
+    """Statistics unit (channels) for a c-channel tensor: divides c/groups AND the group sizes of the UNet's
+    channel concatenations that contain it (320/640/1280 -> 10), so one set of statistics serves every consumer."""
+    base = c // groups if c % groups == 0 else 0
+    if base <= 0:
+        return 0
+    g = math.gcd(base, 10)
+    return g if g > 1 else base
+
+
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
@@ -35,13 +45,15 @@ def require_cuda(t, name="tensor"):
 class Act:
     """A (n, h, w, c) fp16 NHWC activation view: pixel p of image i starts at ptr + 2*((i*h*w + p)*stride)."""
 
-    __slots__ = ("ptr", "n", "h", "w", "c", "stride", "keep", "valid")
+    __slots__ = ("ptr", "n", "h", "w", "c", "stride", "keep", "valid", "gn")
 
     def __init__(self, ptr, n, h, w, c, stride=None, keep=None):
         self.ptr, self.n, self.h, self.w, self.c = ptr, n, h, w, c
         self.stride = c if stride is None else stride
         self.keep = keep  # torch tensor owning the memory when not arena-backed
         self.valid = None  # for padded token sequences: number of real tokens per batch (<= h)
+        # GroupNorm statistics left by the producer(s): list of (c0, c1, stats_ptr, unit) channel parts, or None
+        self.gn = None
 
     @property
     def rows(self):
@@ -113,16 +125,29 @@ class Context:
         self.emb_bias = None       # dict: id(ResBlock) -> device pointer of its (conv bias + emb) fp32 vector
         self.context = None        # Act view of the zero-padded fp16 prompt context (B, Tpad, 768)
         self.context_tokens = 0
+        self.fuse_gn = os.environ.get("TINYFUSERS_B200_FUSE_GN", "1") != "0"
+        self.ctx_kv = None         # dict: id(CrossAttention) -> (k_ptr, ldk, vt_ptr, ldvt) projected once per forward
 
     def ensure_workspaces(self):
         if self.ws is None:
             self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 
     # -- allocation ------------------------------------------------------------------------------
-    def new_act(self, n, h, w, c, stride=None):
+    def new_act(self, n, h, w, c, stride=None, gn=False):
         stride = c if stride is None else stride
         ptr = self.arena.alloc(2 * n * h * w * stride)
-        return Act(ptr, n, h, w, c, stride)
+        a = Act(ptr, n, h, w, c, stride)
+        if gn:
+            self.attach_gn(a)
+        return a
+
+    def attach_gn(self, a):
+        """Give `a` a statistics buffer its producer (a GEMM / conv epilogue) will fill, if the geometry qualifies."""
+        unit = gn_unit(a.c)
+        if self.fuse_gn and unit and b200.tf_gn_stats_supported(a.n, a.h, a.w, a.c, unit, 1):
+            ptr = self.arena.alloc(8 * a.n * (a.h * a.w // 32) * (a.c // unit))
+            a.gn = [(0, a.c, ptr, unit)]
+        return a
 
     def new_f32(self, numel):
         return self.arena.alloc(4 * numel)
@@ -142,25 +167,55 @@ class Context:
         """True when the kernel must not be launched (arena dry run, or bench's per-class timing filter)."""
         return self.dry or (self.only is not None and kind not in self.only)
 
-    def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None):
+    def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None, gn=None):
+        """gn = (stats_ptr, unit, rows_per_image): also emit the GroupNorm statistics of the output."""
         if self.skip("gemm"):
             return
-        st = self._timed(("gemm", M, N, K, flags, residual_ptr is not None),
-                         lambda: b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
-                                                  residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr()))
+        if gn is None:
+            fn = lambda: b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
+                                          residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
+        else:
+            fn = lambda: b200.tf_gemm_gn_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
+                                             residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, gn[0], gn[1], gn[2],
+                                             stream_ptr())
+        st = self._timed(("gemm", M, N, K, flags, residual_ptr is not None), fn)
         b200.check(st, "tf_gemm_f16")
 
-    def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0):
+    def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0, gn=None):
         if self.skip("gemm"):
             return
-        st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None),
-                         lambda: b200.tf_conv2d_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr,
-                                                         out.stride, bias, residual.ptr if residual is not None else None,
-                                                         residual.stride if residual is not None else 0, flags,
-                                                         self.ws.data_ptr(), self.ws_bytes, stream_ptr()))
+        rp = residual.ptr if residual is not None else None
+        rs = residual.stride if residual is not None else 0
+        if gn is None:
+            fn = lambda: b200.tf_conv2d_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr, out.stride,
+                                                 bias, rp, rs, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
+        else:
+            fn = lambda: b200.tf_conv2d_nhwc_gn_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr,
+                                                    out.stride, bias, rp, rs, flags, self.ws.data_ptr(), self.ws_bytes,
+                                                    gn[0], gn[1], stream_ptr())
+        st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None), fn)
         b200.check(st, "tf_conv2d_nhwc_f16")
 
     def groupnorm(self, x, out, gamma, beta, eps, silu, groups=32):
+        parts = x.gn
+        if parts is not None and len(parts) in (1, 2) and x.c % groups == 0:
+            cpg = x.c // groups
+            ok = parts[0][0] == 0 and parts[-1][1] == x.c and all(cpg % pt[3] == 0 and pt[0] % pt[3] == 0 for pt in parts)
+            if len(parts) == 2:
+                ok = ok and parts[0][1] == parts[1][0]
+            if ok:
+                if self.skip("norm"):
+                    return
+                p0 = parts[0]
+                p1 = parts[1] if len(parts) == 2 else None
+                st = self._timed(("groupnorm", x.n, x.h * x.w, x.c),
+                                 lambda: b200.tf_groupnorm_fused_nhwc_f16(
+                                     x.ptr, x.stride, p0[1], p0[2], p0[3],
+                                     x.ptr + 2 * p1[0] if p1 else None, x.stride, p1[1] - p1[0] if p1 else 0,
+                                     p1[2] if p1 else None, p1[3] if p1 else 1, out.ptr, out.stride, x.n, x.h * x.w,
+                                     groups, gamma, beta, eps, 1 if silu else 0, stream_ptr()))
+                b200.check(st, "tf_groupnorm_fused_nhwc_f16")
+                return
         mark = self.arena.mark()
         stats = self.arena.alloc(b200.tf_groupnorm_workspace_bytes(x.n, groups))   # partials + {mean, rstd}
         self.arena.release(mark)                          # stream order keeps the reuse safe

@@ -30,12 +30,17 @@ def _check_supported(ksize, stride, padding, dilation):
 
 
 def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=None, flags=0):
+    # the output's GroupNorm statistics are produced by this launch when `out` carries a (single-part) buffer
+    gn = None
+    if out.gn is not None and len(out.gn) == 1 and out.gn[0][0] == 0 and out.gn[0][1] == cout_p and flags == 0:
+        gn = (out.gn[0][2], out.gn[0][3])
     if k == 3:
-        ctx.conv3x3(x, w_packed.data_ptr(), cout_p, out, bias=bias_ptr, residual=residual, stride=stride, flags=flags)
+        ctx.conv3x3(x, w_packed.data_ptr(), cout_p, out, bias=bias_ptr, residual=residual, stride=stride, flags=flags, gn=gn)
     else:
         ctx.gemm(x.ptr, x.stride, x.rows, x.c, w_packed.data_ptr(), cout_p, out.ptr, out.stride, bias=bias_ptr,
                  residual_ptr=residual.ptr if residual is not None else None,
-                 ldr=residual.stride if residual is not None else 0, flags=flags)
+                 ldr=residual.stride if residual is not None else 0, flags=flags,
+                 gn=(gn[0], gn[1], out.h * out.w) if gn else None)
 
 
 def conv_2d(X_gpu, W_gpu, padding, stride, dilation):

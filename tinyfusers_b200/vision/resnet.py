@@ -57,7 +57,7 @@ class ResBlock:
         mark = ctx.arena.mark()
         h0 = ctx.new_act(x.n, x.h, x.w, x.c)
         self.in_layers[0]._run(ctx, x, h0, silu=True)
-        h1 = ctx.new_act(x.n, x.h, x.w, self.out_channels)
+        h1 = ctx.new_act(x.n, x.h, x.w, self.out_channels, gn=True)   # conv1's epilogue leaves GN2's statistics
         self.in_layers[2]._run(ctx, h0, h1, bias_ptr=emb_bias_ptr)
         h2 = ctx.new_act(x.n, x.h, x.w, self.out_channels)
         self.out_layers[0]._run(ctx, h1, h2, silu=True)

@@ -156,6 +156,32 @@ class UNetModel:
             return w, b, cb, offs, o
         return packing.cached(self, "emb", tensors, build)
 
+    def _cross_attns(self):
+        out = []
+        for group in (self.input_blocks, [self.middle_block], self.output_blocks):
+            for b in group:
+                for layer in b:
+                    if isinstance(layer, SpatialTransformer):
+                        out += [blk.attn2 for blk in layer.transformer_blocks]
+        return out
+
+    def _ctx_kv_pack(self):
+        """Row-concatenated (head-padded) to_k / to_v weights of every cross-attention: the prompt context is the
+        same for all 16 transformer blocks, so their K and V^T projections are two GEMMs per step, not 32."""
+        atts = self._cross_attns()
+        tensors = []
+        for a in atts:
+            tensors += [a.to_k.weight, a.to_v.weight]
+        def build():
+            wk = torch.cat([a._packed()[1] for a in atts], dim=0).contiguous()
+            wv = torch.cat([a._packed()[2] for a in atts], dim=0).contiguous()
+            offs, o = {}, 0
+            for a in atts:
+                offs[id(a)] = o
+                o += a._packed()[1].shape[0]
+            return wk, wv, offs, o
+        return packing.cached(self, "ctxkv", tensors, build)
+
     # ---- fast path ------------------------------------------------------------------------------
     def _run(self, ctx, latent_ptr, n_src, n, H, W, t_ptr, idx_ptr, context_ptr, ctx_tokens, eps_ptr):
         """Enqueue one forward. latent: fp32 NCHW (n_src,4,H,W) (image i of the batch reads i % n_src);
@@ -184,6 +210,14 @@ class UNetModel:
         if misc:
             b200.check(b200.tf_pad_tokens_f32_to_f16(context_ptr, cact.ptr, n, ctx_tokens, tkp, 768, S),
                        "tf_pad_tokens_f32_to_f16")
+        # --- K and V^T of every cross-attention in two launches (same context for all blocks) ---
+        wk_all, wv_all, kv_offs, kv_total = self._ctx_kv_pack()
+        Mc = n * tkp
+        kall = ar.alloc(2 * Mc * kv_total)
+        vtall = ar.alloc(2 * kv_total * Mc)
+        ctx.gemm(cact.ptr, 768, Mc, 768, wk_all.data_ptr(), kv_total, kall, kv_total)
+        ctx.gemm(wv_all.data_ptr(), 768, kv_total, 768, cact.ptr, Mc, vtall, Mc, ldw=768)
+        ctx.ctx_kv = {key: (kall + 2 * off, kv_total, vtall + 2 * off * Mc, Mc) for key, off in kv_offs.items()}
         # --- plan the skip/concat buffers: output block j reads [x | saved[11-j]] ---
         res = [(H, W)]
         in_ch, in_hw = [], []
@@ -205,17 +239,28 @@ class UNetModel:
             cat_c = blk[0].channels
             hh, ww = in_hw[nb - 1 - j]
             cats.append(ctx.new_act(n, hh, ww, cat_c))
-        skip_view = lambda i: cats[nb - 1 - i].channels(cats[nb - 1 - i].c - in_ch[i], cats[nb - 1 - i].c)
-        x_view = lambda j: cats[j].channels(0, cats[j].c - in_ch[nb - 1 - j])
+        # persistent slice views; each gets its own statistics buffer, the concatenation lists both parts
+        svs = [cats[nb - 1 - i].channels(cats[nb - 1 - i].c - in_ch[i], cats[nb - 1 - i].c) for i in range(nb)]
+        xvs = [cats[j].channels(0, cats[j].c - in_ch[nb - 1 - j]) for j in range(nb)]
+        for i in range(1, nb):
+            ctx.attach_gn(svs[i])       # svs[0] is written by conv_in (no statistics): its consumers take the 3-launch path
+        for j in range(nb):
+            ctx.attach_gn(xvs[j])
+            xp, sp = xvs[j].gn, svs[nb - 1 - j].gn
+            if xp is not None and sp is not None:
+                c1 = xvs[j].c
+                cats[j].gn = [xp[0], (c1, cats[j].c, sp[0][2], sp[0][3])]
+        skip_view = lambda i: svs[i]
+        x_view = lambda j: xvs[j]
 
         def run_block(layers, x, final_out):
             for li, layer in enumerate(layers):
                 last = li == len(layers) - 1
                 if isinstance(layer, ResBlock):
-                    out = final_out if last else ctx.new_act(x.n, x.h, x.w, layer.out_channels)
+                    out = final_out if last else ctx.new_act(x.n, x.h, x.w, layer.out_channels, gn=True)
                     x = layer._run(ctx, x, emb_bias(layer), out)
                 elif isinstance(layer, SpatialTransformer):
-                    out = final_out if last else ctx.new_act(x.n, x.h, x.w, x.c)
+                    out = final_out if last else ctx.new_act(x.n, x.h, x.w, x.c, gn=True)
                     x = layer._run(ctx, x, cact, out)
                 elif isinstance(layer, Upsample):
                     out = final_out if last else ctx.new_act(x.n, x.h * 2, x.w * 2, x.c)
@@ -246,7 +291,7 @@ class UNetModel:
             if j + 1 < nb:
                 dst = x_view(j + 1)
             else:
-                dst = ctx.new_act(n, H, W, blk[0].out_channels)
+                dst = ctx.new_act(n, H, W, blk[0].out_channels, gn=True)
             mark = ar.mark()
             x = run_block(blk, cats[j], dst)
             ar.release(mark)
@@ -255,6 +300,7 @@ class UNetModel:
         self.out[0]._run(ctx, x, hn, silu=True)
         eps = Act(eps_ptr, n, H, W, 16, 16)
         self.out[2]._run(ctx, hn, eps, flags=b200.TF_EPI_OUT_F32)
+        ctx.ctx_kv = None
         return eps
 
 
