@@ -20,7 +20,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                      // one 128-byte swizzle atom of fp16
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                 // two per TMEM lane quarter: they alternate over the 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr uint32_t kTmemCols = 512;
@@ -31,7 +32,7 @@ constexpr uint32_t kAccStride = 256;  // columns between the two accumulator buf
 constexpr int kEpiStageBytes = 32 * 128;                    // per warp, 1024-aligned (swizzle atom)
 constexpr int kEpiBiasFloats = 256;
 constexpr int kEpiColsumBytes = 256 * 8;                    // per warp: {sum, sumsq} of each tile column (GroupNorm statistics)
-constexpr int kEpiBytes = 4 * kEpiStageBytes + 4 * kEpiBiasFloats * 4 + 4 * kEpiColsumBytes;  // 28672
+constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes + kEpiWarps * kEpiBiasFloats * 4 + 4 * kEpiColsumBytes;  // 49152
 
 struct ConvGeom {
   int H, W, NI;          // OUTPUT height/width, images
@@ -121,7 +122,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       tf::mbar_init(tfull_bar(a), 1);
-      tf::mbar_init(tempty_bar(a), 128);
+      tf::mbar_init(tempty_bar(a), 32 * kEpiWarps);
     }
     tf::fence_mbar_init();
   }
@@ -219,7 +220,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     // Thread = accumulator row (the 32x32b TMEM load hands every lane its own row). Everything that does not
     // depend on the accumulator is fetched while the main loop runs: the tile's bias slice (-> shared
     // memory, read back as broadcasts) and the first residual chunk (64 contiguous bytes of the thread's
@@ -227,18 +228,22 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // the row chunk into this warp's staging block in the TMA swizzle pattern (conflict-free 16-byte
     // stores), then ONE TMA store ships the 32x32 block; rows / columns outside the tensor are clipped by
     // the TMA unit, so there is no per-element address or bounds arithmetic at all.
+    // Two warps share each TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31): warp `hsel` of the pair
+    // takes the 32-column chunks with (chunk index % 2) == hsel, so a tile drains in half the time of one warp
+    // per quarter - this path is issue-latency bound and the epilogue of a single-tile CTA is not overlapped.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 2, hsel = ew >> 2;
     const int row = q * 32 + lane;
-    const uint32_t stg = epi_base + q * kEpiStageBytes;
-    float* bsm = reinterpret_cast<float*>(smem_raw + (epi_base + 4 * kEpiStageBytes - raw_u32)) + q * kEpiBiasFloats;
+    const uint32_t stg = epi_base + ew * kEpiStageBytes;
+    float* bsm = reinterpret_cast<float*>(smem_raw + (epi_base + kEpiWarps * kEpiStageBytes - raw_u32)) + ew * kEpiBiasFloats;
     const bool partial = p.partial != nullptr;
     const bool geglu = (p.flags & TF_EPI_GEGLU) != 0 && !partial;
     const bool out_f32 = (p.flags & TF_EPI_OUT_F32) != 0 || partial;
     const bool use_bias = p.bias != nullptr && !partial;
     const bool use_res = p.residual != nullptr && !partial;
     const bool gn = p.gn_stats != nullptr && !partial;
-    float2* colsum = reinterpret_cast<float2*>(smem_raw + (epi_base + 4 * kEpiStageBytes + 4 * kEpiBiasFloats * 4 - raw_u32)) +
-                     q * (kEpiColsumBytes / 8);
+    float2* colsum = reinterpret_cast<float2*>(smem_raw + (epi_base + kEpiWarps * kEpiStageBytes + kEpiWarps * kEpiBiasFloats * 4 - raw_u32)) +
+                     q * (kEpiColsumBytes / 8);   // shared by the quarter's two warps (disjoint columns)
     // swizzle of 16-byte chunk j in row r (row = lane): fp32 rows are 128 B (SW128), fp16 64 B (SW64), GEGLU 32 B (SW32)
     const uint32_t row_bytes = out_f32 ? 128u : (geglu ? 32u : 64u);
     const uint32_t swz = out_f32 ? (uint32_t)(lane & 7) : (geglu ? (uint32_t)((lane >> 2) & 1) : (uint32_t)((lane >> 1) & 3));
@@ -280,26 +285,31 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       uint4 rr[4];
-      load_res(0, rr);
+      const int c_first = hsel * 32;
+      load_res(c_first, rr);
       __syncwarp();
       tf::mbar_wait(tfull_bar(as), aphase);
       if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(4);   // accumulator of the first tile complete
       tf::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
-      for (int c = 0; c < p.bn; c += 32) {
+      if (c_first >= p.bn) {   // no chunk for this warp in a 32-column tile: only keep the barrier phases in step
+        tf::tcgen05_fence_before();
+        tf::mbar_arrive(tempty_bar(as));
+      }
+      for (int c = c_first; c < p.bn; c += 64) {
         uint32_t v[32];
         tf::tmem_ld_x16(taddr + c, v);
         tf::tmem_ld_x16(taddr + c + 16, v + 16);   // BN is a multiple of 32 (TMA store granularity)
         uint4 rn[4];
-        load_res(c + 32, rn);            // next chunk's residual goes in flight now
+        load_res(c + 64, rn);            // next chunk's residual goes in flight now
         tf::tmem_ld_wait();
-        if (c + 32 >= p.bn) {            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        if (c + 64 >= p.bn) {            // this warp's last read: hand its share of the TMEM buffer back to the MMA warp
           tf::tcgen05_fence_before();
           tf::mbar_arrive(tempty_bar(as));
         }
         // fp16 / GEGLU blocks are <= 2 KB: two staging halves alternate, so only the store issued two chunks
         // ago must have finished reading shared memory; fp32 blocks use the whole 4 KB
-        const uint32_t stg_c = stg + (out_f32 ? 0u : (uint32_t)((c >> 5) & 1) * 2048u);
+        const uint32_t stg_c = stg + (out_f32 ? 0u : (uint32_t)((c >> 6) & 1) * 2048u);
         const uint32_t srow = stg_c + lane * row_bytes;
         if (lane == 0) {
           if (out_f32) tf::tma_store_wait_read<0>();
@@ -329,11 +339,15 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           float f[32];
           const __half2* r2 = reinterpret_cast<const __half2*>(rr);
+          const float4* b4 = reinterpret_cast<const float4*>(bsm + c);   // 128-bit broadcast reads
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 rv = __half22float2(r2[j >> 1]);
-            f[j] = __uint_as_float(v[j]) + bsm[c + j] + rv.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + bsm[c + j + 1] + rv.y;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = b4[j >> 2];
+            const float2 r0 = __half22float2(r2[j >> 1]), r1 = __half22float2(r2[(j >> 1) + 1]);
+            f[j] = __uint_as_float(v[j]) + bv.x + r0.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + bv.y + r0.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + bv.z + r1.x;
+            f[j + 3] = __uint_as_float(v[j + 3]) + bv.w + r1.y;
           }
           if (out_f32) {
 #pragma unroll
@@ -399,8 +413,9 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 4; ++j) rr[j] = rn[j];
       }
       if (gn) {
-        // fold this warp's column sums into statistics units and publish slot (image, 32-row block)
-        __syncwarp();
+        // fold the quarter's column sums into statistics units and publish slot (image, 32-row block); the two
+        // warps of the quarter meet at a named barrier before (all columns written) and after (buffer reusable)
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         int img, slot;
         bool valid;
         if (p.is_conv) {
@@ -419,7 +434,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (valid) {
           const int utot = p.N / p.gn_unit, u0 = n_tile / p.gn_unit;
           float2* dst = p.gn_stats + ((size_t)img * (p.gn_hw >> 5) + slot) * utot;
-          for (int u = lane; u < p.bn / p.gn_unit; u += 32) {
+          for (int u = lane + 32 * hsel; u < p.bn / p.gn_unit; u += 64) {
             if (u0 + u < utot) {
               float a = 0.f, b = 0.f;
               for (int k = 0; k < p.gn_unit; ++k) {
@@ -430,7 +445,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       }
       if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(5);   // first tile stored (issued)
       as ^= 1;
@@ -587,7 +602,10 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
       if ((sp - 1) * kbs >= k_blocks) continue;  // an empty split
       const long tiles = (long)m_tiles * n_tiles * sp;
       const long waves = (tiles + sms - 1) / sms;
-      const double per_kb = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
+      // MMA cycles vs operand feed: an SM ingests ~52 B/clk from L2 through TMA (measured), so a 128 x bn x 64
+      // k-block is feed-bound for every bn <= 256
+      const double feed = (128.0 + bn) * 128.0 / 52.0;
+      const double per_kb = (2.0 * bn > feed) ? 2.0 * bn : feed;
       double cost = waves * (kbs * per_kb + 1500.0 + 4.0 * bn);
       if (sp > 1) cost += 8000.0 + (double)sp * M * N * 8.0 / (sms * 64.0);
       if (cost < best_cost) {

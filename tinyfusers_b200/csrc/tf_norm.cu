@@ -210,14 +210,31 @@ __global__ void gn_fused_apply_kernel(const __half* __restrict__ x1, int stride1
   if (pl >= npl) return;
   const int c0 = v * 8;
   float a8[8], b8[8];
+  {
+    float gg[8], bb[8];
+    if (gamma) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    const float2 mr = gst[c / cpg];
-    const float ga = gamma ? gamma[c] : 1.f;
-    const float be = beta ? beta[c] : 0.f;
-    a8[j] = mr.y * ga;
-    b8[j] = be - mr.x * mr.y * ga;
+      for (int j = 0; j < 8; ++j) gg[j] = 1.f;
+    }
+    if (beta) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bb[j] = 0.f;
+    }
+    int g = c0 / cpg, left = (g + 1) * cpg - c0;   // channels left in group g (one division per thread)
+    float2 mr = gst[g];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (left == 0) { ++g; mr = gst[min(g, G - 1)]; left = cpg; }
+      --left;
+      a8[j] = mr.y * gg[j];
+      b8[j] = bb[j] - mr.x * mr.y * gg[j];
+    }
   }
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
@@ -340,7 +357,11 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int nrow
     if (live && v < nvec) {
       pk[i].v = *reinterpret_cast<const uint4*>(xr + v * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j % IL] += __half2float(pk[i].h[j]);
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(pk[i].h2[j]);
+        s[(2 * j) % IL] += f.x;
+        s[(2 * j + 1) % IL] += f.y;
+      }
     }
   }
 #pragma unroll
@@ -363,9 +384,11 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int nrow
     const int v = tid + i * THREADS;
     if (live && v < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = __half2float(pk[i].h[j]) - mean[j % IL];
-        s[j % IL] += d * d;
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(pk[i].h2[j]);
+        const float d0 = f.x - mean[(2 * j) % IL], d1 = f.y - mean[(2 * j + 1) % IL];
+        s[(2 * j) % IL] += d0 * d0;
+        s[(2 * j + 1) % IL] += d1 * d1;
       }
     }
   }
@@ -390,11 +413,24 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int nrow
     if (live && v < nvec) {
       tf::Pack16 r;
       const int c0 = (v * 8) / IL;  // first channel covered by this vector (8 / IL channels)
+      if (IL == 1) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j / IL;
-        const float y = (__half2float(pk[i].h[j]) - mean[j % IL]) * rstd[j % IL] * __ldg(gamma + c) + __ldg(beta + c);
-        r.h[j] = __float2half_rn(y);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(pk[i].h2[j]);
+          const float a0 = rstd[0] * gg[2 * j], a1 = rstd[0] * gg[2 * j + 1];
+          r.h2[j] = __floats2half2_rn((f.x - mean[0]) * a0 + bb[2 * j], (f.y - mean[0]) * a1 + bb[2 * j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j / IL;
+          const float y = (__half2float(pk[i].h[j]) - mean[j % IL]) * rstd[j % IL] * __ldg(gamma + c) + __ldg(beta + c);
+          r.h[j] = __float2half_rn(y);
+        }
       }
       *reinterpret_cast<uint4*>(orow + v * 8) = r.v;
     }
