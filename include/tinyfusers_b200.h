@@ -83,6 +83,8 @@ int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_con
 
 /* test / tuning hook: force the N tile and split-K factor of the next GEMM/conv calls (0 = auto) */
 int tf_gemm_set_tuning(int force_bn, int force_splits);
+/* test / tuning hook: 0 = auto, 1 = single-CTA tiles only, 2 = CTA-pair (cta_group::2, 256-row) tiles where M > 128 */
+int tf_gemm_set_ctas(int force_ctas);
 /* debug hook: per-CTA clock64 stamps of the next GEMM/conv launches ([grid][8] int64; NULL = off) */
 int tf_gemm_set_timeline(long long* dev_buf);
 

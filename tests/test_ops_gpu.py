@@ -249,3 +249,67 @@ def test_fused_groupnorm_two_sources(oracle):
     b200.check(st, "tf_groupnorm_fused_nhwc_f16")
     ref = F.group_norm(cat.float().cpu().permute(0, 2, 1).reshape(n, c1 + c2, 16, 16), 32, gamma.cpu(), beta.cpu(), 1e-5)
     assert rel_err(y.permute(0, 2, 1).reshape(n, c1 + c2, 16, 16), ref) < TOL
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("case", [
+    ("gemm", 8192, 320, 320), ("gemm", 300, 72, 200), ("gemm", 2048, 640, 2560), ("gemm", 384, 1280, 640),
+    ("gemm_geglu", 2048, 5120, 640), ("gemm_split", 512, 1280, 5120),
+    ("conv", 2, 64, 64, 320, 320, 1), ("conv", 2, 32, 32, 640, 640, 1), ("conv", 1, 24, 40, 64, 96, 1),
+    ("conv", 2, 32, 32, 320, 320, 2), ("conv_split", 2, 16, 16, 1280, 1280, 1), ("conv", 3, 8, 8, 128, 64, 1),
+])
+def test_gemm_single_and_pair_cta_tiles(oracle, case, ctas):
+    """The same GEMM / implicit-GEMM conv through the single-CTA (128-row) and the CTA-pair (cta_group::2, 256-row)
+    kernels, each against the fp32 oracle; odd m-tile counts, ragged N, split-K and the GEGLU epilogue included."""
+    import torch.nn.functional as F
+    from tinyfusers_b200 import packing
+    from tinyfusers_b200.native.b200.ops import b200
+    from tinyfusers_b200.runtime import standalone_context, stream_ptr
+    ctx = standalone_context()
+    g = _g(21)
+    kind = case[0]
+    b200.tf_gemm_set_ctas(ctas)
+    b200.tf_gemm_set_tuning(0, 3 if kind.endswith("_split") else 0)
+    try:
+        if kind.startswith("gemm"):
+            _, M, N, K = case
+            A = torch.randn(M, K, generator=g)
+            W = torch.randn(N, K, generator=g) / math.sqrt(K)
+            bias = torch.randn(N, generator=g) * 0.1
+            geglu = kind == "gemm_geglu"
+            res = None if geglu else torch.randn(M, N, generator=g)
+            ref = A.half().float() @ W.half().float().t() + bias
+            if geglu:
+                val, gate = ref[:, :N // 2], ref[:, N // 2:]
+                ref = val * F.gelu(gate, approximate="tanh")
+                Wp, bp = packing.geglu_pack(W.cuda(), bias.cuda())
+            else:
+                ref = ref + res.half().float()
+                Wp, bp = W.half().cuda(), bias.cuda()
+            No = N // 2 if geglu else N
+            Ad = A.half().cuda()
+            out = torch.empty(M, No, dtype=torch.half, device="cuda")
+            rd = res.half().cuda() if res is not None else None
+            st = b200.tf_gemm_f16(Ad.data_ptr(), K, Wp.data_ptr(), K, out.data_ptr(), No, M, N, K, bp.data_ptr(),
+                                  rd.data_ptr() if rd is not None else None, No, b200.TF_EPI_GEGLU if geglu else 0,
+                                  ctx.ws.data_ptr(), ctx.ws_bytes, stream_ptr())
+            b200.check(st, "tf_gemm_f16")
+            assert rel_err(out, ref) < 3e-3
+        else:
+            _, n, h, w, cin, cout, stride = case
+            x = torch.randn(n, cin, h, w, generator=g)
+            wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+            bias = torch.randn(cout, generator=g) * 0.1
+            ref = oracle.conv2d(x.half().float(), wt.half().float(), bias, stride=(stride, stride), padding=[1, 1])
+            xa = x.permute(0, 2, 3, 1).contiguous().half().cuda()
+            wp = packing.conv3x3_weight(wt.cuda(), 64, 8)
+            ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+            out = torch.empty(n, ho, wo, cout, dtype=torch.half, device="cuda")
+            bc = bias.cuda()
+            st = b200.tf_conv2d_nhwc_f16(xa.data_ptr(), n, h, w, cin, cin, wp.data_ptr(), cout, 3, stride, out.data_ptr(), cout,
+                                         bc.data_ptr(), None, 0, 0, ctx.ws.data_ptr(), ctx.ws_bytes, stream_ptr())
+            b200.check(st, "tf_conv2d_nhwc_f16")
+            assert rel_err(out.permute(0, 3, 1, 2), ref) < 3e-3
+    finally:
+        b200.tf_gemm_set_ctas(0)
+        b200.tf_gemm_set_tuning(0, 0)

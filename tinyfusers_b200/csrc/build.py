@@ -25,7 +25,7 @@ FLAGS = [
     "-I", os.path.join(ROOT, "include"),
     "-I", HERE,
     "-DTF_BUILDING_LIB",
-]
+] + (["-DTF_GEMM_TRACE=1"] if os.environ.get("TF_GEMM_TRACE") == "1" else [])
 
 
 def sources():

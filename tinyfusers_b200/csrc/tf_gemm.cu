@@ -12,11 +12,16 @@
 // (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 // Tile = 128 x BN x 64, BN in {16..256 step 16} chosen per shape; optional split-K writes fp32 partials
 // that tf_splitk_reduce folds (deep, small-M UNet levels are weight-bandwidth bound at batch 2).
+#include <stdlib.h>
+
 #include "tf_common.cuh"
 #include "tinyfusers_b200.h"
 
 namespace {
 
+#ifndef TF_GEMM_TRACE
+#define TF_GEMM_TRACE 0
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;                      // one 128-byte swizzle atom of fp16
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
@@ -48,6 +53,7 @@ struct ConvGeom {
 struct GemmParams {
   int M, N, K;
   int bn, m_tiles, n_tiles, splits, k_blocks, kb_per_split, stages;
+  int ctas;   // 1, or 2 = CTA-pair kernel (256-row pair tiles)
   int is_conv;
   ConvGeom g;
   void* out;
@@ -85,6 +91,12 @@ __device__ __forceinline__ int tile_row_to_m(const GemmParams& p, int mt, int r)
   return (n * g.H + y) * g.W + x;
 }
 
+// kCtas == 2: the CTA pair variant. Two CTAs of a cluster (ranks 0 / 1 = even / odd m-tile of a 256-row pair tile)
+// run ONE tcgen05.mma.cta_group::2 stream issued by the leader; each CTA loads its own 128 rows of A and only
+// HALF of the weight tile, so the L2 -> SM operand traffic per FLOP (the measured limiter of these kernels)
+// drops by (128 + bn) / (128 + bn/2). Producer and epilogue run in both CTAs; the leader owns the `full`
+// and `tmem empty` barriers, commits are multicast to both CTAs.
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -96,7 +108,10 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const uint32_t b_stage_bytes = (uint32_t)p.bn * 128u;
+  constexpr bool k2 = kCtas == 2;
+  const uint32_t rank = k2 ? tf::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const uint32_t b_stage_bytes = (uint32_t)p.bn * (k2 ? 64u : 128u);   // pair: each CTA holds bn/2 weight rows
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + p.stages * A_STAGE_BYTES;
   const uint32_t epi_base = smem_b + p.stages * b_stage_bytes;
@@ -117,104 +132,150 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      tf::mbar_init(full_bar(s), 1);
+      tf::mbar_init(full_bar(s), kCtas);   // pair: leader's expect_tx arrive + the peer producer's remote arrive
       tf::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       tf::mbar_init(tfull_bar(a), 1);
-      tf::mbar_init(tempty_bar(a), 32 * kEpiWarps);
+      tf::mbar_init(tempty_bar(a), 32 * kEpiWarps * kCtas);
     }
     tf::fence_mbar_init();
   }
   if (warp == 2) {
-    tf::tmem_alloc(tmem_slot, kTmemCols);
-    tf::tmem_relinquish();
+    if (k2) { tf::tmem_alloc_2sm(tmem_slot, kTmemCols); tf::tmem_relinquish_2sm(); }
+    else { tf::tmem_alloc(tmem_slot, kTmemCols); tf::tmem_relinquish(); }
   }
   tf::tcgen05_fence_before();
-  __syncthreads();
+  if (k2) tf::cluster_sync_all();   // the peer's barriers must exist before anything is signalled across the pair
+  else __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   tf::pdl_wait();   // barriers / TMEM / descriptors were set up while the producer kernels drained
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // work items: (m-tile | pair of m-tiles) x n-tile x split, strided over the CTAs | clusters of the grid
+  const int total_tiles = (k2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
+  const int t_first = k2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = k2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   long long* tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 16 : nullptr;
+#if TF_GEMM_TRACE   // debug build only (TF_GEMM_TRACE=1 python -m tinyfusers_b200.csrc.build): the stamps cost issue slots in the role loops
 #define TF_STAMP(i) do { if (tl) tl[i] = clock64(); } while (0)
+#define TF_TRACE_KB(off) do { if (p.timeline && blockIdx.x == 0 && t == t_first && kb - kb0 < 256) p.timeline[148 * 16 + (off) + (kb - kb0)] = clock64() - t_entry; } while (0)
+#else
+#define TF_STAMP(i) do { } while (0)
+#define TF_TRACE_KB(off) do { } while (0)
+#endif
   if (threadIdx.x == 0) { TF_STAMP(0); if (tl) tl[7] = t_entry; }   // setup done (barriers, TMEM alloc)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = t % p.splits;
-        const int t1 = t / p.splits;
-        const int nt = t1 % p.n_tiles;
-        const int mt = t1 / p.n_tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-        int x0 = 0, y0 = 0, n0 = 0;
-        if (p.is_conv) {
-          const ConvGeom& g = p.g;
-          int tx = mt % g.tiles_x;
-          int t2 = mt / g.tiles_x;
-          x0 = tx * g.TW * g.cscale - g.pad;
-          y0 = (t2 % g.tiles_y) * g.TH * g.cscale - g.pad;
-          n0 = (t2 / g.tiles_y) * g.TN;
-        }
-        for (int kb = kb0; kb < kb1; ++kb) {
-          tf::mbar_wait(empty_bar(stage), phase ^ 1u);
-          tf::mbar_expect_tx(full_bar(stage), tx_bytes);
-          const uint32_t a_dst = smem_a + stage * A_STAGE_BYTES;
-          const uint32_t b_dst = smem_b + stage * b_stage_bytes;
-          if (p.is_conv) {
-            const int tap = kb / p.g.cblocks;
-            const int cb = kb - tap * p.g.cblocks;
-            const int r = tap / p.g.ksize;
-            const int s = tap - r * p.g.ksize;
-            tf::tma_load_4d(a_dst, &tmA, full_bar(stage), cb * BK, x0 + s, y0 + r, n0);
+    // The whole warp walks the loop converged and one elected lane issues: every address / coordinate is then
+    // warp-uniform (uniform-register arithmetic, no per-lane R2UR waterfall around UTMALDG), and the k-block
+    // coordinates advance by counters instead of divisions. A single thread running ~150 dependent instructions per
+    // k-block was the measured limiter of the main loop (~500-700 cycles per k-block vs 320 of MMA).
+    const bool elected = tf::elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t a_dst = smem_a, b_dst = smem_b, fbar = full_bar(0), ebar = empty_bar(0);   // advanced with the stage
+    const uint32_t fbar_leader0 = k2 ? tf::mapa_shared(full_bar(0), 0) : 0u;
+    uint32_t fb = fbar_leader0;
+    const uint32_t tx_bytes = (A_STAGE_BYTES + b_stage_bytes) * kCtas;   // the leader's barrier counts both CTAs' bytes
+    const int b_row_off = k2 ? (int)rank * (p.bn >> 1) : 0;
+    const int cblocks = p.is_conv ? p.g.cblocks : 1, ksize = p.is_conv ? p.g.ksize : 1;
+    for (int t = t_first; t < total_tiles; t += t_step) {
+      const int split = t % p.splits;
+      const int t1 = t / p.splits;
+      const int nt = t1 % p.n_tiles;
+      const int mt = k2 ? 2 * (t1 / p.n_tiles) + (int)rank : t1 / p.n_tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      int x0 = 0, y0 = 0, n0 = 0;
+      if (p.is_conv) {
+        const ConvGeom& g = p.g;
+        int tx = mt % g.tiles_x;
+        int t2 = mt / g.tiles_x;
+        x0 = tx * g.TW * g.cscale - g.pad;
+        y0 = (t2 % g.tiles_y) * g.TH * g.cscale - g.pad;
+        n0 = (t2 / g.tiles_y) * g.TN;
+      }
+      // position of k-block kb0: conv = (tap row r, tap column sx, channel block cb); gemm = column kcol
+      int r = (kb0 / cblocks) / ksize, sx = (kb0 / cblocks) % ksize, cb = kb0 % cblocks;
+      int kcol = kb0 * BK;
+      const int arow = mt * BM, brow = nt * p.bn + b_row_off;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        tf::mbar_wait(ebar, phase ^ 1u);
+        if (elected) {
+          TF_TRACE_KB(0);
+          if (k2) {
+            if (leader) tf::mbar_expect_tx(fbar, tx_bytes);
+            else tf::mbar_arrive_cluster(fb);   // fb: the leader's barrier
+            if (p.is_conv) tf::tma_load_4d_2sm(a_dst, &tmA, fb, cb * BK, x0 + sx, y0 + r, n0);
+            else tf::tma_load_2d_2sm(a_dst, &tmA, fb, kcol, arow);
+            tf::tma_load_2d_2sm(b_dst, &tmB, fb, kcol, brow);
           } else {
-            tf::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, mt * BM);
+            tf::mbar_expect_tx(fbar, tx_bytes);
+            if (p.is_conv) tf::tma_load_4d(a_dst, &tmA, fbar, cb * BK, x0 + sx, y0 + r, n0);
+            else tf::tma_load_2d(a_dst, &tmA, fbar, kcol, arow);
+            tf::tma_load_2d(b_dst, &tmB, fbar, kcol, brow);
           }
-          tf::tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, nt * p.bn);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        kcol += BK;
+        if (++cb == cblocks) { cb = 0; if (++sx == ksize) { sx = 0; ++r; } }
+        a_dst += A_STAGE_BYTES; b_dst += b_stage_bytes; fbar += 8u; ebar += 8u; fb += 8u;
+        if (++stage == S) {
+          stage = 0; phase ^= 1u;
+          a_dst = smem_a; b_dst = smem_b; fbar = full_bar(0); ebar = empty_bar(0); fb = fbar_leader0;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = tf::umma_idesc_f16(BM, p.bn);
+    // ===================== MMA issuer (leader CTA; whole warp converged, one elected lane issues) =====================
+    if (leader) {
+      const bool elected = tf::elect_one();
+      const uint32_t idesc = tf::umma_idesc_f16(BM * kCtas, p.bn);
+      const uint64_t adesc0 = tf::umma_desc_sw128_kmajor(smem_a);
+      const uint64_t bdesc0 = tf::umma_desc_sw128_kmajor(smem_b);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      // descriptors / barrier addresses advance with the stage (the start-address field counts 16-byte units and
+      // never carries out of its 14 bits)
+      uint64_t adesc = adesc0, bdesc = bdesc0;
+      uint32_t fbar = full_bar(0), ebar = empty_bar(0);
+      const uint64_t a_step = (uint64_t)(A_STAGE_BYTES >> 4), b_step = (uint64_t)(b_stage_bytes >> 4);
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int split = t % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         tf::mbar_wait(tempty_bar(as), aphase ^ 1u);
-        if (t == blockIdx.x) TF_STAMP(1);
+        if (t == t_first && elected) TF_STAMP(1);
         tf::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
-          tf::mbar_wait(full_bar(stage), phase);
-          if (t == blockIdx.x && kb == kb0) TF_STAMP(2);   // first operands landed
+          tf::mbar_wait(fbar, phase);
           tf::tcgen05_fence_after();
-          const uint64_t adesc = tf::umma_desc_sw128_kmajor(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = tf::umma_desc_sw128_kmajor(smem_b + stage * b_stage_bytes);
+          if (elected) {
+            if (t == t_first && kb == kb0) TF_STAMP(2);   // first operands landed
+            TF_TRACE_KB(256);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes per UMMA_K step inside the 128-byte swizzle atom (start-address field is >>4)
-            tf::umma_f16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc,
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 bytes per UMMA_K step inside the 128-byte swizzle atom (start-address field is >>4)
+              if (k2) tf::umma_f16_ss_2sm(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tf::umma_f16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+            if (k2) tf::umma_commit_2sm(ebar);
+            else tf::umma_commit(ebar);
           }
-          tf::umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs have read it
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          adesc += a_step; bdesc += b_step; fbar += 8u; ebar += 8u;
+          if (++stage == S) { stage = 0; phase ^= 1u; adesc = adesc0; bdesc = bdesc0; fbar = full_bar(0); ebar = empty_bar(0); }
         }
-        if (t == blockIdx.x) TF_STAMP(3);   // all MMAs of the first tile issued
-        tf::umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (elected) {
+          if (t == t_first) TF_STAMP(3);   // all MMAs of the first tile issued
+          // accumulator complete -> epilogue (of both CTAs)
+          if (k2) tf::umma_commit_2sm(tfull_bar(as));
+          else tf::umma_commit(tfull_bar(as));
+        }
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -249,11 +310,13 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t swz = out_f32 ? (uint32_t)(lane & 7) : (geglu ? (uint32_t)((lane >> 2) & 1) : (uint32_t)((lane >> 1) & 3));
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const uint32_t tempty_remote0 = k2 ? tf::mapa_shared(tempty_bar(0), 0) : 0u;   // the leader's barriers
+    const uint32_t tempty_remote1 = k2 ? tf::mapa_shared(tempty_bar(1), 0) : 0u;
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int split = t % p.splits;
       const int t1 = t / p.splits;
       const int nt = t1 % p.n_tiles;
-      const int mt = t1 / p.n_tiles;
+      const int mt = k2 ? 2 * (t1 / p.n_tiles) + (int)rank : t1 / p.n_tiles;
       const int n_tile = nt * p.bn;
       const int m_own = tile_row_to_m(p, mt, row);
       // store coordinates of this warp's 32-row block
@@ -289,13 +352,15 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       load_res(c_first, rr);
       __syncwarp();
       tf::mbar_wait(tfull_bar(as), aphase);
-      if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(4);   // accumulator of the first tile complete
+      if (t == t_first && threadIdx.x == 64) TF_STAMP(4);   // accumulator of the first tile complete
       tf::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
-      if (c_first >= p.bn) {   // no chunk for this warp in a 32-column tile: only keep the barrier phases in step
+      auto release_tmem = [&]() {
         tf::tcgen05_fence_before();
-        tf::mbar_arrive(tempty_bar(as));
-      }
+        if (k2) tf::mbar_arrive_cluster(as ? tempty_remote1 : tempty_remote0);
+        else tf::mbar_arrive(tempty_bar(as));
+      };
+      if (c_first >= p.bn) release_tmem();   // no chunk for this warp in a 32-column tile: keep the barrier phases in step
       for (int c = c_first; c < p.bn; c += 64) {
         uint32_t v[32];
         tf::tmem_ld_x16(taddr + c, v);
@@ -303,10 +368,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint4 rn[4];
         load_res(c + 64, rn);            // next chunk's residual goes in flight now
         tf::tmem_ld_wait();
-        if (c + 64 >= p.bn) {            // this warp's last read: hand its share of the TMEM buffer back to the MMA warp
-          tf::tcgen05_fence_before();
-          tf::mbar_arrive(tempty_bar(as));
-        }
+        if (c + 64 >= p.bn) release_tmem();   // this warp's last read: hand its share of the TMEM buffer back to the MMA warp
         // fp16 / GEGLU blocks are <= 2 KB: two staging halves alternate, so only the store issued two chunks
         // ago must have finished reading shared memory; fp32 blocks use the whole 4 KB
         const uint32_t stg_c = stg + (out_f32 ? 0u : (uint32_t)((c >> 6) & 1) * 2048u);
@@ -447,7 +509,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       }
-      if (t == blockIdx.x && threadIdx.x == 64) TF_STAMP(5);   // first tile stored (issued)
+      if (t == t_first && threadIdx.x == 64) TF_STAMP(5);   // first tile stored (issued)
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -455,13 +517,18 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tf::tcgen05_fence_before();
+  // idle lanes / warps park at the CTA barrier (hardware-blocking); the cluster barrier, which polls, is only
+  // entered once the whole CTA is done: neither CTA may retire while the other still signals it / reads its smem
   __syncthreads();
+  if (k2) tf::cluster_sync_all();
   if (warp == 2) {
     tf::tcgen05_fence_after();
-    tf::tmem_dealloc(tmem_base, kTmemCols);
+    if (k2) tf::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tf::tmem_dealloc(tmem_base, kTmemCols);
   }
   if (threadIdx.x == 0) TF_STAMP(6);
 #undef TF_STAMP
+#undef TF_TRACE_KB
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,7 +634,7 @@ __global__ void tf_splitk_reduce_stats_kernel(const float* __restrict__ partial,
 // host side
 // ------------------------------------------------------------------------------------------------
 struct TileChoice {
-  int bn, splits;
+  int bn, splits, ctas;
 };
 
 // crude cycle model: per 64-deep k-block a CTA needs max(tensor, smem-feed) cycles; pick the
@@ -578,10 +645,12 @@ static int lcm_i(int a, int b) {
   return a / x * b;
 }
 
+static int g_force_bn = 0, g_force_splits = 0, g_force_ctas = 0;
+
 static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool allow_split,
                                size_t ws_bytes, int M, int force_bn, int force_splits, int bn_mult = 32) {
   const int sms = tf_num_sms();
-  TileChoice best{128, 1};
+  TileChoice best{128, 1, 1};
   double best_cost = 1e30;
   (void)flags;
   const int step = bn_mult;  // epilogue ships 32-column blocks; GroupNorm statistics units must not straddle tiles
@@ -600,35 +669,39 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
       }
       const int kbs = ceil_div_i(k_blocks, sp);
       if ((sp - 1) * kbs >= k_blocks) continue;  // an empty split
-      const long tiles = (long)m_tiles * n_tiles * sp;
-      const long waves = (tiles + sms - 1) / sms;
-      // MMA cycles vs operand feed: an SM ingests ~52 B/clk from L2 through TMA (measured), so a 128 x bn x 64
-      // k-block is feed-bound for every bn <= 256
-      const double feed = (128.0 + bn) * 128.0 / 52.0;
-      const double per_kb = (2.0 * bn > feed) ? 2.0 * bn : feed;
-      double cost = waves * (kbs * per_kb + 1500.0 + 4.0 * bn);
-      if (sp > 1) cost += 8000.0 + (double)sp * M * N * 8.0 / (sms * 64.0);
-      if (cost < best_cost) {
-        best_cost = cost;
-        best = {bn, sp};
+      for (int ctas = 1; ctas <= 2; ++ctas) {
+        if (g_force_ctas > 0 && ctas != g_force_ctas) continue;
+        if (ctas == 2 && (m_tiles < 2 || bn % 32 != 0)) continue;   // a pair needs two m-tiles to share a weight tile
+        const long mt_eff = ctas == 2 ? 2L * ((m_tiles + 1) / 2) : m_tiles;
+        const long tiles = mt_eff * n_tiles * sp;
+        const long waves = (tiles + sms - 1) / sms;
+        // MMA cycles vs operand feed: an SM ingests ~52 B/clk from L2 through TMA (measured), so a 128 x bn x 64
+        // k-block is feed-bound for every bn <= 256; a CTA pair loads only half of the weight tile per SM
+        const double feed = (128.0 + (double)bn / ctas) * 128.0 / 52.0;
+        const double per_kb = (2.0 * bn > feed) ? 2.0 * bn : feed;
+        double cost = waves * (kbs * per_kb + 1500.0 + 4.0 * bn + (ctas == 2 ? 300.0 : 0.0));
+        if (sp > 1) cost += 8000.0 + (double)sp * M * N * 8.0 / (sms * 64.0);
+        if (cost < best_cost) {
+          best_cost = cost;
+          best = {bn, sp, ctas};
+        }
       }
     }
   }
   return best;
 }
 
-static int g_force_bn = 0, g_force_splits = 0;
 static long long* g_timeline = nullptr;
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams& p,
                        cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmemBudget));
+    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
-  const int stage_bytes = A_STAGE_BYTES + p.bn * 128;
+  const int stage_bytes = A_STAGE_BYTES + p.bn * 128 / p.ctas;
   int stages = (kSmemBudget - 2048 - kEpiBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) {
@@ -640,10 +713,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   // allocation can never contend with a co-resident CTA.
   size_t smem = (size_t)stages * stage_bytes + kEpiBytes + 2048;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
   p.timeline = g_timeline;
-  TF_LAUNCH(tf_gemm_kernel, grid, kThreads, smem, stream, tmA, tmB, tmC, p);
+  if (p.ctas == 2) {
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+    const int max_pairs = tf_num_sms() / 2;
+    const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    (void)tf_launch_pdl_cluster(tf_gemm_kernel<2>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, p);
+  } else {
+    const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
+    static const bool dbg_cluster = getenv("TF_DEBUG_CLUSTER1") != nullptr;   // experiment: single-CTA kernel, cluster launch
+    if (dbg_cluster && grid % 2 == 0)
+      (void)tf_launch_pdl_cluster(tf_gemm_kernel<1>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, p);
+    else
+    TF_LAUNCH(tf_gemm_kernel<1>, grid, kThreads, smem, stream, tmA, tmB, tmC, p);
+  }
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   if (p.splits > 1 && p.gn_stats != nullptr) {
@@ -687,6 +771,11 @@ extern "C" int tf_gemm_set_tuning(int force_bn, int force_splits) {
   return TF_OK;
 }
 
+extern "C" int tf_gemm_set_ctas(int force_ctas) {
+  g_force_ctas = force_ctas;   // 0 = auto, 1 = single-CTA tiles, 2 = CTA-pair tiles (where M > 128)
+  return TF_OK;
+}
+
 static int gn_check(const void* gn_stats, int gn_unit, int gn_hw, int M, int N, int flags, const char* who) {
   if (!gn_stats) return TF_OK;
   if (flags & (TF_EPI_GEGLU | TF_EPI_OUT_F32)) {
@@ -727,6 +816,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
                                g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32);
   p.bn = tc.bn;
   p.splits = tc.splits;
+  p.ctas = tc.ctas;
   p.n_tiles = ceil_div_i(N, p.bn);
   p.kb_per_split = ceil_div_i(p.k_blocks, p.splits);
   p.out = out; p.ldc = ldc; p.bias = bias;
@@ -746,7 +836,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {BK, (uint32_t)p.bn};
+    uint32_t box[2] = {BK, (uint32_t)(p.bn / p.ctas)};
     uint32_t es[2] = {1, 1};
     int rc = tf_encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W, dims, strides, box, es,
                             CU_TENSOR_MAP_SWIZZLE_128B);
@@ -849,6 +939,7 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
                                g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32);
   p.bn = tc.bn;
   p.splits = tc.splits;
+  p.ctas = tc.ctas;
   p.n_tiles = ceil_div_i(Cout, p.bn);
   p.kb_per_split = ceil_div_i(p.k_blocks, p.splits);
   p.out = out; p.ldc = ldc; p.bias = bias;
@@ -869,7 +960,7 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)Cout};
     uint64_t strides[1] = {(uint64_t)p.K * 2};
-    uint32_t box[2] = {BK, (uint32_t)p.bn};
+    uint32_t box[2] = {BK, (uint32_t)(p.bn / p.ctas)};
     uint32_t es[2] = {1, 1};
     int rc = tf_encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w, dims, strides, box, es,
                             CU_TENSOR_MAP_SWIZZLE_128B);

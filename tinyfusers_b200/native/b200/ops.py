@@ -28,6 +28,7 @@ _SIGNATURES = {
     "tf_launch_count": (c_longlong, []),
     "tf_launch_count_reset": (None, []),
     "tf_gemm_set_tuning": (c_int, [c_int, c_int]),
+    "tf_gemm_set_ctas": (c_int, [c_int]),
     "tf_gemm_set_timeline": (c_int, [_P]),
     "tf_gemm_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
                             _P, c_size_t, _P]),

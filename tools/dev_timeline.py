@@ -5,14 +5,19 @@ from tinyfusers_b200.native.b200.ops import b200
 dev = torch.device("cuda:0"); b200.init(0)
 S = lambda: torch.cuda.current_stream().cuda_stream
 ws = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-tl = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+tl = torch.zeros(148 * 16 + 512, dtype=torch.int64, device=dev)
 def report(name, grid):
     torch.cuda.synchronize()
-    t = tl.view(148, 16)[:grid].cpu().double()
+    t = tl[:148 * 16].view(148, 16)[:grid:2].cpu().double()   # even CTAs (the leaders in pair mode)
     e = t[:, 7:8]
     names = ["setup_done", "mma_start", "first_operands", "mma_issued", "acc_ready", "stored", "exit"]
     d = (t[:, :7] - e)
     ex = {k: int((t[:, i] - e[:, 0]).median().item()) for k, i in (("c0_done", 12), ("c1_tmem_loaded", 8), ("c1_staged", 9), ("c1_lds_done", 10), ("c1_done", 11))}
+    tr = tl[148 * 16:].cpu()
+    nk = int((tr[256:] > 0).sum())
+    print("   issue:", [int(v) for v in tr[:nk][:48]])
+    print("   full :", [int(v) for v in tr[256:256 + nk][:48]])
+    tl.zero_()
     print(name, "grid", grid, " median cycles since kernel entry:", {n: int(d[:, i].median().item()) for i, n in enumerate(names)}, ex)
 def gemm(M, N, K, residual=False, geglu=False, dbg=0):
     A = torch.randn(M, K, device=dev).half(); W = (torch.randn(N, K, device=dev) / 30).half(); b = torch.randn(N, device=dev)
@@ -32,9 +37,11 @@ def conv(NI, H, W, Cin, Cout):
         b200.check(b200.tf_conv2d_nhwc_f16(x.data_ptr(), NI, H, W, Cin, Cin, w.data_ptr(), Cout, 3, 1, out.data_ptr(), Cout, b.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), S()), "conv")
     b200.tf_gemm_set_timeline(None)
     report(f"conv {NI}x{H}x{W} {Cin}->{Cout}", 128)
-gemm(8192, 320, 320, residual=True)
-gemm(8192, 320, 320)
-gemm(8192, 320, 1280, residual=True)
-gemm(8192, 2560, 320, geglu=True)
-conv(2, 64, 64, 320, 320)
-conv(2, 32, 32, 640, 640)
+for ctas in ((1,) if os.environ.get('TF_DEBUG_CLUSTER1') else (1, 2)):
+    b200.tf_gemm_set_ctas(ctas)
+    print("=== ctas", ctas)
+    gemm(8192, 320, 320, residual=True)
+    gemm(8192, 320, 1280, residual=True)
+    gemm(8192, 2560, 320, geglu=True)
+    conv(2, 64, 64, 320, 320)
+    conv(2, 32, 32, 640, 640)
