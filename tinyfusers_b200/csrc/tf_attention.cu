@@ -67,7 +67,8 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t smem_k = smem_q + q_bytes;
   const uint32_t smem_v = smem_k + ST * k_bytes;
   const uint32_t smem_p = smem_v + ST * k_bytes;
-  const uint32_t bar_base = smem_p + p_bytes;
+  const uint32_t smem_ones = smem_p + p_bytes;   // 16 x 64 fp16 ones (one 128B-swizzle atom): the row sums come from the MMA
+  const uint32_t bar_base = smem_ones + 2048;
   // barriers
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
@@ -102,13 +103,19 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tf::tmem_alloc(tmem_slot, p.tmem_cols);
     tf::tmem_relinquish();
   }
+  if (warp >= 2) {   // 2 KB of fp16 1.0 (swizzling a constant tile is the identity)
+    const uint32_t i = threadIdx.x - 64;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_ones + i * 16u), "r"(0x3C003C00u) : "memory");
+    tf::fence_proxy_async_smem();
+  }
   tf::tcgen05_fence_before();
   __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   tf::pdl_wait();
   const uint32_t tmem_s0 = tmem_base;            // S buffers: columns [0,BN) and [BN,2BN)
-  const uint32_t tmem_o = tmem_base + 2 * BN;    // O: dp columns
+  const uint32_t tmem_o = tmem_base + 2 * BN;    // O: dp columns, then 16 columns of L = P . 1 (the softmax denominator)
+  const uint32_t tmem_l = tmem_o + p.dp;
 
   const int nkv = p.nkv;
   const int slabs = p.dp / 16;
@@ -135,6 +142,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc_s = tf::umma_idesc_f16(BQ, BN);
       const uint32_t idesc_o = tf::umma_idesc_f16(BQ, p.dp);
+      const uint32_t idesc_l = tf::umma_idesc_f16(BQ, 16);
       auto issue_s = [&](int j) {
         const int s = j % ST;
         tf::mbar_wait(kv_full(s), (uint32_t)(j / ST) & 1u);
@@ -162,6 +170,9 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tf::umma_f16_ss(tmem_o, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub,
                           tf::umma_desc_sw128_kmajor(vbase + atom * (p.dp * 128)) + 2u * sub, idesc_o,
                           (j > 0 || k > 0) ? 1u : 0u);
+          // L += P . ones: the denominator accumulates from the SAME fp16-rounded P the numerator uses
+          tf::umma_f16_ss(tmem_l, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub,
+                          tf::umma_desc_sw128_kmajor(smem_ones) + 2u * sub, idesc_l, (j > 0 || k > 0) ? 1u : 0u);
         }
         tf::umma_commit(pv_done);
         tf::umma_commit(kv_empty(s));
@@ -172,8 +183,11 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
-    float m_run = -INFINITY;  // running max, already in the scaled log2 domain
-    float l_run = 0.f;
+    // Online softmax, one thread per query row. Per element the loop is FMNMX (max) + FFMA (scale and shift folded)
+    // + MUFU.EX2 + half a pack: the row sum is NOT accumulated here (the L columns of the PV MMA do it), and the
+    // running max is lazy: O / L are only rescaled when a row's max grows by more than 2^8 (P stays <= 256 in
+    // fp16, accumulation is fp32, and O / L is exact whatever reference max is used).
+    float m_run = -INFINITY;  // reference max of this row, in the scaled log2 domain
     for (int j = 0; j < nkv; ++j) {
       const int buf = j & 1;
       tf::mbar_wait(s_full(buf), ((uint32_t)(j >> 1)) & 1u);
@@ -185,28 +199,32 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tf::tcgen05_fence_before();
       tf::mbar_arrive(s_empty(buf));
       const int valid = min(BN, p.Tk - j * BN);  // keys >= Tk are padding / another batch
-      float mx = -INFINITY;
+      if (valid < BN) {
 #pragma unroll
-      for (int i = 0; i < BN; ++i) {
-        float x = __uint_as_float(v[i]) * p.scale_log2;
-        x = (i < valid) ? x : -INFINITY;
-        v[i] = __float_as_uint(x);
-        mx = fmaxf(mx, x);
+        for (int i = 0; i < BN; ++i)
+          if (i >= valid) v[i] = 0xff800000u;   // -inf
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      float rowsum = 0.f;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < BN; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(v[i + u]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;   // scale > 0
+      float alpha = 1.0f;
+      if (mx > m_run + 8.0f) {          // also taken on the first block (m_run = -inf)
+        alpha = exp2f(m_run - mx);      // 0 on the first block
+        m_run = mx;
+      }
+      const float neg_m = -m_run;
       uint32_t pk[BN / 2];
 #pragma unroll
       for (int i = 0; i < BN; i += 2) {
-        const float p0 = exp2f(__uint_as_float(v[i]) - m_new);
-        const float p1 = exp2f(__uint_as_float(v[i + 1]) - m_new);
-        rowsum += p0 + p1;
+        const float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+        const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
         __half2 hh = __floats2half2_rn(p0, p1);
         pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
       // P smem and O are owned by the tensor core until PV_{j-1} has completed
       if (j > 0) {
         tf::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
@@ -227,7 +245,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       // rescale the running output if any row of this warp moved its max
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        for (int c = 0; c < p.dp; c += 16) {
+        for (int c = 0; c < p.dp + 16; c += 16) {   // O and the L columns
           uint32_t o[16];
           tf::tmem_ld_x16(tmem_o + lane_field + c, o);
           tf::tmem_ld_wait();
@@ -244,7 +262,13 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---- epilogue: O / l -> fp16 -> global ----
     tf::mbar_wait(pv_done, (uint32_t)(nkv - 1) & 1u);
     tf::tcgen05_fence_after();
-    const float inv_l = 1.0f / l_run;
+    float inv_l;
+    {
+      uint32_t l16[16];
+      tf::tmem_ld_x16(tmem_l + lane_field, l16);
+      tf::tmem_ld_wait();
+      inv_l = 1.0f / __uint_as_float(l16[0]);
+    }
     const int t = qt * BQ + row;
     __half* orow = p.out + (long long)b * p.osb + (long long)h * p.osh + (long long)t * p.ost;
     for (int c = 0; c < p.dp; c += 16) {
@@ -305,12 +329,12 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
 
   int BN = 64;  // 64-key blocks: two CTAs per SM (TMEM 2*64 + dp <= 256 columns) hide softmax latency
   if (g_force_attn_bn == 64 || g_force_attn_bn == 128) BN = g_force_attn_bn;
-  if (BN == 128 && 2 * 128 + dp > 512) BN = 64;
+  if (BN == 128 && 2 * 128 + dp + 16 > 512) BN = 64;
 
   AttnParams p{};
   p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp;
   p.nkv = ceil_div_i(Tk, BN);
-  uint32_t need = 2 * BN + dp, cols = 32;
+  uint32_t need = 2 * BN + dp + 16, cols = 32;   // S double buffer, O, L
   while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -319,12 +343,12 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
 
   const size_t q_bytes = (size_t)BQ * dp * 2, k_bytes = (size_t)BN * dp * 2, p_bytes = (size_t)BQ * BN * 2;
   const size_t budget = (cols <= 256 ? 113 : 227) * 1024 - 2048;
-  int stages = (int)((budget - q_bytes - p_bytes) / (2 * k_bytes));
+  int stages = (int)((budget - q_bytes - p_bytes - 2048) / (2 * k_bytes));
   if (stages > 4) stages = 4;
   if (stages > p.nkv) stages = p.nkv < 1 ? 1 : p.nkv;
   TF_CHECK_ARG(stages >= 1, "tf_attention_f16: head dim %d does not fit shared memory", dp);
   p.stages = stages;
-  const size_t smem = q_bytes + p_bytes + (size_t)stages * 2 * k_bytes + 2048;
+  const size_t smem = q_bytes + p_bytes + 2048 + (size_t)stages * 2 * k_bytes + 2048;
 
   CUtensorMap tmQ, tmK, tmV;
   {

@@ -368,6 +368,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint4 rn[4];
         load_res(c + 64, rn);            // next chunk's residual goes in flight now
         tf::tmem_ld_wait();
+        if (t == t_first && threadIdx.x == 64) TF_STAMP(c == c_first ? 8 : 11);
         if (c + 64 >= p.bn) release_tmem();   // this warp's last read: hand its share of the TMEM buffer back to the MMA warp
         // fp16 / GEGLU blocks are <= 2 KB: two staging halves alternate, so only the store issued two chunks
         // ago must have finished reading shared memory; fp32 blocks use the whole 4 KB
@@ -456,6 +457,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (t == t_first && threadIdx.x == 64 && c == c_first) TF_STAMP(9);
         tf::fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
@@ -471,6 +473,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           tf::tma_store_commit();
         }
+        if (t == t_first && threadIdx.x == 64) TF_STAMP(c == c_first ? 10 : 12);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rr[j] = rn[j];
       }

@@ -37,11 +37,50 @@ def conv(NI, H, W, Cin, Cout):
         b200.check(b200.tf_conv2d_nhwc_f16(x.data_ptr(), NI, H, W, Cin, Cin, w.data_ptr(), Cout, 3, 1, out.data_ptr(), Cout, b.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), S()), "conv")
     b200.tf_gemm_set_timeline(None)
     report(f"conv {NI}x{H}x{W} {Cin}->{Cout}", 128)
-for ctas in ((1,) if os.environ.get('TF_DEBUG_CLUSTER1') else (1, 2)):
-    b200.tf_gemm_set_ctas(ctas)
-    print("=== ctas", ctas)
-    gemm(8192, 320, 320, residual=True)
-    gemm(8192, 320, 1280, residual=True)
-    gemm(8192, 2560, 320, geglu=True)
-    conv(2, 64, 64, 320, 320)
-    conv(2, 32, 32, 640, 640)
+def cadence(name):
+    torch.cuda.synchronize()
+    tr = tl[148 * 16:].cpu()
+    nk = int((tr[256:] > 0).sum())
+    full = [int(v) for v in tr[256:256 + nk]]
+    iss = [int(v) for v in tr[:nk]]
+    if nk > 8:
+        print(f"{name}: kbs={nk} full cadence {(full[-1] - full[4]) / (nk - 5):.0f} cyc/kb, issue cadence {(iss[-1] - iss[4]) / (nk - 5):.0f}, first full {full[0]}, issue->full latency {full[0] - iss[0]}")
+    tl.zero_()
+def gemm_c(M, N, K, bn, ctas):
+    b200.tf_gemm_set_ctas(ctas); b200.tf_gemm_set_tuning(bn, 1)
+    A = torch.randn(M, K, device=dev).half(); W = (torch.randn(N, K, device=dev) / 30).half(); b = torch.randn(N, device=dev)
+    out = torch.empty(M, N, dtype=torch.half, device=dev)
+    for i in range(3):
+        b200.tf_gemm_set_timeline(tl.data_ptr() if i == 2 else None)
+        b200.check(b200.tf_gemm_f16(A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, b.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), S()), "gemm")
+    b200.tf_gemm_set_timeline(None)
+    cadence(f"gemm {M}x{N}x{K} bn={bn} ctas={ctas}")
+def conv_c(NI, H, W, Cin, Cout, bn, ctas):
+    b200.tf_gemm_set_ctas(ctas); b200.tf_gemm_set_tuning(bn, 1)
+    x = torch.randn(NI, H, W, Cin, device=dev).half(); w = (torch.randn(Cout, 3, 3, Cin, device=dev) / 50).half()
+    b = torch.randn(Cout, device=dev); out = torch.empty(NI, H, W, Cout, dtype=torch.half, device=dev)
+    for i in range(3):
+        b200.tf_gemm_set_timeline(tl.data_ptr() if i == 2 else None)
+        b200.check(b200.tf_conv2d_nhwc_f16(x.data_ptr(), NI, H, W, Cin, Cin, w.data_ptr(), Cout, 3, 1, out.data_ptr(), Cout, b.data_ptr(), None, 0, 0, ws.data_ptr(), ws.numel(), S()), "conv")
+    b200.tf_gemm_set_timeline(None)
+    cadence(f"conv {NI}x{H}x{W} {Cin}->{Cout} bn={bn} ctas={ctas}")
+b200.tf_gemm_set_ctas(0); b200.tf_gemm_set_tuning(0, 0)
+def epi(name, grid):
+    torch.cuda.synchronize()
+    t = tl[:148 * 16].view(148, 16)[:grid:2].cpu().double()
+    e = t[:, 7]
+    names = {0: "setup_done", 1: "mma_start", 2: "first_full", 3: "mma_issued", 4: "acc_ready", 8: "c0_tmem", 9: "c0_staged", 10: "c0_tma", 11: "cN_tmem", 12: "cN_tma", 5: "stored", 6: "exit"}
+    print(name, {v: int((t[:, k] - e).median().item()) for k, v in names.items()})
+    tl.zero_()
+def gemm_e(M, N, K, residual):
+    A = torch.randn(M, K, device=dev).half(); W = (torch.randn(N, K, device=dev) / 30).half(); b = torch.randn(N, device=dev)
+    R = torch.randn(M, N, device=dev).half()
+    out = torch.empty(M, N, dtype=torch.half, device=dev)
+    for i in range(3):
+        b200.tf_gemm_set_timeline(tl.data_ptr() if i == 2 else None)
+        b200.check(b200.tf_gemm_f16(A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), N, M, N, K, b.data_ptr(), R.data_ptr() if residual else None, N, 0, ws.data_ptr(), ws.numel(), S()), "gemm")
+    b200.tf_gemm_set_timeline(None)
+    epi(f"gemm {M}x{N}x{K} res={residual}", 128)
+gemm_e(8192, 320, 320, True)
+gemm_e(8192, 320, 320, False)
+gemm_e(8192, 320, 1280, True)
