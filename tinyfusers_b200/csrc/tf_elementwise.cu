@@ -54,18 +54,25 @@ __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restric
 
 // 3x3 pad-1 conv with a tiny input-channel count, fp32 NCHW in -> fp16 NHWC out.
 // reference: UNetModel.input_blocks[0] = Conv2d(4, 320, 3x3, pad 1) (vision/unet.py:13).
-// w: fp32 (Cout, Cin, 3, 3) exactly as the reference stores it. Block = 32 pixels x 4 warps: lane = pixel (its
-// 36 inputs stay in registers), warp = a quarter of the output-channel groups, so weight reads are
+// w: fp32 (Cout, Cin, 3, 3) exactly as the reference stores it. Block = 32 pixels x 8 warps: lane = pixel (its
+// 36 inputs stay in registers), warp = an eighth of the output-channel groups, so weight reads are
 // warp-uniform shared-memory broadcasts.
 template <int CIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                         __half* __restrict__ out, int NI, int H, int W_, int Cout, int out_stride, int x_images) {
-  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
+  tf::pdl_trigger();
   extern __shared__ float ws[];  // [Cout][CIN*9] then [Cout] bias
   float* bs = ws + Cout * CIN * 9;
-  for (int i = threadIdx.x; i < Cout * CIN * 9; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+  // weights do not depend on the producer kernels: stage them (128-bit loads) before the dependency wait
+  {
+    const int n4 = (Cout * CIN * 9) >> 2;   // Cout % 8 == 0 -> a whole number of float4
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    float4* ws4 = reinterpret_cast<float4*>(ws);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) ws4[i] = __ldg(w4 + i);
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+  }
+  tf::pdl_wait();
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long npix = (long)NI * H * W_;
@@ -86,7 +93,7 @@ conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w
             (yy >= 0 && yy < H && xx >= 0 && xx < W_) ? x[(((size_t)n * CIN + c) * H + yy) * W_ + xx] : 0.f;
       }
   const int groups = Cout / 8;
-  for (int g = warp; g < groups; g += 4) {
+  for (int g = warp; g < groups; g += 8) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -251,7 +258,8 @@ extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const f
     TF_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  TF_LAUNCH((conv3x3_smallcin_kernel<4>), (unsigned)((npix + 31) / 32), 128, smem, (cudaStream_t)stream, 
+  TF_CHECK_ARG(((uintptr_t)w & 15) == 0, "tf_conv3x3_smallcin_f32nchw: weights must be 16-byte aligned");
+  TF_LAUNCH((conv3x3_smallcin_kernel<4>), (unsigned)((npix + 31) / 32), 256, smem, (cudaStream_t)stream, 
       x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride, x_images);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);

@@ -613,12 +613,21 @@ __global__ void tf_splitk_reduce_stats_kernel(const float* __restrict__ partial,
   for (int j = 0; j < 4; ++j) rsm[ty * bw + 4 * tx + j] = make_float2(f[j], f[j] * f[j]);
   __syncthreads();
   const int tid = ty * blockDim.x + tx, nthreads = blockDim.x * blockDim.y;
-  // column totals over the 32 rows (fixed order), then units
-  float2* tot = rsm + 32 * bw;
+  // column totals over the 32 rows in two fixed-order levels (8 x 4 rows, every thread busy), then units
+  float2* part = rsm + 32 * bw;
+  float2* tot = part + 8 * bw;
+  {
+    const int c = tid % bw, pt = tid / bw;   // nthreads == 8 * bw
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { a += rsm[(pt * 4 + r) * bw + c].x; b += rsm[(pt * 4 + r) * bw + c].y; }
+    part[pt * bw + c] = make_float2(a, b);
+  }
+  __syncthreads();
   for (int c = tid; c < bw; c += nthreads) {
     float a = 0.f, b = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) { a += rsm[r * bw + c].x; b += rsm[r * bw + c].y; }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { a += part[r * bw + c].x; b += part[r * bw + c].y; }
     tot[c] = make_float2(a, b);
   }
   __syncthreads();
@@ -744,7 +753,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
       return TF_ERR_UNSUPPORTED;
     }
     const dim3 grid(p.N / bw, ceil_div_i(p.M, 32)), block(bw / 4, 32);
-    TF_LAUNCH(tf_splitk_reduce_stats_kernel, grid, block, (size_t)33 * bw * sizeof(float2), stream, p.partial, p.splits, p.M,
+    TF_LAUNCH(tf_splitk_reduce_stats_kernel, grid, block, (size_t)41 * bw * sizeof(float2), stream, p.partial, p.splits, p.M,
               p.N, p.bias, p.residual, p.ldr, reinterpret_cast<__half*>(p.out), p.ldc, p.gn_stats, p.gn_unit, p.gn_hw, bw);
     TF_LAUNCH_CHECK();
     tf_launch_count_add(1);

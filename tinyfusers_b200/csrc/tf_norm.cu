@@ -153,14 +153,49 @@ __global__ void gn_fused_apply_kernel(const __half* __restrict__ x1, int stride1
                                       const float2* __restrict__ st2, int unit2, int HW, int cpg, int G, int pix_per_block,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                       float inv_count, int silu, __half* __restrict__ out, int out_stride) {
-  tf::pdl_prologue();
+  tf::pdl_trigger();
   extern __shared__ float2 fsm[];   // [units] unit totals, [G] {mean, rstd}, [SG][units] partials of the fold
   const int n = blockIdx.y;
   const int slots = HW >> 5;
   const int units1 = C1 / unit1, units2 = x2 ? C2 / unit2 : 0;
   const int units = units1 + units2;
-  // fold: thread (sg, u) sums slots sg, sg + SG, ... of unit u (independent, coalesced loads: no shuffle in the
-  // loop, so they pipeline), then thread u adds the SG partials in a fixed order
+  // ---- this thread's channels / pixels; everything that can be fetched early is: the affine parameters do not
+  // depend on the producer kernels (loaded before the dependency wait), the pixels only on the producer's output
+  // (loaded before the statistics fold), so the three global round trips of the kernel overlap ----
+  const int nvec = (C1 + C2) >> 3;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int npl = blockDim.x / nvec;
+  const bool worker = pl < npl;
+  const int c0 = v * 8;
+  float gg[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { gg[j] = 1.f; bb[j] = 0.f; }
+  if (worker && gamma) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+  }
+  if (worker && beta) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+  }
+  tf::pdl_wait();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const __half* xin;
+  int xs;
+  if (c0 < C1) { xin = x1 + (size_t)n * HW * stride1 + c0; xs = stride1; }
+  else { xin = x2 + (size_t)n * HW * stride2 + (c0 - C1); xs = stride2; }
+  constexpr int kPre = 3;
+  uint4 pre[kPre];
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) {
+    const int p = p0 + pl + i * npl;
+    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (worker && p < p1) pre[i] = *reinterpret_cast<const uint4*>(xin + (size_t)p * xs);
+  }
+  // ---- fold: thread (sg, u) sums slots sg, sg + SG, ... of unit u (independent, coalesced loads: no shuffle in the
+  // loop, so they pipeline), then thread u adds the SG partials in a fixed order ----
   float2* part = fsm + units + G;
   const int SG = min((int)blockDim.x / units, slots);
   {
@@ -203,29 +238,9 @@ __global__ void gn_fused_apply_kernel(const __half* __restrict__ x1, int stride1
     gst[g] = make_float2(mean, rsqrtf(var + eps));
   }
   __syncthreads();
-  const int nvec = (C1 + C2) >> 3;
-  const int v = threadIdx.x % nvec;
-  const int pl = threadIdx.x / nvec;
-  const int npl = blockDim.x / nvec;
-  if (pl >= npl) return;
-  const int c0 = v * 8;
+  if (!worker) return;
   float a8[8], b8[8];
   {
-    float gg[8], bb[8];
-    if (gamma) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-      gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gg[j] = 1.f;
-    }
-    if (beta) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-      bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bb[j] = 0.f;
-    }
     int g = c0 / cpg, left = (g + 1) * cpg - c0;   // channels left in group g (one division per thread)
     float2 mr = gst[g];
 #pragma unroll
@@ -236,16 +251,17 @@ __global__ void gn_fused_apply_kernel(const __half* __restrict__ x1, int stride1
       b8[j] = bb[j] - mr.x * mr.y * gg[j];
     }
   }
-  const int p0 = blockIdx.x * pix_per_block;
-  const int p1 = min(HW, p0 + pix_per_block);
-  const __half* xin;
-  int xs;
-  if (c0 < C1) { xin = x1 + (size_t)n * HW * stride1 + c0; xs = stride1; }
-  else { xin = x2 + (size_t)n * HW * stride2 + (c0 - C1); xs = stride2; }
   __half* o = out + (size_t)n * HW * out_stride + c0;
-  for (int p = p0 + pl; p < p1; p += npl) {
+  int i = 0;
+  for (int p = p0 + pl; p < p1; p += npl, ++i) {
     tf::Pack16 pk;
-    pk.v = *reinterpret_cast<const uint4*>(xin + (size_t)p * xs);
+    if (i < kPre) {
+#pragma unroll
+      for (int k = 0; k < kPre; ++k)
+        if (k == i) pk.v = pre[k];
+    } else {
+      pk.v = *reinterpret_cast<const uint4*>(xin + (size_t)p * xs);
+    }
     tf::Pack16 r;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -339,12 +355,27 @@ template <int IL, int THREADS, int MAXV, int ROWS>
 __global__ void __launch_bounds__(THREADS * ROWS)
 ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int nrows, int C, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps) {
-  tf::pdl_prologue();  // PDL: let the next kernel start launching, then wait for our producers
+  tf::pdl_trigger();
   __shared__ float red[2][ROWS][THREADS / 32][IL];   // ROWS rows per block, THREADS threads each (whole warps)
   const int rib = threadIdx.x / THREADS, tid = threadIdx.x % THREADS;
   const int row = blockIdx.x * ROWS + rib;
   const bool live = row < nrows;
   const int nvec = (C * IL) >> 3;
+  // the affine parameters do not depend on the producer kernels: fetch them before the dependency wait (IL == 1)
+  float4 gpre[MAXV][2], bpre[MAXV][2];
+  if (IL == 1) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = tid + i * THREADS;
+      if (v < nvec) {
+        gpre[i][0] = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        gpre[i][1] = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        bpre[i][0] = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        bpre[i][1] = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      }
+    }
+  }
+  tf::pdl_wait();
   const __half* xr = x + (size_t)row * C * IL;
   const int warp = tid >> 5, lane = tid & 31;
   tf::Pack16 pk[MAXV];
@@ -414,8 +445,7 @@ ln_block_kernel(const __half* __restrict__ x, __half* __restrict__ out, int nrow
       tf::Pack16 r;
       const int c0 = (v * 8) / IL;  // first channel covered by this vector (8 / IL channels)
       if (IL == 1) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        const float4 g0 = gpre[i][0], g1 = gpre[i][1], b0 = bpre[i][0], b1 = bpre[i][1];
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
