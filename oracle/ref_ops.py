@@ -123,7 +123,7 @@ def softmax_rows(x):
 def scaled_dot_product_attention(q, k, v, attn_mask=None):
     # attention/sdpa.py:53-77 — scale * (q @ k^T) [+ mask] -> row softmax -> @ v
     HS = q.shape[-1]
-    scale = torch.tensor(1.0 / math.sqrt(HS), dtype=torch.float32).to(q.dtype)  # cp.single, sdpa.py:62
+    scale = torch.tensor(1.0 / math.sqrt(HS), dtype=torch.float32).to(device=q.device, dtype=q.dtype)  # cp.single, sdpa.py:62
     preatt = scale * (q @ k.transpose(-1, -2))
     if attn_mask is not None:
         if attn_mask.dtype == torch.bool:
@@ -295,7 +295,7 @@ def _run_layer(sd, p, layer, x, emb, context, quirks, ln_strided=False):
 def unet_forward(sd, x, timesteps, context, prefix="model.diffusion_model", quirks=True, ln_strided=False):
     # vision/unet.py:51-76
     P = prefix
-    t_emb = timestep_embedding(timesteps, 320).to(x.dtype)
+    t_emb = timestep_embedding(timesteps, 320).to(device=x.device, dtype=x.dtype)
     emb = linear(t_emb, _w(sd, P + ".time_embed.0.weight"), _b(sd, P + ".time_embed.0.bias"))
     emb = linear(silu(emb), _w(sd, P + ".time_embed.2.weight"), _b(sd, P + ".time_embed.2.bias"))
     saved = []
