@@ -160,7 +160,7 @@ class Context:
         e0.record()
         r = fn()
         e1.record()
-        self.prof.append((key, e0, e1))
+        self.prof.append((key, e0, e1, fn))
         return r
 
     def skip(self, kind):

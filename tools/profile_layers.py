@@ -18,7 +18,7 @@ eng.ctx.prof = []
 s.enqueue_step()
 torch.cuda.synchronize()
 agg = collections.OrderedDict()
-for key, e0, e1 in eng.ctx.prof:
+for key, e0, e1, _fn in eng.ctx.prof:
     a = agg.setdefault(key, [0, 0.0]); a[0] += 1; a[1] += e0.elapsed_time(e1) * 1000
 eng.ctx.prof = None
 tot = sum(v[1] for v in agg.values())
