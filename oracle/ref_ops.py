@@ -355,6 +355,135 @@ def sampler_schedule(steps, alphas_cumprod=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# VAE decoder — reference: tinyfusers/vae/decoder.py:8-34, vae/mid.py:5-12,
+# vision/resnet.py:33-45, attention/attention.py:10-24, vae/vae.py:5-18, variants/sd.py:48-54
+# ------------------------------------------------------------------------------------------------
+
+
+def _pw(sd, p):
+    return sd[p + ".weight"]
+
+
+def _pb(sd, p):
+    return sd.get(p + ".bias")
+
+
+def _gn(sd, p, x, eps=1e-5):
+    return group_norm_affine(x, 32, _pw(sd, p), _pb(sd, p), eps)
+
+
+def _conv(sd, p, x, padding=(0, 0), stride=(1, 1)):
+    return conv2d(x, _pw(sd, p), _pb(sd, p), stride=stride, padding=padding)
+
+
+def resnet_block(sd, p, x):
+    # vision/resnet.py:41-45   conv1(swish(norm1 x)) -> conv2(swish(norm2 .)) ; + nin_shortcut(x) (1x1) | x
+    h = _conv(sd, p + ".conv1", silu(_gn(sd, p + ".norm1", x)), padding=(1, 1))
+    h = _conv(sd, p + ".conv2", silu(_gn(sd, p + ".norm2", h)), padding=(1, 1))
+    sc = _conv(sd, p + ".nin_shortcut", x) if (p + ".nin_shortcut.weight") in sd else x
+    return sc + h
+
+
+def attn_block(sd, p, x, quirks=True):
+    """attention/attention.py:19-24. The reference hands the 4-D (B,C,H,W) q/k/v straight to SDPA
+    (attention.py:21-22), which reads them as (B, NH=C, T=H, HS=W): per channel, an H x H attention over the
+    rows of that channel's H x W plane, scale 1/sqrt(W) (SURVEY.md §8 parity note 3). quirks=False is the
+    canonical LDM AttnBlock: one head over the H*W pixels, head dim C."""
+    h_ = _gn(sd, p + ".norm", x)
+    q, k, v = (_conv(sd, f"{p}.{n}", h_) for n in ("q", "k", "v"))
+    if quirks:
+        h = scaled_dot_product_attention(q, k, v)
+    else:
+        B, C, H, W = q.shape
+        tok = lambda t: t.reshape(B, C, H * W).transpose(1, 2).reshape(B, 1, H * W, C)
+        h = scaled_dot_product_attention(tok(q), tok(k), tok(v)).reshape(B, H * W, C).transpose(1, 2).reshape(B, C, H, W)
+    return x + _conv(sd, p + ".proj_out", h)
+
+
+def vae_mid(sd, p, x, quirks=True):
+    # vae/mid.py:11-12
+    x = resnet_block(sd, p + ".block_1", x)
+    x = attn_block(sd, p + ".attn_1", x, quirks)
+    return resnet_block(sd, p + ".block_2", x)
+
+
+VAE_DECODER_SZ = [(128, 256), (256, 512), (512, 512), (512, 512)]   # vae/decoder.py:10
+
+
+def vae_decoder(sd, p, x, quirks=True):
+    # vae/decoder.py:22-34
+    x = _conv(sd, p + ".conv_in", x, padding=(1, 1))
+    x = vae_mid(sd, p + ".mid", x, quirks)
+    for i in (3, 2, 1, 0):
+        for j in range(3):
+            x = resnet_block(sd, f"{p}.up.{i}.block.{j}", x)
+        if i != 0:
+            bs, c, py, px = x.shape   # nearest x2 (decoder.py:30-31)
+            x = x.reshape(bs, c, py, 1, px, 1).expand(bs, c, py, 2, px, 2).reshape(bs, c, py * 2, px * 2)
+            x = _conv(sd, f"{p}.up.{i}.upsample.conv", x, padding=(1, 1))
+    return _conv(sd, p + ".conv_out", silu(_gn(sd, p + ".norm_out", x)), padding=(1, 1))
+
+
+def vae_decode_float(sd, x, prefix="first_stage_model", quirks=True):
+    """variants/sd.py:48-51: post_quant_conv(x / 0.18215) -> decoder -> (x + 1) / 2, before clipping / uint8."""
+    x = _conv(sd, prefix + ".post_quant_conv", (1 / 0.18215) * x)
+    x = vae_decoder(sd, prefix + ".decoder", x, quirks)
+    return (x + 1.0) / 2.0
+
+
+def vae_decode(sd, x, prefix="first_stage_model", quirks=True):
+    """variants/sd.py:48-54 with the hard-coded 512 (sd.py:52) generalised to the decoded size:
+    clip(transpose(x.reshape(3,H,W), (1,2,0)), 0, 1) * 255 -> uint8 (truncation, like cp.astype)."""
+    y = vae_decode_float(sd, x, prefix, quirks)
+    _, _, H, W = y.shape
+    img = torch.clamp(y.reshape(3, H, W).permute(1, 2, 0), 0, 1) * 255
+    return img.to(torch.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP text encoder (SURVEY.md §8f rank 2) — reference: tinyfusers/vae/encoder.py:36-81,
+# attention/attention.py:78-99, ff/nn.py:25-34, ff/embedding.py:6-23
+# ------------------------------------------------------------------------------------------------
+
+
+def clip_attention(sd, p, x, mask):
+    # attention/attention.py:88-99: 12 heads x 64, q/k/v/out Linear WITH bias, heads transposed back (canonical)
+    B, T, E = x.shape
+    NH, HD = 12, E // 12
+    q, k, v = (linear(x, _pw(sd, f"{p}.{n}"), _pb(sd, f"{p}.{n}")) for n in ("q_proj", "k_proj", "v_proj"))
+    q, k, v = (t.reshape(B, T, NH, HD).transpose(1, 2) for t in (q, k, v))
+    o = scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    o = o.transpose(1, 2).reshape(B, T, E)
+    return linear(o, _pw(sd, p + ".out_proj"), _pb(sd, p + ".out_proj"))
+
+
+def clip_encoder_layer(sd, p, x, mask):
+    # vae/encoder.py:53-64
+    h = layer_norm(x, _pw(sd, p + ".layer_norm1"), _pb(sd, p + ".layer_norm1"))
+    x = x + clip_attention(sd, p + ".self_attn", h, mask)
+    h = layer_norm(x, _pw(sd, p + ".layer_norm2"), _pb(sd, p + ".layer_norm2"))
+    h = linear(h, _pw(sd, p + ".mlp.fc1"), _pb(sd, p + ".mlp.fc1"))     # ff/nn.py:30-34
+    h = linear(quick_gelu(h), _pw(sd, p + ".mlp.fc2"), _pb(sd, p + ".mlp.fc2"))
+    return x + h
+
+
+def clip_text_transformer(sd, input_ids, prefix="cond_stage_model.transformer.text_model", layers=12):
+    """vae/encoder.py:72-81. token + position embedding -> 12 pre-LN layers under the additive causal mask
+    triu(full((1,1,77,77), -inf), k=1) -> final LayerNorm. The reference's Embedding (ff/embedding.py:15-23) builds
+    a one-hot matrix of the wrong shape (embed_sz x N instead of vocab x N) and cannot run; what it means —
+    row lookup, weight[idx] — is restated here."""
+    P = prefix
+    ids = torch.as_tensor(input_ids, dtype=torch.long).reshape(1, -1)
+    T = ids.shape[1]
+    x = _pw(sd, P + ".embeddings.token_embedding")[ids[0]] + _pw(sd, P + ".embeddings.position_embedding")[torch.arange(T)]
+    x = x.reshape(1, T, -1)
+    mask = torch.triu(torch.full((1, 1, T, T), float("-inf")), diagonal=1).to(x.dtype)
+    for i in range(layers):
+        x = clip_encoder_layer(sd, f"{P}.encoder.layers.{i}", x, mask)
+    return layer_norm(x, _pw(sd, P + ".final_layer_norm"), _pb(sd, P + ".final_layer_norm"))
+
+
+# ------------------------------------------------------------------------------------------------
 # synthetic weights (SURVEY.md §8d): deterministic per key, identical for oracle and kernels.
 # ------------------------------------------------------------------------------------------------
 
@@ -444,6 +573,59 @@ def make_unet_state_dict(seed=1234, prefix="model.diffusion_model"):
             _add_layer(sd, f"{P}.output_blocks.{i}.{j}", layer, seed)
     _add_norm(sd, P + ".out.0", 320, seed)
     _add_conv(sd, P + ".out.2", 320, 4, 3, seed)
+    return sd
+
+
+def add_resnet_block(sd, p, cin, cout, seed=1234):
+    _add_norm(sd, p + ".norm1", cin, seed)
+    _add_conv(sd, p + ".conv1", cin, cout, 3, seed)
+    _add_norm(sd, p + ".norm2", cout, seed)
+    _add_conv(sd, p + ".conv2", cout, cout, 3, seed)
+    if cin != cout:
+        _add_conv(sd, p + ".nin_shortcut", cin, cout, 1, seed)
+
+
+def add_attn_block(sd, p, c, seed=1234):
+    _add_norm(sd, p + ".norm", c, seed)
+    for n in ("q", "k", "v", "proj_out"):
+        _add_conv(sd, f"{p}.{n}", c, c, 1, seed)
+
+
+def make_vae_decoder_state_dict(seed=4321, prefix="first_stage_model"):
+    """Seeded synthetic post_quant_conv + Decoder weights under the reference's checkpoint key names (~198 MB fp32)."""
+    sd = {}
+    _add_conv(sd, prefix + ".post_quant_conv", 4, 4, 1, seed)
+    D = prefix + ".decoder"
+    _add_conv(sd, D + ".conv_in", 4, 512, 3, seed)
+    add_resnet_block(sd, D + ".mid.block_1", 512, 512, seed)
+    add_attn_block(sd, D + ".mid.attn_1", 512, seed)
+    add_resnet_block(sd, D + ".mid.block_2", 512, 512, seed)
+    for i, (lo, hi) in enumerate(VAE_DECODER_SZ):
+        add_resnet_block(sd, f"{D}.up.{i}.block.0", hi, lo, seed)
+        add_resnet_block(sd, f"{D}.up.{i}.block.1", lo, lo, seed)
+        add_resnet_block(sd, f"{D}.up.{i}.block.2", lo, lo, seed)
+        if i != 0:
+            _add_conv(sd, f"{D}.up.{i}.upsample.conv", lo, lo, 3, seed)
+    _add_norm(sd, D + ".norm_out", 128, seed)
+    _add_conv(sd, D + ".conv_out", 128, 3, 3, seed)
+    return sd
+
+
+def make_clip_state_dict(seed=777, prefix="cond_stage_model.transformer.text_model", layers=12):
+    """Seeded synthetic CLIP text-encoder weights under the reference's checkpoint key names (~490 MB fp32)."""
+    sd = {}
+    P = prefix
+    sd[P + ".embeddings.token_embedding.weight"] = _randn(P + ".tok", seed, (49408, 768), 0.02)
+    sd[P + ".embeddings.position_embedding.weight"] = _randn(P + ".pos", seed, (77, 768), 0.01)
+    for i in range(layers):
+        L = f"{P}.encoder.layers.{i}"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            _add_linear(sd, f"{L}.self_attn.{n}", 768, 768, seed)
+        _add_norm(sd, L + ".layer_norm1", 768, seed)
+        _add_norm(sd, L + ".layer_norm2", 768, seed)
+        _add_linear(sd, L + ".mlp.fc1", 768, 3072, seed)
+        _add_linear(sd, L + ".mlp.fc2", 3072, 768, seed)
+    _add_norm(sd, P + ".final_layer_norm", 768, seed)
     return sd
 
 
