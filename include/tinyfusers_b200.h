@@ -135,6 +135,12 @@ int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void*
                      long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
                      int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream);
 int tf_attention_set_tuning(int force_bn);
+/* Same, under a causal mask: query t attends to keys <= t only (Tq == Tk). Replaces CLIPAttention's
+ * scaled_dot_product_attention(q, k, v, attn_mask = triu(full(-inf), k=1))
+ *           tinyfusers/attention/attention.py:88-99, tinyfusers/vae/encoder.py:79, attention/sdpa.py:67-68. */
+int tf_attention_causal_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
+                            long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
+                            int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream);
 
 /* ---- small ops of the step --------------------------------------------------------------------------- */
 /* [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / (dim/2)); t = timesteps_dev[*index_dev]
@@ -181,6 +187,29 @@ int tf_nhwc_f32_to_nchw_f32(const float* x, int x_pixel_stride, float* out, int 
  * Replaces: StableDiffusion.get_x_prev_and_pred_x0  tinyfusers/variants/sd.py:14-25. */
 int tf_ddim_step_f32(const float* x, const float* e_t, const float* a_t_dev, const float* a_prev_dev, float* x_prev,
                      float* pred_x0, long long n, void* stream);
+
+
+/* ---- rows next to the hot path: VAE decoder, CLIP text encoder --------------------- */
+/* Attention of the reference's AttnBlock as the reference executes it: 4-D (B,C,H,W) q/k/v handed to
+ * scaled_dot_product_attention are read as (B, NH = C, T = H, HS = W), i.e. per channel plane
+ * softmax(scale * Q K^T) V with Q, K, V the H x W planes.  q, k, v, out: (planes, H, W) fp16 contiguous (NCHW).
+ * Replaces: AttnBlock.__call__ -> scaled_dot_product_attention   tinyfusers/attention/attention.py:19-24,
+ *           tinyfusers/attention/sdpa.py:53-77. */
+int tf_plane_attention_f16(const void* q, const void* k, const void* v, void* out, int planes, int H, int W, float scale,
+                           void* stream);
+/* out[n,co,p] = bias[co] + sum_ci w[co,ci] * (scale * x[n,ci,p]); fp32 NCHW, Cin, Cout <= 8.
+ * Replaces: post_quant_conv(1/0.18215 * x)   tinyfusers/variants/sd.py:49, tinyfusers/vae/vae.py:10. */
+int tf_conv1x1_small_f32nchw(const float* x, const float* w, const float* bias, float* out, int NI, int Cin, int Cout,
+                             int HW, float scale, void* stream);
+/* clip((x + 1) / 2, 0, 1) * 255 -> uint8 (truncating cast); fp32 NHWC (pixel stride >= C) -> uint8 HWC.
+ * Replaces: StableDiffusion.decode post-processing   tinyfusers/variants/sd.py:51-53. */
+int tf_image_to_u8(const float* x_nhwc, int x_pixel_stride, void* out_u8, long long pixels, int C, void* stream);
+/* out[r, :] = table[ids[r], :] + pos_table[r % T, :] (pos_table may be NULL); fp32 tables -> fp16 rows.
+ * Replaces: Embedding.__call__ (one-hot GEMM)   tinyfusers/ff/embedding.py:15-23, CLIPTextEmbeddings
+ *           tinyfusers/vae/encoder.py:66-70. */
+int tf_embedding_f16(const int* ids, const float* table, const float* pos_table, void* out, int rows, int T, int E,
+                     int vocab, void* stream);
+int tf_cast_f16_to_f32(const void* x, float* out, long long n, void* stream);
 
 #ifdef __cplusplus
 }

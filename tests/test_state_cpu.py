@@ -94,7 +94,14 @@ def test_full_model_key_set_matches_oracle(oracle):
         for j, l in enumerate(b): layer(f"{P}.output_blocks.{i}.{j}", l)
     assert len(want) == 686
     nobias = {k for k in walked if k.endswith((".to_q.bias", ".to_k.bias", ".to_v.bias"))}
-    assert walked - nobias == want
+    assert {k for k in walked if k.startswith(P)} - nobias == want
+    # the rows next to the hot path: every key of the synthetic VAE-decoder / CLIP dicts has a slot in the tree
+    assert set(oracle.make_vae_decoder_state_dict().keys()) <= walked
+    assert set(oracle.make_clip_state_dict().keys()) <= walked
+    # ... and the tree has no VAE-decoder / CLIP slot the generators do not fill (encoder / quant_conv are not built)
+    extra = {k for k in walked if k.startswith(("first_stage_model.decoder", "first_stage_model.post_quant_conv",
+                                                "cond_stage_model"))}
+    assert extra == set(oracle.make_vae_decoder_state_dict().keys()) | set(oracle.make_clip_state_dict().keys())
 
 
 def test_sampler_schedule_matches_reference_loop(oracle):

@@ -1,0 +1,225 @@
+"""Rows next to the hot path: VAE decoder and CLIP text encoder on the B200 kernels, against the oracle
+(oracle/ref_ops.py) and the golden vectors produced by the reference's own Python
+(tests/golden/reference_outputs_vae_clip.npz). Tolerance: max|a-b| / max|b| <= 1e-2 per op / block (fp16 operands,
+fp32 accumulate - BASELINE.json north_star); deep compositions state their own bound."""
+import contextlib
+import io
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs_vae_clip.npz"))
+
+
+def rnd(seed, *shape, scale=1.0, shift=0.0):
+    g = np.random.Generator(np.random.Philox(seed))
+    return torch.from_numpy(g.standard_normal(shape, dtype=np.float32) * np.float32(scale) + np.float32(shift))
+
+
+def gold(name):
+    return torch.from_numpy(GOLD[name])
+
+
+def _load(obj, sd, prefix):
+    from tinyfusers_b200.storage.state import update_state
+    with contextlib.redirect_stdout(io.StringIO()):
+        update_state(obj, sd, prefix)
+    return obj
+
+
+@pytest.fixture(scope="module")
+def vae(oracle):
+    from tinyfusers_b200.vae.vae import AutoencoderKL
+    sd = oracle.make_vae_decoder_state_dict()
+    return _load(AutoencoderKL(), sd, "first_stage_model"), sd
+
+
+@pytest.fixture(scope="module")
+def clip(oracle):
+    from tinyfusers_b200.vae.encoder import CLIPTextTransformer
+    sd = oracle.make_clip_state_dict()
+    return _load(CLIPTextTransformer(), sd, "cond_stage_model.transformer.text_model"), sd
+
+
+# ---- kernels ----------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("planes,H,W", [(16, 6, 10), (64, 64, 64), (8, 96, 96), (4, 33, 18)])
+def test_plane_attention_kernel(planes, H, W):
+    from tinyfusers_b200.native.b200.ops import b200
+    b200.init(0)
+    g = torch.Generator().manual_seed(planes + H)
+    q, k, v = (torch.randn(planes, H, W, generator=g).cuda().half() for _ in range(3))
+    out = torch.empty_like(q)
+    st = b200.tf_plane_attention_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), planes, H, W,
+                                     1.0 / math.sqrt(W), torch.cuda.current_stream().cuda_stream)
+    b200.check(st, "tf_plane_attention_f16")
+    ref = torch.softmax(q.float() @ k.float().transpose(1, 2) / math.sqrt(W), dim=-1) @ v.float()
+    assert rel_err(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("T,NH,d", [(77, 12, 64), (200, 4, 64), (384, 2, 48)])
+def test_causal_attention_kernel(T, NH, d):
+    from tinyfusers_b200.native.b200.ops import b200
+    b200.init(0)
+    g = torch.Generator().manual_seed(T)
+    Tp = (T + 7) // 8 * 8
+    q = torch.randn(T, NH * d, generator=g).cuda().half()
+    k = torch.zeros(Tp, NH * d, dtype=torch.half, device="cuda")
+    k[:T] = torch.randn(T, NH * d, generator=g).cuda().half()
+    v = torch.randn(T, NH * d, generator=g).cuda().half()
+    vt = torch.zeros(NH * d, Tp, dtype=torch.half, device="cuda")
+    vt[:, :T] = v.t()
+    out = torch.zeros(T, NH * d, dtype=torch.half, device="cuda")
+    st = b200.tf_attention_causal_f16(q.data_ptr(), NH * d, k.data_ptr(), NH * d, vt.data_ptr(), Tp, out.data_ptr(),
+                                      T * NH * d, d, NH * d, 1, NH, T, T, Tp, d, d, 1.0 / math.sqrt(d),
+                                      torch.cuda.current_stream().cuda_stream)
+    b200.check(st, "tf_attention_causal_f16")
+    heads = lambda t: t.float().reshape(T, NH, d).transpose(0, 1)[None]
+    ref = torch.nn.functional.scaled_dot_product_attention(heads(q), heads(k[:T]), heads(v), is_causal=True)
+    ref = ref[0].transpose(0, 1).reshape(T, NH * d)
+    assert rel_err(out, ref) < 3e-3
+
+
+def test_embedding_kernel():
+    from tinyfusers_b200.ff.embedding import Embedding
+    e = Embedding(1000, 768)
+    e.weight = rnd(5, 1000, 768).cuda()
+    ids = np.array([[3, 999, 0, 17, 17, 512]])
+    out = e(ids)
+    assert rel_err(out, e.weight[torch.from_numpy(ids[0]).cuda()]) < 1e-3
+
+
+# ---- VAE blocks -------------------------------------------------------------------------------------------------
+
+def test_resnet_block(oracle):
+    from tinyfusers_b200.vision.resnet import ResnetBlock
+    sd = {}
+    oracle.add_resnet_block(sd, "rn", 64, 128, seed=701)
+    oracle.add_resnet_block(sd, "rn2", 64, 64, seed=702)
+    x = rnd(703, 1, 64, 8, 8, scale=1.3, shift=0.2)
+    y = _load(ResnetBlock(64, 128), sd, "rn")(x.cuda())
+    assert rel_err(y, gold("resnet_block_64_128")) < 1e-2
+    y2 = _load(ResnetBlock(64, 64), sd, "rn2")(x.cuda())
+    assert rel_err(y2, gold("resnet_block_64_64")) < 1e-2
+    # VAE geometry: 256 -> 128 channels at 64x64 (producer GroupNorm statistics with a 4-channel unit)
+    sd = {}
+    oracle.add_resnet_block(sd, "r", 256, 128, seed=9)
+    x = rnd(10, 2, 256, 64, 64)
+    with torch.no_grad():
+        ref = oracle.resnet_block(sd, "r", x)
+    assert rel_err(_load(ResnetBlock(256, 128), sd, "r")(x.cuda()), ref) < 1e-2
+
+
+def test_attn_block_reference_reading(oracle):
+    from tinyfusers_b200.attention.attention import AttnBlock
+    sd = {}
+    oracle.add_attn_block(sd, "ab", 64, seed=711)
+    ab = _load(AttnBlock(64), sd, "ab")
+    assert rel_err(ab(rnd(712, 1, 64, 6, 10).cuda()), gold("attn_block_6x10")) < 1e-2
+    assert rel_err(ab(rnd(713, 1, 64, 8, 8).cuda()), gold("attn_block_8x8")) < 1e-2
+    # the VAE's own geometry (512 channels, 64x64), batch 2
+    sd = {}
+    oracle.add_attn_block(sd, "a", 512, seed=3)
+    x = rnd(4, 2, 512, 64, 64)
+    with torch.no_grad():
+        ref = oracle.attn_block(sd, "a", x)
+    assert rel_err(_load(AttnBlock(512), sd, "a")(x.cuda()), ref) < 1e-2
+
+
+def test_attn_block_canonical_raises():
+    import tinyfusers_b200
+    from tinyfusers_b200.attention.attention import AttnBlock
+    tinyfusers_b200.set_quirks(False)
+    try:
+        with pytest.raises(RuntimeError, match="not built"):
+            AttnBlock(64)(torch.randn(1, 64, 8, 8).cuda())
+    finally:
+        tinyfusers_b200.set_quirks(True)
+
+
+def test_mid(oracle):
+    from tinyfusers_b200.vae.mid import Mid
+    sd = {}
+    oracle.add_resnet_block(sd, "mid.block_1", 64, 64, seed=721)
+    oracle.add_attn_block(sd, "mid.attn_1", 64, seed=721)
+    oracle.add_resnet_block(sd, "mid.block_2", 64, 64, seed=721)
+    assert rel_err(_load(Mid(64), sd, "mid")(rnd(722, 1, 64, 8, 8).cuda()), gold("mid_64")) < 1e-2
+
+
+# ---- decoder / decode -------------------------------------------------------------------------------------------
+
+def test_decoder_against_reference_golden(vae):
+    m, _ = vae
+    y = m.decoder(rnd(731, 1, 4, 4, 4).cuda())
+    assert y.shape == (1, 3, 32, 32)
+    assert rel_err(y, gold("decoder_4x4")) < 2e-2      # 30 convolutions deep in fp16
+
+
+@pytest.mark.parametrize("hw", [16, 32])
+def test_decoder_against_oracle(vae, oracle, hw):
+    m, sd = vae
+    z = rnd(40 + hw, 1, 4, hw, hw)
+    with torch.no_grad():
+        ref = oracle.vae_decoder(sd, "first_stage_model.decoder", z)
+    y = m.decoder(z.cuda())
+    assert y.shape == (1, 3, 8 * hw, 8 * hw)
+    assert rel_err(y, ref) < 2e-2
+
+
+def test_decode_uint8(vae, oracle):
+    from tinyfusers_b200.variants.sd import StableDiffusion
+    m, sd = vae
+    model = StableDiffusion.__new__(StableDiffusion)
+    model.first_stage_model = m
+    z = 0.18215 * rnd(51, 1, 4, 16, 16)
+    img = model.decode(z.cuda())
+    assert img.shape == (128, 128, 3) and img.dtype == torch.uint8
+    with torch.no_grad():
+        ref = oracle.vae_decode(sd, z)
+        ref_f = oracle.vae_decode_float(sd, z)
+    d = (img.cpu().float() - ref.float()).abs()
+    # fp16 convolutions move the float image by <= 2e-2 of its range before the * 255 quantisation
+    tol_levels = 2e-2 * ref_f.abs().max().item() * 255 / 2 + 1
+    assert d.max().item() <= tol_levels and d.mean().item() < 1.0
+    # PSNR of the decoded image against the oracle's, the north-star gate (>= 40 dB)
+    mse = ((img.cpu().float() - ref.float()) ** 2).mean().item()
+    assert 10 * math.log10(255.0 ** 2 / max(mse, 1e-12)) > 40.0
+
+
+def test_decode_full_size_batch_consistency(vae):
+    """512^2 (64x64 latent): finite, bit-reproducible, and image i of a batch equals the same image decoded alone."""
+    m, _ = vae
+    z = rnd(61, 2, 4, 64, 64).cuda()
+    y2 = m.decoder(z)
+    assert y2.shape == (2, 3, 512, 512) and torch.isfinite(y2).all()
+    y0 = m.decoder(z[:1])
+    assert torch.equal(m.decoder(z[:1]), y0)
+    assert rel_err(y2[:1], y0) < 5e-3     # different tile / split choices at M = 2x vs 1x pixels: fp16 accumulation order
+
+
+# ---- CLIP -------------------------------------------------------------------------------------------------------
+
+def test_clip_mlp_and_attention(clip):
+    m, _ = clip
+    h = rnd(751, 1, 77, 768).cuda()
+    assert rel_err(m.encoder.layers[0].mlp(h), gold("clip_mlp")) < 1e-2
+    assert rel_err(m.encoder.layers[0].self_attn(h, None), gold("clip_attention")) < 1e-2
+
+
+def test_clip_text_transformer(clip, oracle):
+    m, sd = clip
+    ids = GOLD["clip_ids"].astype(np.int64)
+    out = m(ids)
+    assert out.shape == (1, 77, 768) and out.dtype == torch.float32
+    assert rel_err(out, gold("clip_text_transformer")) < 2e-2     # 12 layers, fp16 residual stream
+    # a short prompt (T < 77) and a batch of two
+    ids2 = np.stack([ids[0, :16], np.roll(ids[0, :16], 3)])
+    with torch.no_grad():
+        ref = torch.cat([oracle.clip_text_transformer(sd, ids2[i:i + 1]) for i in range(2)])
+    assert rel_err(m(ids2), ref) < 2e-2

@@ -178,3 +178,123 @@ class SpatialTransformer:
         self.proj_out._run(ctx, h, out, residual=x)
         ctx.arena.release(mark)
         return out
+
+
+class AttnBlock:
+    """VAE attention block (reference: tinyfusers/attention/attention.py:10-24).
+
+    The reference passes the 4-D (B,C,H,W) q/k/v straight into scaled_dot_product_attention, which reads them as
+    (B, NH = C, T = H, HS = W): every channel plane attends over its own rows (SURVEY.md section 8 parity note 3).
+    That is what runs here under `set_quirks(True)` (default): GroupNorm -> ONE GEMM for [q | k | v] (bias fused)
+    -> NHWC->NCHW planes -> tf_plane_attention_f16 -> NCHW->NHWC -> proj_out GEMM (+bias +x).
+    The canonical LDM block (one head over H*W pixels, head dim C = 512) is not built: it needs a 512-wide head."""
+
+    def __init__(self, in_channels):
+        self.norm = GroupNorm(32, in_channels)
+        self.q = Conv2d(in_channels, in_channels, kernel_size=[1, 1])
+        self.k = Conv2d(in_channels, in_channels, kernel_size=[1, 1])
+        self.v = Conv2d(in_channels, in_channels, kernel_size=[1, 1])
+        self.proj_out = Conv2d(in_channels, in_channels, kernel_size=[1, 1])
+        self.in_channels = in_channels
+
+    def _packed(self):
+        def build():
+            w = torch.cat([packing.conv1x1_weight(m.weight, 8) for m in (self.q, self.k, self.v)], dim=0).contiguous()
+            b = torch.cat([packing.f32(m.bias) for m in (self.q, self.k, self.v)]).contiguous()
+            return w, b
+        return packing.cached(self, "qkv", (self.q.weight, self.k.weight, self.v.weight, self.q.bias, self.k.bias,
+                                            self.v.bias), build)
+
+    def __call__(self, x):
+        require_cuda(x, "x")
+        ctx = standalone_context()
+        ctx.arena.reset()
+        a = nchw_to_act(x, c_pad_to=8)
+        out = new_act_tensor(a.n, a.h, a.w, a.c, device=x.device)
+        self._run(ctx, a, out)
+        return act_to_nchw(out, x.shape[1])
+
+    def _run(self, ctx, x, out):
+        if not ctx.quirks:
+            raise RuntimeError("tinyfusers_b200 AttnBlock: the canonical single-head block (head dim = channels) is not "
+                               "built; only the reference's per-plane reading (set_quirks(True)) is")
+        C, H, W = x.c, x.h, x.w
+        if C % 8 != 0 or W % 2 != 0:
+            raise RuntimeError(f"tinyfusers_b200 AttnBlock: needs channels % 8 == 0 and an even width (C={C}, W={W})")
+        mark = ctx.arena.mark()
+        hn = ctx.new_act(x.n, H, W, C)
+        self.norm._run(ctx, x, hn, silu=False)
+        w, b = self._packed()
+        qkv = ctx.new_act(x.n, H, W, 3 * C)
+        ctx.gemm(hn.ptr, hn.stride, hn.rows, C, w.data_ptr(), 3 * C, qkv.ptr, 3 * C, bias=b.data_ptr())
+        planes = ctx.arena.alloc(2 * x.n * 3 * C * H * W)       # (n, 3C, H, W): q planes, k planes, v planes per image
+        ctx.to_nchw_f16(qkv, planes)
+        o_planes = ctx.arena.alloc(2 * x.n * C * H * W)
+        pb = 2 * C * H * W
+        for i in range(x.n):
+            base = planes + i * 3 * pb
+            ctx.plane_attention(base, base + pb, base + 2 * pb, o_planes + i * pb, C, H, W)
+        o = ctx.new_act(x.n, H, W, C)
+        ctx.from_nchw_f16(o_planes, o)
+        self.proj_out._run(ctx, o, out, residual=x)
+        ctx.arena.release(mark)
+        return out
+
+
+class CLIPAttention:
+    """CLIP self-attention (reference: tinyfusers/attention/attention.py:78-99): 12 heads x 64, q/k/v/out Linears with
+    bias, additive causal mask, heads merged canonically. Fast path: ONE GEMM for [q | k] (bias fused), V^T from a
+    swapped-operand GEMM, causal tcgen05 flash attention, out_proj GEMM (+bias +residual). The V bias never touches
+    the attention: softmax rows sum to 1, so P (V + 1 b_v^T) = P V + b_v^T, and b_v is folded into the out_proj bias
+    (b_o + W_o b_v) when the weights are packed."""
+
+    def __init__(self):
+        self.embed_dim = 768
+        self.num_heads = 12
+        self.head_dim = self.embed_dim // self.num_heads
+        self.k_proj = Linear(self.embed_dim, self.embed_dim)
+        self.v_proj = Linear(self.embed_dim, self.embed_dim)
+        self.q_proj = Linear(self.embed_dim, self.embed_dim)
+        self.out_proj = Linear(self.embed_dim, self.embed_dim)
+
+    def _packed(self):
+        mods = (self.q_proj, self.k_proj, self.v_proj, self.out_proj)
+        def build():
+            wqk = torch.cat((self.q_proj.weight, self.k_proj.weight), dim=0).to(F16).contiguous()
+            bqk = torch.cat((packing.f32(self.q_proj.bias), packing.f32(self.k_proj.bias))).contiguous()
+            wv = self.v_proj.weight.to(F16).contiguous()
+            wo = self.out_proj.weight.to(F16).contiguous()
+            bo = (packing.f32(self.out_proj.bias) + packing.f32(self.out_proj.weight) @ packing.f32(self.v_proj.bias)).contiguous()
+            return wqk, bqk, wv, wo, bo
+        return packing.cached(self, "clipattn", tuple(m.weight for m in mods) + tuple(m.bias for m in mods), build)
+
+    def __call__(self, hidden_states, causal_attention_mask=None):
+        """(B, T, 768) -> (B, T, 768). The mask argument is accepted for signature parity; the kernel applies the causal
+        mask the reference always passes (vae/encoder.py:79)."""
+        require_cuda(hidden_states, "hidden_states")
+        ctx = standalone_context()
+        B, T, E = hidden_states.shape
+        Tp = (T + 7) // 8 * 8
+        outs = []
+        for i in range(B):
+            ctx.arena.reset()
+            xn = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
+            xn[:T] = hidden_states[i]
+            h = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
+            self._run(ctx, xn.data_ptr(), h.data_ptr(), T, Tp, residual=False)
+            outs.append(h[:T].to(F32))
+        return torch.stack(outs)
+
+    # xn: (Tp, E) fp16 normalised input whose rows >= T are zero; h (Tp, E): h <- out_proj(attn) (+ h)
+    def _run(self, ctx, xn_ptr, h_ptr, T, Tp, residual=True):
+        E, NH, D = self.embed_dim, self.num_heads, self.head_dim
+        wqk, bqk, wv, wo, bo = self._packed()
+        mark = ctx.arena.mark()
+        qk = ctx.arena.alloc(2 * Tp * 2 * E)
+        ctx.gemm(xn_ptr, E, T, E, wqk.data_ptr(), 2 * E, qk, 2 * E, bias=bqk.data_ptr())
+        vt = ctx.arena.alloc(2 * E * Tp)
+        ctx.gemm(wv.data_ptr(), E, E, E, xn_ptr, Tp, vt, Tp, ldw=E)          # V^T (E, Tp): pad columns are exact zeros
+        a = ctx.arena.alloc(2 * Tp * E)
+        ctx.attention_causal(qk, 2 * E, qk + 2 * E, 2 * E, vt, Tp, a, 1, NH, T, Tp, D, D)
+        ctx.gemm(a, E, T, E, wo.data_ptr(), E, h_ptr, E, bias=bo.data_ptr(), residual_ptr=h_ptr if residual else None, ldr=E)
+        ctx.arena.release(mark)

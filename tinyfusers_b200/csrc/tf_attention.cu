@@ -30,6 +30,7 @@ struct AttnParams {
   int B, NH, Tq, Tk, Tk_pad, d, dp;
   int nkv;      // key blocks
   int stages;   // K/V ring depth
+  int causal;   // 1: query t only sees keys <= t (CLIP's additive triu(-inf, k=1) mask, vae/encoder.py:79)
   uint32_t tmem_cols;
   float scale_log2;  // (1/sqrt(d)) * log2(e)
   __half* out;
@@ -198,7 +199,8 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tf::tmem_ld_wait();
       tf::tcgen05_fence_before();
       tf::mbar_arrive(s_empty(buf));
-      const int valid = min(BN, p.Tk - j * BN);  // keys >= Tk are padding / another batch
+      int valid = min(BN, p.Tk - j * BN);  // keys >= Tk are padding / another batch
+      if (p.causal) valid = min(valid, qt * BQ + row + 1 - j * BN);   // per row: keys above the diagonal are masked
       if (valid < BN) {
 #pragma unroll
         for (int i = 0; i < BN; ++i)
@@ -308,9 +310,9 @@ extern "C" int tf_attention_set_tuning(int force_bn) {
   return TF_OK;
 }
 
-extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
-                                long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
-                                int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream_) {
+static int attention_impl(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
+                          long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
+                          int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, int causal, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TF_CHECK_ARG(q && k && vt && out, "tf_attention_f16: null pointer");
   TF_CHECK_ARG(B > 0 && NH > 0 && Tq > 0 && Tk > 0 && Tk_pad >= Tk, "tf_attention_f16: bad dims");
@@ -334,6 +336,7 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
   AttnParams p{};
   p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp;
   p.nkv = ceil_div_i(Tk, BN);
+  p.causal = causal ? 1 : 0;
   uint32_t need = 2 * BN + dp + 16, cols = 32;   // S double buffer, O, L
   while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
@@ -397,4 +400,19 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
+}
+
+extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
+                                long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
+                                int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream) {
+  return attention_impl(q, ldq, k, ldk, vt, ldvt, out, out_stride_b, out_stride_h, out_stride_t, B, NH, Tq, Tk, Tk_pad, d, dp,
+                        scale, 0, stream);
+}
+
+extern "C" int tf_attention_causal_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
+                                       long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
+                                       int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream) {
+  TF_CHECK_ARG(Tq == Tk, "tf_attention_causal_f16: causal masking needs Tq == Tk (got %d, %d)", Tq, Tk);
+  return attention_impl(q, ldq, k, ldk, vt, ldvt, out, out_stride_b, out_stride_h, out_stride_t, B, NH, Tq, Tk, Tk_pad, d, dp,
+                        scale, 1, stream);
 }

@@ -249,13 +249,13 @@ extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const f
                                            void* stream) {
   TF_CHECK_ARG(x && w && out && x_images > 0, "tf_conv3x3_smallcin_f32nchw: null pointer");
   TF_CHECK_ARG(Cin == 4, "tf_conv3x3_smallcin_f32nchw: only Cin == 4 is built (got %d)", Cin);
-  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && (Cout * Cin * 9 + Cout) * 4 <= 64 * 1024,
+  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && (Cout * Cin * 9 + Cout) * 4 <= 100 * 1024,
                "tf_conv3x3_smallcin_f32nchw: bad Cout %d", Cout);
   const long npix = (long)NI * H * W;
   const size_t smem = (size_t)(Cout * Cin * 9 + Cout) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    TF_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
   TF_CHECK_ARG(((uintptr_t)w & 15) == 0, "tf_conv3x3_smallcin_f32nchw: weights must be 16-byte aligned");

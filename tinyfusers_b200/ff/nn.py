@@ -57,3 +57,32 @@ class FeedForward:
         ctx.gemm(g_ptr, inner, M, inner, w.data_ptr(), dim, h_ptr, dim, bias=b.data_ptr() if b is not None else None,
                  residual_ptr=h_ptr, ldr=dim)
         ctx.arena.release(mark)
+
+
+class CLIPMLP:
+    """reference: tinyfusers/ff/nn.py:25-34 — fc1 -> quick_gelu -> fc2."""
+
+    def __init__(self):
+        self.fc1 = Linear(768, 3072)
+        self.fc2 = Linear(3072, 768)
+
+    def __call__(self, hidden_states):
+        require_cuda(hidden_states, "hidden_states")
+        ctx = standalone_context()
+        ctx.arena.reset()
+        x2 = hidden_states.reshape(-1, 768).to(F16).contiguous()
+        h = torch.zeros_like(x2)
+        self._run(ctx, x2.data_ptr(), h.data_ptr(), x2.shape[0], residual=False)
+        return h.to(F32).reshape(hidden_states.shape)
+
+    # h (M, 768) fp16:  h <- fc2(quick_gelu(fc1(xn))) (+ h)
+    def _run(self, ctx, xn_ptr, h_ptr, M, residual=True):
+        w1, b1 = self.fc1._packed()
+        w2, b2 = self.fc2._packed()
+        mark = ctx.arena.mark()
+        m = ctx.arena.alloc(2 * M * 3072)
+        ctx.gemm(xn_ptr, 768, M, 768, w1.data_ptr(), 3072, m, 3072, bias=b1.data_ptr() if b1 is not None else None)
+        ctx.unary(m, M * 3072, 3)
+        ctx.gemm(m, 3072, M, 3072, w2.data_ptr(), 768, h_ptr, 768, bias=b2.data_ptr() if b2 is not None else None,
+                 residual_ptr=h_ptr if residual else None, ldr=768)
+        ctx.arena.release(mark)

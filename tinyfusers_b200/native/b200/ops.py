@@ -48,6 +48,13 @@ _SIGNATURES = {
     "tf_attention_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "tf_attention_set_tuning": (c_int, [c_int]),
+    "tf_attention_causal_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
+                                        c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
+    "tf_plane_attention_f16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "tf_conv1x1_small_f32nchw": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    "tf_image_to_u8": (c_int, [_P, c_int, _P, c_longlong, c_int, _P]),
+    "tf_embedding_f16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "tf_cast_f16_to_f32": (c_int, [_P, _P, c_longlong, _P]),
     "tf_timestep_embedding_f32": (c_int, [_P, _P, c_int, c_float, _P, _P]),
     "tf_gemv_f16w": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "tf_conv3x3_smallcin_f32nchw": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -127,23 +127,28 @@ class Context:
         self.context_tokens = 0
         self.fuse_gn = os.environ.get("TINYFUSERS_B200_FUSE_GN", "1") != "0"
         self.ctx_kv = None         # dict: id(CrossAttention) -> (k_ptr, ldk, vt_ptr, ldvt) projected once per forward
+        self.gn_fuse_max_hw = 16384
 
     def ensure_workspaces(self):
         if self.ws is None:
             self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 
     # -- allocation ------------------------------------------------------------------------------
-    def new_act(self, n, h, w, c, stride=None, gn=False):
+    def new_act(self, n, h, w, c, stride=None, gn=False, gn_unit=None):
         stride = c if stride is None else stride
         ptr = self.arena.alloc(2 * n * h * w * stride)
         a = Act(ptr, n, h, w, c, stride)
         if gn:
-            self.attach_gn(a)
+            self.attach_gn(a, gn_unit)
         return a
 
-    def attach_gn(self, a):
-        """Give `a` a statistics buffer its producer (a GEMM / conv epilogue) will fill, if the geometry qualifies."""
-        unit = gn_unit(a.c)
+    def attach_gn(self, a, unit=None):
+        """Give `a` a statistics buffer its producer (a GEMM / conv epilogue) will fill, if the geometry qualifies.
+        Every block of the one-launch GroupNorm folds all (rows/32) slots of its image, which stops paying beyond
+        ~16k pixels per image (VAE decoder at 256^2 / 512^2): those tensors take the statistics-pass path."""
+        unit = gn_unit(a.c) if unit is None else unit
+        if a.h * a.w > self.gn_fuse_max_hw:
+            return a
         if self.fuse_gn and unit and b200.tf_gn_stats_supported(a.n, a.h, a.w, a.c, unit, 1):
             ptr = self.arena.alloc(8 * a.n * (a.h * a.w // 32) * (a.c // unit))
             a.gn = [(0, a.c, ptr, unit)]
@@ -245,6 +250,43 @@ class Context:
                          lambda: b200.tf_attention_f16(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, osb, osh, ost, B, NH, Tq,
                                                        Tk, Tk_pad, d, dp, 1.0 / math.sqrt(d), stream_ptr()))
         b200.check(st, "tf_attention_f16")
+
+    def attention_causal(self, q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, B, NH, T, T_pad, d, dp):
+        """Causal self-attention with the canonical head merge (CLIPAttention, reference attention.py:88-99)."""
+        if self.skip("attention"):
+            return
+        st = self._timed(("attention_causal", B, NH, T, T, d),
+                         lambda: b200.tf_attention_causal_f16(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, T * NH * d, d,
+                                                              NH * d, B, NH, T, T, T_pad, d, dp, 1.0 / math.sqrt(d),
+                                                              stream_ptr()))
+        b200.check(st, "tf_attention_causal_f16")
+
+    def plane_attention(self, q_ptr, k_ptr, v_ptr, out_ptr, planes, H, W):
+        if self.skip("attention"):
+            return
+        st = self._timed(("plane_attention", planes, H, W),
+                         lambda: b200.tf_plane_attention_f16(q_ptr, k_ptr, v_ptr, out_ptr, planes, H, W, 1.0 / math.sqrt(W),
+                                                             stream_ptr()))
+        b200.check(st, "tf_plane_attention_f16")
+
+    def to_nchw_f16(self, x, out_ptr):
+        """fp16 NHWC Act -> fp16 NCHW planes at out_ptr."""
+        if self.skip("misc"):
+            return
+        st = b200.tf_nhwc_to_nchw(x.ptr, x.stride, out_ptr, 0, x.n, x.c, x.h * x.w, stream_ptr())
+        b200.check(st, "tf_nhwc_to_nchw")
+
+    def from_nchw_f16(self, src_ptr, out):
+        """fp16 NCHW planes at src_ptr -> fp16 NHWC Act."""
+        if self.skip("misc"):
+            return
+        st = b200.tf_nchw_to_nhwc_f16(src_ptr, 0, out.ptr, out.n, out.c, out.h * out.w, out.stride, stream_ptr())
+        b200.check(st, "tf_nchw_to_nhwc_f16")
+
+    def unary(self, ptr, n, op):
+        if self.skip("misc"):
+            return
+        b200.check(b200.tf_unary(ptr, ptr, n, op, 0, stream_ptr()), "tf_unary")
 
     def upsample2x(self, x, out):
         if self.skip("misc"):

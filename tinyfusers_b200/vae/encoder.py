@@ -1,0 +1,124 @@
+"""CLIP text encoder + VAE image encoder containers with the reference's signatures
+(reference: tinyfusers/vae/encoder.py:12-81).
+
+CLIPTextTransformer: token + position embedding (one gather kernel) -> 12 pre-LN layers
+[LayerNorm -> causal 12-head attention -> +residual ; LayerNorm -> fc1 -> quick_gelu -> fc2 -> +residual] -> final
+LayerNorm. 7 launches per layer on the tcgen05 GEMM / attention kernels; the residual stream is fp16 (Tp = 80 rows,
+rows >= 77 stay zero so that the swapped-operand V^T projection yields exact zeros in its pad columns).
+The VAE `Encoder` (image -> latent) is not on the text-to-image path: it keeps its constructor so that checkpoint
+keys load, and raises when called."""
+import numpy as np
+import torch
+
+from ..attention.attention import CLIPAttention
+from ..ff.embedding import Embedding, _ids_tensor
+from ..ff.group_norm import GroupNorm
+from ..ff.layer_norm import LayerNorm
+from ..ff.nn import CLIPMLP
+from ..native.b200.ops import b200
+from ..runtime import F16, F32, standalone_context, stream_ptr
+from ..vision.conv2d import Conv2d
+from ..vision.resnet import ResnetBlock
+from .mid import Mid
+
+
+class Encoder:
+    def __init__(self):
+        sz = [(128, 128), (128, 256), (256, 512), (512, 512)]
+        self.conv_in = Conv2d(3, 128, kernel_size=[3, 3], padding=[1, 1])
+        arr = []
+        for i, s in enumerate(sz):
+            arr.append({"block": [ResnetBlock(s[0], s[1]), ResnetBlock(s[1], s[1])]})
+            if i != 3:
+                arr[-1]['downsample'] = {"conv": Conv2d(s[1], s[1], kernel_size=[3, 3], stride=[2, 2], padding=[0, 1, 0, 1])}
+        self.down = arr
+        self.mid = Mid(512)
+        self.norm_out = GroupNorm(32, 512)
+        self.conv_out = Conv2d(512, 8, kernel_size=[3, 3], padding=[1, 1])
+
+    def __call__(self, x):
+        raise RuntimeError("tinyfusers_b200: the VAE image Encoder is not built (text-to-image uses the Decoder only; "
+                           "its asymmetric-padding stride-2 convolutions have no B200 kernel yet)")
+
+
+class CLIPEncoderLayer:
+    def __init__(self):
+        self.self_attn = CLIPAttention()
+        self.layer_norm1 = LayerNorm(768)
+        self.mlp = CLIPMLP()
+        self.layer_norm2 = LayerNorm(768)
+
+    def __call__(self, hidden_states, causal_attention_mask=None):
+        B, T, E = hidden_states.shape
+        ctx = standalone_context()
+        Tp = (T + 7) // 8 * 8
+        outs = []
+        for i in range(B):
+            ctx.arena.reset()
+            h = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
+            h[:T] = hidden_states[i]
+            xn = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
+            self._run(ctx, h.data_ptr(), xn.data_ptr(), T, Tp)
+            outs.append(h[:T].to(F32))
+        return torch.stack(outs)
+
+    # h (Tp, 768) fp16 residual stream, updated in place; xn: scratch for the normalised rows (rows >= T stay zero)
+    def _run(self, ctx, h_ptr, xn_ptr, T, Tp):
+        self.layer_norm1._run(ctx, h_ptr, xn_ptr, 1, T, 768)
+        self.self_attn._run(ctx, xn_ptr, h_ptr, T, Tp)
+        self.layer_norm2._run(ctx, h_ptr, xn_ptr, 1, T, 768)
+        self.mlp._run(ctx, xn_ptr, h_ptr, T)
+
+
+class CLIPEncoder:
+    def __init__(self):
+        self.layers = [CLIPEncoderLayer() for i in range(12)]
+
+    def __call__(self, hidden_states, causal_attention_mask=None):
+        for l in self.layers:
+            hidden_states = l(hidden_states, causal_attention_mask)
+        return hidden_states
+
+
+class CLIPTextEmbeddings:
+    def __init__(self):
+        self.token_embedding = Embedding(49408, 768)
+        self.position_embedding = Embedding(77, 768)
+
+    def __call__(self, input_ids, position_ids):
+        return self.token_embedding(input_ids) + self.position_embedding(position_ids)
+
+
+class CLIPTextTransformer:
+    def __init__(self):
+        self.embeddings = CLIPTextEmbeddings()
+        self.encoder = CLIPEncoder()
+        self.final_layer_norm = LayerNorm(768)
+
+    def __call__(self, input_ids):
+        """(B, T <= 77) token ids -> (B, T, 768) fp32 prompt embeddings (reference: encoder.py:78-81)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        b200.init(dev.index)
+        ids = _ids_tensor(input_ids, dev)
+        if ids.dim() == 1:
+            ids = ids.reshape(1, -1)
+        B, T = ids.shape
+        if T > 77:
+            raise RuntimeError(f"CLIPTextTransformer: {T} tokens, the position table has 77")
+        Tp = (T + 7) // 8 * 8
+        ctx = standalone_context()
+        out = torch.empty((B, T, 768), dtype=F32, device=dev)
+        tok = self.embeddings.token_embedding.weight
+        pos = self.embeddings.position_embedding.weight
+        S = stream_ptr()
+        for i in range(B):
+            ctx.arena.reset()
+            h = torch.zeros((Tp, 768), dtype=F16, device=dev)
+            xn = torch.zeros((Tp, 768), dtype=F16, device=dev)
+            b200.check(b200.tf_embedding_f16(ids[i].data_ptr(), tok.data_ptr(), pos.data_ptr(), h.data_ptr(), T, T, 768,
+                                             tok.shape[0], S), "tf_embedding_f16")
+            for l in self.encoder.layers:
+                l._run(ctx, h.data_ptr(), xn.data_ptr(), T, Tp)
+            self.final_layer_norm._run(ctx, h.data_ptr(), xn.data_ptr(), 1, T, 768)
+            b200.check(b200.tf_cast_f16_to_f32(xn.data_ptr(), out[i].data_ptr(), T * 768, S), "tf_cast_f16_to_f32")
+        return out

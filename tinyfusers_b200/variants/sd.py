@@ -6,8 +6,8 @@ step (sd.py:34-41); here the step is a fixed launch sequence on one stream — c
 by index, one fused kernel does CFG + DDIM in place — and `sample()` captures it once into a CUDA graph
 and replays it with a device-resident step counter selecting (t, a_t, a_prev) from device tables.
 
-The VAE and the CLIP text encoder are outside the denoising hot path (SURVEY.md §8f "next" rows) and are
-not built yet: `decode` and `cond_stage_model` raise loudly instead of falling back to anything.
+`decode` (post_quant_conv -> VAE decoder -> uint8 image) and `cond_stage_model` (CLIP text encoder) are the rows next
+to the hot path; they run on the same kernels (tinyfusers_b200/vae).
 """
 from collections import namedtuple
 
@@ -17,18 +17,9 @@ import torch
 from .. import get_layernorm_strided, get_quirks
 from ..native.b200.ops import b200
 from ..runtime import F32, require_cuda, stream_ptr
+from ..vae.encoder import CLIPTextTransformer
+from ..vae.vae import AutoencoderKL
 from ..vision.unet import UNetModel
-
-
-class _NotBuilt:
-    def __init__(self, what):
-        self._what = what
-
-    def __getattr__(self, name):
-        raise RuntimeError(f"tinyfusers_b200: {self._what} is not built yet (outside the UNet hot path, SURVEY.md §8f)")
-
-    def __call__(self, *a, **k):
-        raise RuntimeError(f"tinyfusers_b200: {self._what} is not built yet (outside the UNet hot path, SURVEY.md §8f)")
 
 
 def get_alphas_cumprod(beta_start=0.00085, beta_end=0.0120, n_training_steps=1000):
@@ -43,8 +34,9 @@ class StableDiffusion:
     def __init__(self):
         self.alphas_cumprod = get_alphas_cumprod()
         self.model = namedtuple("DiffusionModel", ["diffusion_model"])(diffusion_model=UNetModel())
-        self.first_stage_model = _NotBuilt("AutoencoderKL (VAE)")
-        self.cond_stage_model = _NotBuilt("CLIPTextTransformer")
+        self.first_stage_model = AutoencoderKL()
+        self.cond_stage_model = namedtuple("CondStageModel", ["transformer"])(
+            transformer=namedtuple("Transformer", ["text_model"])(text_model=CLIPTextTransformer()))
         self._samplers = {}
 
     # ---- reference API -------------------------------------------------------------------------
@@ -67,7 +59,18 @@ class StableDiffusion:
         return s.e_t.clone()
 
     def decode(self, x):
-        return self.first_stage_model.decoder(x)
+        """Latent (B,4,h,w) -> uint8 image (8h, 8w, 3) for B = 1 (as the reference), (B, 8h, 8w, 3) otherwise
+        (reference: sd.py:48-54, whose reshape(3,512,512) is generalised to the decoded size)."""
+        require_cuda(x, "x")
+        fsm = self.first_stage_model
+        z = fsm.post_quant(x, 1 / 0.18215)
+        eng = fsm.decoder._engine(tuple(z.shape))
+        img = eng.decode_nhwc_f32(z)                       # (B, H, W, 8) fp32 NHWC, channels 0..2 valid
+        B, H, W, _ = img.shape
+        out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device)
+        st = b200.tf_image_to_u8(img.data_ptr(), 8, out.data_ptr(), B * H * W, 3, stream_ptr())
+        b200.check(st, "tf_image_to_u8")
+        return out[0] if B == 1 else out
 
     def __call__(self, unconditional_context, context, latent, timestep, alphas, alphas_prev, guidance):
         s = self._sampler(latent.shape, context.shape[1])

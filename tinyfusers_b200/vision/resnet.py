@@ -69,3 +69,44 @@ class ResBlock:
         self.out_layers[3]._run(ctx, h2, out, residual=res)
         ctx.arena.release(mark)
         return out
+
+
+class ResnetBlock:
+    """VAE residual block (reference: tinyfusers/vision/resnet.py:33-45): conv1(swish(norm1 x)) -> conv2(swish(norm2 .))
+    + nin_shortcut(x) (1x1 conv when the channel count changes). Fast path: 2 x GroupNorm+SiLU, 2 implicit-GEMM convs;
+    conv1's epilogue leaves norm2's statistics, the shortcut is conv2's epilogue residual."""
+
+    def __init__(self, in_channels, out_channels=None):
+        out_channels = in_channels if out_channels is None else out_channels
+        self.norm1 = GroupNorm(32, in_channels)
+        self.conv1 = Conv2d(in_channels, out_channels, kernel_size=[3, 3], padding=[1, 1])
+        self.norm2 = GroupNorm(32, out_channels)
+        self.conv2 = Conv2d(out_channels, out_channels, kernel_size=[3, 3], padding=[1, 1])
+        self.nin_shortcut = Conv2d(in_channels, out_channels, kernel_size=[1, 1]) if in_channels != out_channels else lambda x: x
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+    def __call__(self, x):
+        require_cuda(x, "x")
+        ctx = standalone_context()
+        ctx.arena.reset()
+        a = nchw_to_act(x, c_pad_to=8)
+        out = new_act_tensor(a.n, a.h, a.w, self.out_channels, device=x.device)
+        self._run(ctx, a, out)
+        return act_to_nchw(out, self.out_channels)
+
+    def _run(self, ctx, x, out):
+        mark = ctx.arena.mark()
+        h0 = ctx.new_act(x.n, x.h, x.w, x.c)
+        self.norm1._run(ctx, x, h0, silu=True)
+        h1 = ctx.new_act(x.n, x.h, x.w, self.out_channels, gn=True, gn_unit=self.out_channels // 32)
+        self.conv1._run(ctx, h0, h1)
+        h2 = ctx.new_act(x.n, x.h, x.w, self.out_channels)
+        self.norm2._run(ctx, h1, h2, silu=True)
+        if isinstance(self.nin_shortcut, Conv2d):
+            res = ctx.new_act(x.n, x.h, x.w, self.out_channels)
+            self.nin_shortcut._run(ctx, x, res)
+        else:
+            res = x
+        self.conv2._run(ctx, h2, out, residual=res)
+        ctx.arena.release(mark)
+        return out
