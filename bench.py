@@ -272,6 +272,44 @@ def run_ours(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
+    # ---- BASELINE.json configs[2] (C3), N = 1 only: token ids -> CLIP -> 50 graph-replayed steps -> VAE decode ----
+    c3 = None
+    if world == 1:
+        import numpy as np
+        with contextlib.redirect_stdout(io.StringIO()):
+            update_state(model.first_stage_model, R.make_vae_decoder_state_dict(), "first_stage_model")
+            update_state(model.cond_stage_model, R.make_clip_state_dict(), "cond_stage_model")
+        ids = np.array([[49406, 320, 1125, 539, 320, 2368, 6765, 525, 320, 11795] + [49407] * 67])
+        empty = np.array([[49406] + [49407] * 76])
+        text_model = model.cond_stage_model.transformer.text_model
+        lat_dev = lat.to(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+        def one_image(timed):
+            if timed:
+                ev[0].record()
+            c, u = text_model(ids), text_model(empty)
+            if timed:
+                ev[1].record()
+            x = model.sample(u, c, lat_dev, ts, alphas, alphas_prev, guidance)
+            if timed:
+                ev[2].record()
+            img = model.decode(x)
+            if timed:
+                ev[3].record()
+            return img
+        one_image(False)
+        torch.cuda.synchronize()
+        b200.tf_launch_count_reset()
+        img = one_image(True)
+        torch.cuda.synchronize()
+        clip_ms, sample_ms, decode_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+        vae_flops = 2.47e12
+        c3 = {"workload": "SD1.5 text-to-image: CLIP text encoder (2 prompts) + 50-step sampler + VAE decode, 512^2, batch 1",
+              "images_per_s": 1000.0 / (clip_ms + sample_ms + decode_ms), "clip_ms": clip_ms, "sampler_50_steps_ms": sample_ms,
+              "vae_decode_ms": decode_ms, "vae_decode_tflops": vae_flops / (decode_ms / 1000.0) / 1e12,
+              "image_shape": list(img.shape), "eager_launches_clip_and_decode": int(b200.tf_launch_count())}
+
     # ---- per-kernel-class device time inside the step (graphs holding only that class), rank 0 ----
     peaks = measured_peaks()
     eng = sampler.unet_engine
@@ -334,6 +372,7 @@ def run_ours(args, rank, local_rank, world):
         "breakdown_ms": breakdown,
         "attention": {"achieved": attn_tflops, "unit": "TFLOP/s", "algorithmic_flops_per_step": flops["attention"]},
         "whole_step_tflops": flops["total"] / (ms / args.steps / 1000.0) / 1e12,
+        "c3_text_to_image": c3,
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"one oracle CFG step at {hw}x{hw} latent (batch 2), scaled to 64x64 by the "
                                    f"algorithmic FLOP ratio {ratio:.2f}"},

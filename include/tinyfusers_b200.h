@@ -135,6 +135,8 @@ int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void*
                      long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
                      int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream);
 int tf_attention_set_tuning(int force_bn);
+/* debug hook: per-block clock64 stamps of one softmax warp ([64][8] int64; NULL = off; TF_ATT_TRACE builds only) */
+int tf_attention_set_timeline(long long* dev_buf);
 /* Same, under a causal mask: query t attends to keys <= t only (Tq == Tk). Replaces CLIPAttention's
  * scaled_dot_product_attention(q, k, v, attn_mask = triu(full(-inf), k=1))
  *           tinyfusers/attention/attention.py:88-99, tinyfusers/vae/encoder.py:79, attention/sdpa.py:67-68. */

@@ -25,7 +25,8 @@ FLAGS = [
     "-I", os.path.join(ROOT, "include"),
     "-I", HERE,
     "-DTF_BUILDING_LIB",
-] + (["-DTF_GEMM_TRACE=1"] if os.environ.get("TF_GEMM_TRACE") == "1" else [])
+] + (["-DTF_GEMM_TRACE=1"] if os.environ.get("TF_GEMM_TRACE") == "1" else []) \
+  + (["-DTF_ATT_TRACE=1"] if os.environ.get("TF_ATT_TRACE") == "1" else [])
 
 
 def sources():

@@ -6,7 +6,11 @@
 // Here scores never leave the SM: S = Q·K^T goes to TMEM, four softmax warps (one thread per query
 // row — the 32x32b TMEM load hands each thread its own row, so row max / sum need no shuffles) run the
 // online softmax and write P (fp16) to shared memory in the 128B-swizzled K-major layout, and
-// O += P·V accumulates in TMEM. S is double-buffered so QK^T of block j+1 overlaps softmax of block j.
+// O += P·V accumulates in TMEM. S lives in ONE TMEM buffer: the softmax warps copy it to registers, so QK^T of
+// block j+1 is issued as soon as block j has been drained and overlaps its exponentials. Key blocks are 128 wide
+// where shared memory allows two CTAs per SM (head dim <= 48), 64 otherwise: the per-block fixed cost (barrier round
+// trips, TMEM load latency, fences; ~700 of ~1800 cycles per 64-key block, measured with tools/dev_attn_timeline.py)
+// is paid half as often.
 //
 // Operand layouts (produced by the projection GEMMs, see tinyfusers_b200/attention/attention.py):
 //   Q  : (B*Tq,      ldq)  fp16, head h at columns [h*dp, (h+1)*dp), dp = head dim padded to 16
@@ -35,7 +39,17 @@ struct AttnParams {
   float scale_log2;  // (1/sqrt(d)) * log2(e)
   __half* out;
   long long osb, osh, ost;
+  long long* timeline;   // debug (TF_ATT_TRACE build): clock stamps of CTA (0,0,0), softmax warp 0: [block][8]
 };
+
+#ifndef TF_ATT_TRACE
+#define TF_ATT_TRACE 0
+#endif
+#if TF_ATT_TRACE
+#define ATT_STAMP(i) do { if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64 && j < 64) p.timeline[j * 8 + (i)] = clock64(); } while (0)
+#else
+#define ATT_STAMP(i) do { } while (0)
+#endif
 
 // K-major operand, 32-byte swizzle: rows are 32 B (16 fp16), 8-row groups 256 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw32_kmajor(uint32_t smem_addr) {
@@ -48,8 +62,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw32_kmajor(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kAttThreads, (BN == 64) ? 2 : 1)
+// OCC = CTAs per SM the register allocation is bounded for (3: 64-key blocks, head dim <= 48, long sequences: three
+// resident CTAs keep the MUFU pipe ~85 % busy instead of ~57 %, and 444 slots swallow the 512-CTA grid of a
+// 4096-token SD self-attention in one wave plus a short tail)
+template <int BN, int OCC>
+__global__ void __launch_bounds__(kAttThreads, OCC)
 tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -74,8 +91,8 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
-  auto s_full = [&](int i) { return bar_base + 8u * (1 + 2 * ST + i); };
-  auto s_empty = [&](int i) { return bar_base + 8u * (3 + 2 * ST + i); };
+  const uint32_t s_full = bar_base + 8u * (1 + 2 * ST);
+  const uint32_t s_empty = bar_base + 8u * (3 + 2 * ST);
   const uint32_t p_full = bar_base + 8u * (5 + 2 * ST);
   const uint32_t pv_done = bar_base + 8u * (6 + 2 * ST);
   const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * ST);
@@ -92,10 +109,8 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tf::mbar_init(kv_full(s), 1);
       tf::mbar_init(kv_empty(s), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      tf::mbar_init(s_full(i), 1);
-      tf::mbar_init(s_empty(i), 128);
-    }
+    tf::mbar_init(s_full, 1);
+    tf::mbar_init(s_empty, 128);
     tf::mbar_init(p_full, 128);
     tf::mbar_init(pv_done, 1);
     tf::fence_mbar_init();
@@ -114,8 +129,8 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   tf::pdl_wait();
-  const uint32_t tmem_s0 = tmem_base;            // S buffers: columns [0,BN) and [BN,2BN)
-  const uint32_t tmem_o = tmem_base + 2 * BN;    // O: dp columns, then 16 columns of L = P . 1 (the softmax denominator)
+  const uint32_t tmem_s0 = tmem_base;            // S: columns [0,BN)
+  const uint32_t tmem_o = tmem_base + BN;        // O: dp columns, then 16 columns of L = P . 1 (the softmax denominator)
   const uint32_t tmem_l = tmem_o + p.dp;
 
   const int nkv = p.nkv;
@@ -147,15 +162,15 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto issue_s = [&](int j) {
         const int s = j % ST;
         tf::mbar_wait(kv_full(s), (uint32_t)(j / ST) & 1u);
-        const int buf = j & 1;
-        tf::mbar_wait(s_empty(buf), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        // S_{j-1} must have been drained to registers by all four softmax warps
+        tf::mbar_wait(s_empty, ((uint32_t)j & 1u) ^ 1u);
         tf::tcgen05_fence_after();
         const uint32_t kbase = smem_k + s * k_bytes;
         for (int k = 0; k < slabs; ++k) {
-          tf::umma_f16_ss(tmem_s0 + buf * BN, umma_desc_sw32_kmajor(smem_q + k * (BQ * 32)),
+          tf::umma_f16_ss(tmem_s0, umma_desc_sw32_kmajor(smem_q + k * (BQ * 32)),
                           umma_desc_sw32_kmajor(kbase + k * (BN * 32)), idesc_s, k > 0 ? 1u : 0u);
         }
-        tf::umma_commit(s_full(buf));
+        tf::umma_commit(s_full);
       };
       tf::mbar_wait(q_full, 0);
       issue_s(0);
@@ -190,56 +205,77 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // fp16, accumulation is fp32, and O / L is exact whatever reference max is used).
     float m_run = -INFINITY;  // reference max of this row, in the scaled log2 domain
     for (int j = 0; j < nkv; ++j) {
-      const int buf = j & 1;
-      tf::mbar_wait(s_full(buf), ((uint32_t)(j >> 1)) & 1u);
+      ATT_STAMP(0);
+      tf::mbar_wait(s_full, (uint32_t)j & 1u);
       tf::tcgen05_fence_after();
-      uint32_t v[BN];
+      ATT_STAMP(1);
+      constexpr int NH64 = BN / 64;              // 64-column halves of the block: registers hold one half at a time
+      int valid = min(BN, p.Tk - j * BN);
+      if (p.causal) valid = min(valid, qt * BQ + row + 1 - j * BN);
+      // keys >= valid (padding / another batch / above the causal diagonal, per row) are masked
+      uint32_t v[64];
+      auto load_half = [&](int hh) {
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) tf::tmem_ld_x32(tmem_s0 + lane_field + buf * BN + c, v + c);
-      tf::tmem_ld_wait();
-      tf::tcgen05_fence_before();
-      tf::mbar_arrive(s_empty(buf));
-      int valid = min(BN, p.Tk - j * BN);  // keys >= Tk are padding / another batch
-      if (p.causal) valid = min(valid, qt * BQ + row + 1 - j * BN);   // per row: keys above the diagonal are masked
-      if (valid < BN) {
+        for (int c = 0; c < 64; c += 32) tf::tmem_ld_x32(tmem_s0 + lane_field + hh * 64 + c, v + c);
+        tf::tmem_ld_wait();
+        const int vh = valid - hh * 64;
+        if (vh < 64) {
 #pragma unroll
-        for (int i = 0; i < BN; ++i)
-          if (i >= valid) v[i] = 0xff800000u;   // -inf
-      }
+          for (int i = 0; i < 64; ++i)
+            if (i >= vh) v[i] = 0xff800000u;   // -inf
+        }
+      };
+      // ---- pass 1: block max (BN = 128 re-reads the halves from TMEM in pass 2: a 64-column load is ~30 cycles) ----
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < BN; i += 4) {
+      for (int hh = 0; hh < NH64; ++hh) {
+        load_half(hh);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(v[i + u]));
+        for (int i = 0; i < 64; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(v[i + u]));
+        }
       }
+      ATT_STAMP(2);
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;   // scale > 0
       float alpha = 1.0f;
       if (mx > m_run + 8.0f) {          // also taken on the first block (m_run = -inf)
         alpha = exp2f(m_run - mx);      // 0 on the first block
         m_run = mx;
       }
+      ATT_STAMP(3);
       const float neg_m = -m_run;
-      uint32_t pk[BN / 2];
+      // ---- pass 2: exponentials, pack, store P ----
 #pragma unroll
-      for (int i = 0; i < BN; i += 2) {
-        const float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-        const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
-        __half2 hh = __floats2half2_rn(p0, p1);
-        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-      }
-      // P smem and O are owned by the tensor core until PV_{j-1} has completed
-      if (j > 0) {
-        tf::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
-        tf::tcgen05_fence_after();
-      }
-      // P -> shared memory, K-major 128B swizzle: 16-byte chunk index XOR (row & 7)
+      for (int hh = 0; hh < NH64; ++hh) {
+        if (NH64 > 1) load_half(hh);   // BN = 64 still holds its only half
+        if (hh == NH64 - 1) {          // S is in registers: the tensor core may overwrite it with S_{j+1}
+          tf::tcgen05_fence_before();
+          tf::mbar_arrive(s_empty);
+        }
+        uint32_t pk[32];
 #pragma unroll
-      for (int a = 0; a < BN / 64; ++a) {
-        const uint32_t rbase = smem_p + a * (BQ * 128) + row * 128;
+        for (int i = 0; i < 64; i += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+          const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
+          __half2 h2v = __floats2half2_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2v);
+        }
+        if (hh == 0) {
+          ATT_STAMP(4);
+          // P smem and O are owned by the tensor core until PV_{j-1} has completed
+          if (j > 0) {
+            tf::mbar_wait(pv_done, (uint32_t)(j - 1) & 1u);
+            tf::tcgen05_fence_after();
+          }
+          ATT_STAMP(5);
+        }
+        // P -> shared memory, K-major 128B swizzle: 16-byte chunk index XOR (row & 7)
+        const uint32_t rbase = smem_p + hh * (BQ * 128) + row * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           const uint32_t addr = rbase + ((uint32_t)(ch ^ (row & 7)) << 4);
-          const int w = a * 32 + ch * 4;
+          const int w = ch * 4;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[w]), "r"(pk[w + 1]),
                        "r"(pk[w + 2]), "r"(pk[w + 3])
                        : "memory");
@@ -257,9 +293,11 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         tf::tmem_st_wait();
       }
+      ATT_STAMP(6);
       tf::fence_proxy_async_smem();
       tf::tcgen05_fence_before();
       tf::mbar_arrive(p_full);
+      ATT_STAMP(7);
     }
     // ---- epilogue: O / l -> fp16 -> global ----
     tf::mbar_wait(pv_done, (uint32_t)(nkv - 1) & 1u);
@@ -302,10 +340,19 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 int g_force_attn_bn = 0;
+int g_force_attn_occ = 0;
+long long* g_attn_timeline = nullptr;
 
 }  // namespace
 
+extern "C" int tf_attention_set_timeline(long long* dev_buf) {
+  g_attn_timeline = dev_buf;   // >= 64 * 8 int64; debug only (stamps exist in TF_ATT_TRACE builds)
+  return TF_OK;
+}
+
 extern "C" int tf_attention_set_tuning(int force_bn) {
+  g_force_attn_occ = force_bn / 1000;   // thousands digit: CTAs per SM (0 = auto), e.g. 3064 = 64-key blocks, 3 CTAs / SM
+  force_bn %= 1000;
   g_force_attn_bn = force_bn;
   return TF_OK;
 }
@@ -329,15 +376,39 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
                    ((uintptr_t)out & 15) == 0,
                "tf_attention_f16: pointers must be 16-byte aligned");
 
-  int BN = 64;  // 64-key blocks: two CTAs per SM (TMEM 2*64 + dp <= 256 columns) hide softmax latency
+  // 128-key blocks when two CTAs per SM still fit (TMEM <= 256 columns, >= 2 K/V stages in half an SM's shared
+  // memory) and the sequence is long enough to amortise them; 64-key blocks otherwise
+  auto fits2 = [&](int bn) {
+    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * bn * 2 + 4096 + 2 * (size_t)(2 * bn * dp * 2);
+    return bn + dp + 16 <= 256 && need <= (size_t)113 * 1024 - 2048;
+  };
+  // measured on B200 (tools/dev_attn_variants.py): 2 CTAs/SM x 128 keys beats 2 x 64 by 1-2 % at 4096 tokens;
+  // 1 CTA/SM x 128 keys beats 64 by 23 % when the grid has no second CTA per SM to offer (1024 tokens, d = 80);
+  // 3 CTAs/SM x 64 keys sustains 19 % more (444 vs 373 TFLOP/s) but only pays once the grid is several waves long
+  // (a 512-CTA grid on 444 slots runs one slow wave plus a full-length tail)
+  const long grid_ctas = (long)ceil_div_i(Tq, BQ) * NH * B;
+  auto fits1 = [&](int bn) {
+    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * bn * 2 + 4096 + 2 * (size_t)(2 * bn * dp * 2);
+    return bn + dp + 16 <= 512 && need <= (size_t)227 * 1024 - 2048;
+  };
+  auto fits3 = [&]() {
+    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * 64 * 2 + 4096 + 2 * (size_t)(2 * 64 * dp * 2);
+    return 64 + dp + 16 <= 128 && need <= (size_t)75 * 1024 - 1024;
+  };
+  int BN = 64, occ = 2;
+  if (Tk >= 512 && (fits2(128) || (grid_ctas <= tf_num_sms() && fits1(128)))) BN = 128;
+  if (Tk >= 512 && fits3() && grid_ctas >= 1024) { BN = 64; occ = 3; }
   if (g_force_attn_bn == 64 || g_force_attn_bn == 128) BN = g_force_attn_bn;
-  if (BN == 128 && 2 * 128 + dp + 16 > 512) BN = 64;
+  if (g_force_attn_occ == 2 || (g_force_attn_occ == 3 && BN == 64 && fits3())) occ = g_force_attn_occ;
+  if (BN == 128) occ = 2;
+  if (BN == 128 && 128 + dp + 16 > 512) BN = 64;
 
   AttnParams p{};
   p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp;
   p.nkv = ceil_div_i(Tk, BN);
   p.causal = causal ? 1 : 0;
-  uint32_t need = 2 * BN + dp + 16, cols = 32;   // S double buffer, O, L
+  p.timeline = g_attn_timeline;
+  uint32_t need = BN + dp + 16, cols = 32;   // S, O, L
   while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -345,11 +416,17 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
   p.osb = out_stride_b; p.osh = out_stride_h; p.ost = out_stride_t;
 
   const size_t q_bytes = (size_t)BQ * dp * 2, k_bytes = (size_t)BN * dp * 2, p_bytes = (size_t)BQ * BN * 2;
-  const size_t budget = (cols <= 256 ? 113 : 227) * 1024 - 2048;
-  int stages = (int)((budget - q_bytes - p_bytes - 2048) / (2 * k_bytes));
+  // half an SM's shared memory (two CTAs per SM) when that still holds a K/V ring of >= 2 stages - the MMA warp
+  // issues S_{j+1} before PV_j, so block j+1 must land while block j's stage is still in use - else the whole SM
+  auto ring = [&](size_t budget) {
+    const long room = (long)budget - (long)q_bytes - (long)p_bytes - 2048;
+    return room < 0 ? 0 : (int)(room / (long)(2 * k_bytes));
+  };
+  int stages = occ == 3 ? ring((size_t)75 * 1024 - 1024) : (cols <= 256 ? ring((size_t)113 * 1024 - 2048) : 0);
+  if (stages < 2 && stages < p.nkv) stages = ring((size_t)227 * 1024 - 2048);
   if (stages > 4) stages = 4;
   if (stages > p.nkv) stages = p.nkv < 1 ? 1 : p.nkv;
-  TF_CHECK_ARG(stages >= 1, "tf_attention_f16: head dim %d does not fit shared memory", dp);
+  TF_CHECK_ARG(stages >= 2 || (stages == 1 && p.nkv == 1), "tf_attention_f16: head dim %d does not fit shared memory", dp);
   p.stages = stages;
   const size_t smem = q_bytes + p_bytes + 2048 + (size_t)stages * 2 * k_bytes + 2048;
 
@@ -382,21 +459,16 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
     if (rc) return rc;
   }
   dim3 grid(ceil_div_i(Tq, BQ), NH, B);
-  if (BN == 64) {
-    static bool set64 = false;
-    if (!set64) {
-      TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      set64 = true;
-    }
-    TF_LAUNCH((tf_attention_kernel<64>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
-  } else {
-    static bool set128 = false;
-    if (!set128) {
-      TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      set128 = true;
-    }
-    TF_LAUNCH((tf_attention_kernel<128>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
   }
+  if (BN == 64 && occ == 3) TF_LAUNCH((tf_attention_kernel<64, 3>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
+  else if (BN == 64) TF_LAUNCH((tf_attention_kernel<64, 2>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
+  else TF_LAUNCH((tf_attention_kernel<128, 2>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
