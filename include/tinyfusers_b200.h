@@ -85,6 +85,14 @@ int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_con
 int tf_gemm_set_tuning(int force_bn, int force_splits);
 /* test / tuning hook: 0 = auto, 1 = single-CTA tiles only, 2 = CTA-pair (cta_group::2, 256-row) tiles where M > 128 */
 int tf_gemm_set_ctas(int force_ctas);
+/* measured tile choices: (is_conv, M, N, K, class) -> (BN, split-K factor, CTAs per tile) overrides the built-in cost
+ * model for that shape. class bits: 1 GEGLU, 2 fp32 out, 4 GroupNorm statistics, 8 residual, 16 stride-2 conv. For a
+ * conv, M = NI*Ho*Wo, N = Cout, K = 9*Cin. Entries that do not fit a call (workspace too small, ...) are ignored.
+ * tools/autotune_gemm.py writes native/b200/gemm_tuning.json on a B200; the Python binding loads it in init(). */
+int tf_gemm_tuning_add(int is_conv, int M, int N, int K, int klass, int bn, int splits, int ctas);
+int tf_gemm_tuning_clear(void);
+/* the (BN, split-K, CTAs) the most recent GEMM / conv call on this process used */
+int tf_gemm_last_choice(int* bn, int* splits, int* ctas);
 /* debug hook: per-CTA clock64 stamps of the next GEMM/conv launches ([grid][8] int64; NULL = off) */
 int tf_gemm_set_timeline(long long* dev_buf);
 

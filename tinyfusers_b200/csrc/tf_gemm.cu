@@ -14,6 +14,10 @@
 // that tf_splitk_reduce folds (deep, small-M UNet levels are weight-bandwidth bound at batch 2).
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "tf_common.cuh"
 #include "tinyfusers_b200.h"
 
@@ -659,9 +663,33 @@ static int lcm_i(int a, int b) {
 
 static int g_force_bn = 0, g_force_splits = 0, g_force_ctas = 0;
 
+// Measured tile choices (tools/autotune_gemm.py on a B200 -> native/b200/gemm_tuning.json, loaded by the binding at
+// init): (is_conv, M, N, K, class) -> (BN, split-K, CTAs per tile). class = epilogue / geometry bits that change the
+// cost: 1 GEGLU, 2 fp32 out, 4 GroupNorm statistics, 8 residual, 16 stride-2 conv. Shapes without an entry use the
+// cycle model below.
+typedef std::tuple<int, int, int, int, int> TuneKey;
+static std::map<TuneKey, TileChoice>* g_tune = nullptr;
+static std::mutex g_tune_mutex;
+static TileChoice g_last_choice{0, 0, 0};
+
 static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool allow_split,
-                               size_t ws_bytes, int M, int force_bn, int force_splits, int bn_mult = 32) {
+                               size_t ws_bytes, int M, int force_bn, int force_splits, int bn_mult, const TuneKey& key) {
   const int sms = tf_num_sms();
+  if (force_bn <= 0 && force_splits <= 0 && g_force_ctas <= 0) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    if (g_tune) {
+      auto it = g_tune->find(key);
+      if (it != g_tune->end()) {
+        const TileChoice t = it->second;   // validated like the model's candidates: a stale table can never mis-launch
+        const int kbs = ceil_div_i(k_blocks, t.splits);
+        const bool ok = t.bn >= bn_mult && t.bn <= 256 && t.bn % bn_mult == 0 && t.splits >= 1 &&
+                        (t.splits == 1 || (allow_split && (size_t)t.splits * M * N * sizeof(float) <= ws_bytes &&
+                                           (t.splits - 1) * kbs < k_blocks)) &&
+                        (t.ctas == 1 || (t.ctas == 2 && m_tiles >= 2 && t.bn % 32 == 0));
+        if (ok) return t;
+      }
+    }
+  }
   TileChoice best{128, 1, 1};
   double best_cost = 1e30;
   (void)flags;
@@ -691,7 +719,7 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
         // k-block is feed-bound for every bn <= 256; a CTA pair loads only half of the weight tile per SM
         const double feed = (128.0 + (double)bn / ctas) * 128.0 / 52.0;
         const double per_kb = (2.0 * bn > feed) ? 2.0 * bn : feed;
-        double cost = waves * (kbs * per_kb + 1500.0 + 4.0 * bn + (ctas == 2 ? 300.0 : 0.0));
+        double cost = waves * (kbs * per_kb + 1500.0 + 4.0 * bn + (ctas == 2 ? 1200.0 : 0.0));   // pair: cluster launch + two cluster barriers, measured 950-1450 cycles (tools/autotune_gemm.py)
         if (sp > 1) cost += 8000.0 + (double)sp * M * N * 8.0 / (sms * 64.0);
         if (cost < best_cost) {
           best_cost = cost;
@@ -783,6 +811,27 @@ extern "C" int tf_gemm_set_tuning(int force_bn, int force_splits) {
   return TF_OK;
 }
 
+extern "C" int tf_gemm_tuning_add(int is_conv, int M, int N, int K, int klass, int bn, int splits, int ctas) {
+  TF_CHECK_ARG(bn > 0 && bn <= 256 && splits >= 1 && splits <= 64 && (ctas == 1 || ctas == 2), "tf_gemm_tuning_add: bad entry");
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  if (!g_tune) g_tune = new std::map<TuneKey, TileChoice>();
+  (*g_tune)[TuneKey(is_conv, M, N, K, klass)] = TileChoice{bn, splits, ctas};
+  return TF_OK;
+}
+
+extern "C" int tf_gemm_tuning_clear(void) {
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  if (g_tune) g_tune->clear();
+  return TF_OK;
+}
+
+extern "C" int tf_gemm_last_choice(int* bn, int* splits, int* ctas) {
+  if (bn) *bn = g_last_choice.bn;
+  if (splits) *splits = g_last_choice.splits;
+  if (ctas) *ctas = g_last_choice.ctas;
+  return TF_OK;
+}
+
 extern "C" int tf_gemm_set_ctas(int force_ctas) {
   g_force_ctas = force_ctas;   // 0 = auto, 1 = single-CTA tiles, 2 = CTA-pair tiles (where M > 128)
   return TF_OK;
@@ -824,8 +873,10 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   p.m_tiles = ceil_div_i(M, BM);
   p.k_blocks = ceil_div_i(K, BK);
   const bool allow_split = !(flags & TF_EPI_GEGLU) && workspace != nullptr;
+  const int klass = (flags & 3) | (gn_stats ? 4 : 0) | (residual ? 8 : 0);
   TileChoice tc = choose_tiles(p.m_tiles, N, p.k_blocks, flags, allow_split, ws_bytes, M, g_force_bn,
-                               g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32);
+                               g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32, TuneKey(0, M, N, K, klass));
+  g_last_choice = tc;
   p.bn = tc.bn;
   p.splits = tc.splits;
   p.ctas = tc.ctas;
@@ -947,8 +998,10 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   // store box of one epilogue warp = 32 consecutive tile rows (x fastest, then y, then image)
   g.sbw = g.TW >= 32 ? 32 : g.TW;
   g.sbh = g.TW >= 32 ? 1 : (g.TW * g.TH >= 32 ? 32 / g.TW : g.TH);
+  const int klass = (flags & 3) | (gn_stats ? 4 : 0) | (residual ? 8 : 0) | (stride == 2 ? 16 : 0);
   TileChoice tc = choose_tiles(p.m_tiles, Cout, p.k_blocks, flags, workspace != nullptr, ws_bytes, p.M, g_force_bn,
-                               g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32);
+                               g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32, TuneKey(1, p.M, Cout, p.K, klass));
+  g_last_choice = tc;
   p.bn = tc.bn;
   p.splits = tc.splits;
   p.ctas = tc.ctas;

@@ -30,6 +30,9 @@ _SIGNATURES = {
     "tf_gemm_set_tuning": (c_int, [c_int, c_int]),
     "tf_gemm_set_ctas": (c_int, [c_int]),
     "tf_gemm_set_timeline": (c_int, [_P]),
+    "tf_gemm_tuning_add": (c_int, [c_int] * 8),
+    "tf_gemm_tuning_clear": (c_int, []),
+    "tf_gemm_last_choice": (c_int, [_P, _P, _P]),
     "tf_gemm_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
                             _P, c_size_t, _P]),
     "tf_conv2d_nhwc_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
@@ -99,6 +102,21 @@ class B200:
         if not self._initialised:
             self.check(self.tf_init(int(device)), "tf_init")
             self._initialised = True
+            self.load_tuning()
+
+    def load_tuning(self, path=None):
+        """Measured GEMM / conv tile choices (tools/autotune_gemm.py, run on a B200). Optional: shapes without an entry
+        use the library's cost model. TINYFUSERS_B200_TUNING=0 disables the table."""
+        import json
+        path = os.path.join(_HERE, "gemm_tuning.json") if path is None else path
+        self.tf_gemm_tuning_clear()
+        if os.environ.get("TINYFUSERS_B200_TUNING", "1") == "0" or not os.path.exists(path):
+            return 0
+        with open(path) as fh:
+            entries = json.load(fh)["entries"]
+        for e in entries:
+            self.check(self.tf_gemm_tuning_add(*[int(v) for v in e[:8]]), "tf_gemm_tuning_add")
+        return len(entries)
 
 
 b200 = B200()

@@ -183,7 +183,7 @@ class Context:
             fn = lambda: b200.tf_gemm_gn_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
                                              residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, gn[0], gn[1], gn[2],
                                              stream_ptr())
-        st = self._timed(("gemm", M, N, K, flags, residual_ptr is not None), fn)
+        st = self._timed(("gemm", M, N, K, flags, residual_ptr is not None, gn[1] if gn else 0, gn[2] if gn else 0), fn)
         b200.check(st, "tf_gemm_f16")
 
     def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0, gn=None):
@@ -198,7 +198,7 @@ class Context:
             fn = lambda: b200.tf_conv2d_nhwc_gn_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w, cout, 3, stride, out.ptr,
                                                     out.stride, bias, rp, rs, flags, self.ws.data_ptr(), self.ws_bytes,
                                                     gn[0], gn[1], stream_ptr())
-        st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None), fn)
+        st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None, gn[1] if gn else 0), fn)
         b200.check(st, "tf_conv2d_nhwc_f16")
 
     def groupnorm(self, x, out, gamma, beta, eps, silu, groups=32):
