@@ -27,5 +27,7 @@ conv(2, 32, 32, 640, 640)
 gemm(8192, 2560, 320)
 gemm(8192, 320, 320)
 attn(2, 8, 4096, 40)
+conv(1, 512, 512, 128, 128, reps=2)      # VAE decoder, last stage (M = 262 144 pixels)
+attn(16, 8, 4096, 40, reps=2)            # C4 (8 images / GPU): 3 CTAs per SM variant
 torch.cuda.synchronize()
 print("done")
