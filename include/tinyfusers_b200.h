@@ -32,7 +32,7 @@ int tf_version(void);
 int tf_init(int device);
 const char* tf_last_error(void);
 /* number of kernels this library has launched since the last reset (bench.py: gpu_launches) */
-/* programmatic dependent launch between this library's kernels (default off; env TINYFUSERS_B200_PDL=1) */
+/* programmatic dependent launch between this library's kernels (default on; env TINYFUSERS_B200_PDL=0 disables) */
 int tf_set_pdl(int enable);
 long long tf_launch_count(void);
 void tf_launch_count_reset(void);
@@ -42,6 +42,11 @@ void tf_launch_count_reset(void);
 #define TF_EPI_OUT_F32 1 /* write fp32 instead of fp16 */
 #define TF_EPI_GEGLU 2   /* out[m, j] = (acc[m, v_j] + b) * gelu_tanh(acc[m, g_j] + b); weight rows packed
                             by tf_pack_geglu_rows: every 32 rows = 16 value rows then 16 gate rows */
+#define TF_GEMM_W_STATIC 4 /* promise: the W operand is a static weight, complete in memory before this call is enqueued
+                            (not written by a kernel still running on the stream). The kernel then starts fetching its
+                            first W tiles BEFORE it waits for the preceding kernel (programmatic dependent launch):
+                            every layer's weights arrive cold from HBM. Never set it for swapped-operand GEMMs that put
+                            an activation in the W slot (V^T = Wv . X^T). */
 
 /* D[M,N] = A[M,K] · W[N,K]^T (+ bias[N]) (+ residual[M,N]); fp16 in, fp32 accumulate (tcgen05/TMEM).
  * Replaces: Linear.__call__  cp.dot(x, W.T) + b          tinyfusers/ff/linear.py:116-121

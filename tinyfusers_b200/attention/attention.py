@@ -71,7 +71,7 @@ class CrossAttention:
                 raise RuntimeError(f"tinyfusers_b200 self-attention: {T} tokens per image; the B200 kernel needs a "
                                    "multiple of 8 (latent height*width at every UNet level)")
             vt_ptr = ctx.arena.alloc(2 * nh * dp * M)
-            ctx.gemm(wv.data_ptr(), C, nh * dp, C, xn_ptr, M, vt_ptr, M, ldw=C)
+            ctx.gemm(wv.data_ptr(), C, nh * dp, C, xn_ptr, M, vt_ptr, M, ldw=C, w_static=False)
             q_ptr, ldq, k_ptr, ldk = qk_ptr, 2 * nh * dp, qk_ptr + 2 * nh * dp, 2 * nh * dp
             Tk, Tkp, ldvt = T, T, M
         else:
@@ -88,7 +88,8 @@ class CrossAttention:
                 k_ptr = ctx.arena.alloc(2 * Mc * nh * dp)
                 ctx.gemm(context.ptr, context.stride, Mc, Cc, wk.data_ptr(), nh * dp, k_ptr, nh * dp)
                 vt_ptr = ctx.arena.alloc(2 * nh * dp * Mc)
-                ctx.gemm(wv.data_ptr(), Cc, nh * dp, Cc, context.ptr, Mc, vt_ptr, Mc, ldw=context.stride)
+                ctx.gemm(wv.data_ptr(), Cc, nh * dp, Cc, context.ptr, Mc, vt_ptr, Mc, ldw=context.stride,
+                         w_static=False)
                 ldk, ldvt = nh * dp, Mc
         a_ptr = ctx.arena.alloc(2 * M * nh * d)
         ctx.attention(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, a_ptr, B, nh, T, Tk, Tkp, d, dp, head_major=ctx.quirks)
@@ -293,7 +294,7 @@ class CLIPAttention:
         qk = ctx.arena.alloc(2 * Tp * 2 * E)
         ctx.gemm(xn_ptr, E, T, E, wqk.data_ptr(), 2 * E, qk, 2 * E, bias=bqk.data_ptr())
         vt = ctx.arena.alloc(2 * E * Tp)
-        ctx.gemm(wv.data_ptr(), E, E, E, xn_ptr, Tp, vt, Tp, ldw=E)          # V^T (E, Tp): pad columns are exact zeros
+        ctx.gemm(wv.data_ptr(), E, E, E, xn_ptr, Tp, vt, Tp, ldw=E, w_static=False)   # V^T (E, Tp): pad columns are exact zeros
         a = ctx.arena.alloc(2 * Tp * E)
         ctx.attention_causal(qk, 2 * E, qk + 2 * E, 2 * E, vt, Tp, a, 1, NH, T, Tp, D, D)
         ctx.gemm(a, E, T, E, wo.data_ptr(), E, h_ptr, E, bias=bo.data_ptr(), residual_ptr=h_ptr if residual else None, ldr=E)

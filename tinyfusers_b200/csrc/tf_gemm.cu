@@ -154,7 +154,10 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  tf::pdl_wait();   // barriers / TMEM / descriptors were set up while the producer kernels drained
+  // PDL: barriers / TMEM / descriptors were set up while the producer kernels drained. The dependency wait itself is
+  // taken per role below: the TMA warp first puts the WEIGHT tiles of its first ring fill in flight (weights do not
+  // depend on any kernel, and every layer's weights arrive cold from HBM), then waits, then loads activations.
+  if (warp != 0) tf::pdl_wait();
 
   // work items: (m-tile | pair of m-tiles) x n-tile x split, strided over the CTAs | clusters of the grid
   const int total_tiles = (k2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
@@ -185,6 +188,32 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tx_bytes = (A_STAGE_BYTES + b_stage_bytes) * kCtas;   // the leader's barrier counts both CTAs' bytes
     const int b_row_off = k2 ? (int)rank * (p.bn >> 1) : 0;
     const int cblocks = p.is_conv ? p.g.cblocks : 1, ksize = p.is_conv ? p.g.ksize : 1;
+    // ---- weight prefetch before the dependency wait: B tiles of the first min(S, k-blocks) stages of the first tile.
+    // Each stage's barrier is armed with the FULL byte count here; the matching A loads follow after the wait. ----
+    int pre = 0;   // k-blocks of the first tile whose barrier is armed and whose B tile is in flight
+    if (t_first < total_tiles && (p.flags & TF_GEMM_W_STATIC)) {
+      const int split = t_first % p.splits;
+      const int nt = (t_first / p.splits) % p.n_tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      pre = min(S, kb1 - kb0);
+      if (elected) {
+        const int brow = nt * p.bn + b_row_off;
+        for (int i = 0; i < pre; ++i) {
+          const uint32_t bd = smem_b + i * b_stage_bytes;
+          if (k2) {
+            const uint32_t fbl = fbar_leader0 + 8u * i;
+            if (leader) tf::mbar_expect_tx(full_bar(i), tx_bytes);
+            else tf::mbar_arrive_cluster(fbl);
+            tf::tma_load_2d_2sm(bd, &tmB, fbl, (kb0 + i) * BK, brow);
+          } else {
+            tf::mbar_expect_tx(full_bar(i), tx_bytes);
+            tf::tma_load_2d(bd, &tmB, full_bar(i), (kb0 + i) * BK, brow);
+          }
+        }
+      }
+    }
+    tf::pdl_wait();
     for (int t = t_first; t < total_tiles; t += t_step) {
       const int split = t % p.splits;
       const int t1 = t / p.splits;
@@ -205,7 +234,31 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int r = (kb0 / cblocks) / ksize, sx = (kb0 / cblocks) % ksize, cb = kb0 % cblocks;
       int kcol = kb0 * BK;
       const int arow = mt * BM, brow = nt * p.bn + b_row_off;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      auto advance = [&]() {
+        kcol += BK;
+        if (++cb == cblocks) { cb = 0; if (++sx == ksize) { sx = 0; ++r; } }
+        a_dst += A_STAGE_BYTES; b_dst += b_stage_bytes; fbar += 8u; ebar += 8u; fb += 8u;
+        if (++stage == S) {
+          stage = 0; phase ^= 1u;
+          a_dst = smem_a; b_dst = smem_b; fbar = full_bar(0); ebar = empty_bar(0); fb = fbar_leader0;
+        }
+      };
+      int kb = kb0;
+      // first tile only: the k-blocks whose barrier was armed and whose B tile was issued before the dependency wait
+      // get their A tile now (peeled, so the steady-state loop below keeps its instruction count: it is issue-bound)
+      for (; pre > 0; --pre, ++kb) {
+        if (elected) {
+          if (k2) {
+            if (p.is_conv) tf::tma_load_4d_2sm(a_dst, &tmA, fb, cb * BK, x0 + sx, y0 + r, n0);
+            else tf::tma_load_2d_2sm(a_dst, &tmA, fb, kcol, arow);
+          } else {
+            if (p.is_conv) tf::tma_load_4d(a_dst, &tmA, fbar, cb * BK, x0 + sx, y0 + r, n0);
+            else tf::tma_load_2d(a_dst, &tmA, fbar, kcol, arow);
+          }
+        }
+        advance();
+      }
+      for (; kb < kb1; ++kb) {
         tf::mbar_wait(ebar, phase ^ 1u);
         if (elected) {
           TF_TRACE_KB(0);
@@ -222,13 +275,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tf::tma_load_2d(b_dst, &tmB, fbar, kcol, brow);
           }
         }
-        kcol += BK;
-        if (++cb == cblocks) { cb = 0; if (++sx == ksize) { sx = 0; ++r; } }
-        a_dst += A_STAGE_BYTES; b_dst += b_stage_bytes; fbar += 8u; ebar += 8u; fb += 8u;
-        if (++stage == S) {
-          stage = 0; phase ^= 1u;
-          a_dst = smem_a; b_dst = smem_b; fbar = full_bar(0); ebar = empty_bar(0); fb = fbar_leader0;
-        }
+        advance();
       }
     }
   } else if (warp == 1) {

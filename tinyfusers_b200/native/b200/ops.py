@@ -127,3 +127,4 @@ b200.TF_ERR_DEVICE = -3
 b200.TF_EPI_NONE = 0
 b200.TF_EPI_OUT_F32 = 1
 b200.TF_EPI_GEGLU = 2
+b200.TF_GEMM_W_STATIC = 4

@@ -18,6 +18,10 @@ def cached(obj, name, tensors, builder):
     if hit is not None and hit[0] == key:
         return hit[1]
     val = builder()
+    if torch.cuda.is_available():
+        # the packed tensors are handed to kernels as STATIC weights (TF_GEMM_W_STATIC: fetched before the dependency
+        # wait of programmatic dependent launch), so they must be complete in memory before anything else is enqueued
+        torch.cuda.current_stream().synchronize()
     obj.__dict__[slot] = (key, val)
     return val
 

@@ -172,10 +172,15 @@ class Context:
         """True when the kernel must not be launched (arena dry run, or bench's per-class timing filter)."""
         return self.dry or (self.only is not None and kind not in self.only)
 
-    def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None, gn=None):
-        """gn = (stats_ptr, unit, rows_per_image): also emit the GroupNorm statistics of the output."""
+    def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None, gn=None,
+             w_static=True):
+        """gn = (stats_ptr, unit, rows_per_image): also emit the GroupNorm statistics of the output.
+        w_static: `w` is a packed weight (packing.cached synchronises after building it), so the kernel may fetch it
+        before waiting for the preceding kernel; False for swapped-operand calls whose W slot holds an activation."""
         if self.skip("gemm"):
             return
+        if w_static:
+            flags |= b200.TF_GEMM_W_STATIC
         if gn is None:
             fn = lambda: b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
                                           residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
@@ -183,12 +188,14 @@ class Context:
             fn = lambda: b200.tf_gemm_gn_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
                                              residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, gn[0], gn[1], gn[2],
                                              stream_ptr())
-        st = self._timed(("gemm", M, N, K, flags, residual_ptr is not None, gn[1] if gn else 0, gn[2] if gn else 0), fn)
+        st = self._timed(("gemm", M, N, K, flags & 3, residual_ptr is not None, gn[1] if gn else 0, gn[2] if gn else 0), fn)
         b200.check(st, "tf_gemm_f16")
 
-    def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0, gn=None):
+    def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0, gn=None, w_static=True):
         if self.skip("gemm"):
             return
+        if w_static:
+            flags |= b200.TF_GEMM_W_STATIC
         rp = residual.ptr if residual is not None else None
         rs = residual.stride if residual is not None else 0
         if gn is None:

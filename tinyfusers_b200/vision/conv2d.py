@@ -29,18 +29,19 @@ def _check_supported(ksize, stride, padding, dilation):
     return k[0], s[0]
 
 
-def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=None, flags=0):
+def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=None, flags=0, w_static=True):
     # the output's GroupNorm statistics are produced by this launch when `out` carries a (single-part) buffer
     gn = None
     if out.gn is not None and len(out.gn) == 1 and out.gn[0][0] == 0 and out.gn[0][1] == cout_p and flags == 0:
         gn = (out.gn[0][2], out.gn[0][3])
     if k == 3:
-        ctx.conv3x3(x, w_packed.data_ptr(), cout_p, out, bias=bias_ptr, residual=residual, stride=stride, flags=flags, gn=gn)
+        ctx.conv3x3(x, w_packed.data_ptr(), cout_p, out, bias=bias_ptr, residual=residual, stride=stride, flags=flags, gn=gn,
+                    w_static=w_static)
     else:
         ctx.gemm(x.ptr, x.stride, x.rows, x.c, w_packed.data_ptr(), cout_p, out.ptr, out.stride, bias=bias_ptr,
                  residual_ptr=residual.ptr if residual is not None else None,
                  ldr=residual.stride if residual is not None else 0, flags=flags,
-                 gn=(gn[0], gn[1], out.h * out.w) if gn else None)
+                 gn=(gn[0], gn[1], out.h * out.w) if gn else None, w_static=w_static)
 
 
 def conv_2d(X_gpu, W_gpu, padding, stride, dilation):
@@ -58,7 +59,7 @@ def conv_2d(X_gpu, W_gpu, padding, stride, dilation):
     Op = w.shape[0]
     Ho, Wo = (a.h + 2 * (k // 2) - k) // s + 1, (a.w + 2 * (k // 2) - k) // s + 1
     out = new_act_tensor(a.n, Ho, Wo, Op, device=X_gpu.device)
-    _conv_act(ctx, a, w, Op, k, s, out)
+    _conv_act(ctx, a, w, Op, k, s, out, w_static=False)    # w was packed a moment ago on this stream: not a static weight
     return act_to_nchw(out, O)
 
 

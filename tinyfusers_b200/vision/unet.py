@@ -216,7 +216,7 @@ class UNetModel:
         kall = ar.alloc(2 * Mc * kv_total)
         vtall = ar.alloc(2 * kv_total * Mc)
         ctx.gemm(cact.ptr, 768, Mc, 768, wk_all.data_ptr(), kv_total, kall, kv_total)
-        ctx.gemm(wv_all.data_ptr(), 768, kv_total, 768, cact.ptr, Mc, vtall, Mc, ldw=768)
+        ctx.gemm(wv_all.data_ptr(), 768, kv_total, 768, cact.ptr, Mc, vtall, Mc, ldw=768, w_static=False)
         ctx.ctx_kv = {key: (kall + 2 * off, kv_total, vtall + 2 * off * Mc, Mc) for key, off in kv_offs.items()}
         # --- plan the skip/concat buffers: output block j reads [x | saved[11-j]] ---
         res = [(H, W)]
