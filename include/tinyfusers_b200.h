@@ -14,6 +14,11 @@
  *     device; all work is enqueued on `stream`, so every call is CUDA-graph capturable;
  *   - activations are fp16, NHWC for images ( == (B, T, C) for token sequences ), accumulation,
  *     statistics and softmax are fp32. Weights are fp16 in the layouts stated per function.
+ *   - kernels are chained by programmatic dependent launch: each one lets its successor start launching on entry and
+ *     waits for its predecessor before it reads ACTIVATIONS. PARAMETERS (norm gamma / beta, the Cin = 4 conv weights,
+ *     and W with TF_GEMM_W_STATIC) are fetched before that wait, so they must be complete in memory when the call is
+ *     enqueued - i.e. not written by the kernel enqueued immediately before it on the same stream (the Python layer
+ *     synchronises once after packing weights);
  *   - there is NO CPU fallback. On a machine without an sm_100 GPU tf_init() fails.
  */
 #ifndef TINYFUSERS_B200_H_
@@ -98,6 +103,8 @@ int tf_gemm_tuning_add(int is_conv, int M, int N, int K, int klass, int bn, int 
 int tf_gemm_tuning_clear(void);
 /* the (BN, split-K, CTAs) the most recent GEMM / conv call on this process used */
 int tf_gemm_last_choice(int* bn, int* splits, int* ctas);
+/* measurement hook: cap the shared-memory ring depth of the next GEMM/conv launches (0 = as many stages as fit) */
+int tf_gemm_set_max_stages(int max_stages);
 /* debug hook: per-CTA clock64 stamps of the next GEMM/conv launches ([grid][8] int64; NULL = off) */
 int tf_gemm_set_timeline(long long* dev_buf);
 

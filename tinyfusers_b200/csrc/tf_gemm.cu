@@ -779,6 +779,7 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
 }
 
 static long long* g_timeline = nullptr;
+static int g_max_stages = 0;   // debug: cap the smem ring depth (0 = as many as fit)
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams& p,
                        cudaStream_t stream) {
@@ -791,6 +792,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int stage_bytes = A_STAGE_BYTES + p.bn * 128 / p.ctas;
   int stages = (kSmemBudget - 2048 - kEpiBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (g_max_stages >= 2 && stages > g_max_stages) stages = g_max_stages;
   if (stages < 2) {
     tf_set_error("gemm: tile too large for shared memory");
     return TF_ERR_ARG;
@@ -876,6 +878,11 @@ extern "C" int tf_gemm_last_choice(int* bn, int* splits, int* ctas) {
   if (bn) *bn = g_last_choice.bn;
   if (splits) *splits = g_last_choice.splits;
   if (ctas) *ctas = g_last_choice.ctas;
+  return TF_OK;
+}
+
+extern "C" int tf_gemm_set_max_stages(int max_stages) {
+  g_max_stages = max_stages;   // debug / measurement hook: 0 = no cap
   return TF_OK;
 }
 

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "tf_gemm_set_tuning": (c_int, [c_int, c_int]),
     "tf_gemm_set_ctas": (c_int, [c_int]),
     "tf_gemm_set_timeline": (c_int, [_P]),
+    "tf_gemm_set_max_stages": (c_int, [c_int]),
     "tf_gemm_tuning_add": (c_int, [c_int] * 8),
     "tf_gemm_tuning_clear": (c_int, []),
     "tf_gemm_last_choice": (c_int, [_P, _P, _P]),
