@@ -248,8 +248,9 @@ def run_ours(args, rank, local_rank, world):
     n_e2e = max(3, min(args.steps, 50))
 
     def e2e_step(i):
-        x = model(h_unc.to(dev, non_blocking=True), h_ctx.to(dev, non_blocking=True), h_lat.to(dev, non_blocking=True),
-                  torch.tensor([ts[i % 50]]), alphas[[i % 50]], alphas_prev[[i % 50]], torch.tensor([guidance]))
+        # pinned host tensors go straight into the call: it copies them into the sampler's resident device buffers
+        x = model(h_unc, h_ctx, h_lat, torch.tensor([ts[i % 50]]), alphas[[i % 50]], alphas_prev[[i % 50]],
+                  torch.tensor([guidance]))
         h_out.copy_(x, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller owns the result only after the read-back
 

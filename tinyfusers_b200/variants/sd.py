@@ -116,24 +116,39 @@ class SamplerEngine:
         self.context = e.context                    # (2B,T,768) fp32: [uncond ; cond]  (sd.py:32)
         self.e_t = torch.zeros((B, 4, H, W), dtype=F32, device=dev)
         self.max_steps = 1024
-        self.t_tab = torch.zeros(self.max_steps, dtype=F32, device=dev)
-        self.a_tab = torch.ones(self.max_steps, dtype=F32, device=dev)
-        self.ap_tab = torch.ones(self.max_steps, dtype=F32, device=dev)
+        # schedule tables: one (3, max_steps) buffer = [t ; a_t ; a_prev], so that the per-call scalars of the drop-in
+        # __call__ (column 0 of each row) arrive in ONE host->device copy from a pinned staging buffer
+        self.tab = torch.ones((3, self.max_steps), dtype=F32, device=dev)
+        self.tab[0].zero_()
+        self.t_tab, self.a_tab, self.ap_tab = self.tab[0], self.tab[1], self.tab[2]
+        self._scal_host = torch.zeros(3, dtype=F32).pin_memory()
+        self._scal_last = None
+        self._idx_zero = True
         self.idx = torch.zeros(1, dtype=torch.int32, device=dev)
         self.guidance = 7.5
 
     def load(self, unconditional_context, context, latent):
-        require_cuda(latent, "latent")
-        self.latent.copy_(latent.reshape(self.latent.shape))
+        """Device tensors, or host tensors (pinned: asynchronous) copied straight into the sampler's resident buffers."""
         B = self.B
-        self.context[:B].copy_(unconditional_context.reshape(B, -1, 768))
-        self.context[B:].copy_(context.reshape(B, -1, 768))
+        self.latent.copy_(latent.reshape(self.latent.shape), non_blocking=True)
+        self.context[:B].copy_(unconditional_context.reshape(B, -1, 768), non_blocking=True)
+        self.context[B:].copy_(context.reshape(B, -1, 768), non_blocking=True)
 
     def set_scalars(self, timestep, a_t, a_prev, guidance):
-        self.t_tab[0] = _scalar(timestep)
-        self.a_tab[0] = _scalar(a_t)
-        self.ap_tab[0] = _scalar(a_prev)
-        self.idx.zero_()
+        vals = (_scalar(timestep), _scalar(a_t), _scalar(a_prev))
+        if vals != self._scal_last:
+            # the pinned staging buffer may still be the source of the previous call's copy
+            ev = getattr(self, "_scal_event", None)
+            if ev is not None:
+                ev.synchronize()
+            self._scal_host[0], self._scal_host[1], self._scal_host[2] = vals
+            self.tab[:, 0].copy_(self._scal_host, non_blocking=True)
+            self._scal_event = torch.cuda.Event()
+            self._scal_event.record()
+            self._scal_last = vals
+        if not self._idx_zero:
+            self.idx.zero_()
+            self._idx_zero = True
         self.guidance = _scalar(guidance)
 
     def set_tables(self, timesteps, alphas, alphas_prev, guidance):
@@ -143,6 +158,7 @@ class SamplerEngine:
         self.a_tab[:n].copy_(torch.as_tensor(alphas, dtype=F32).reshape(-1)[:n])
         self.ap_tab[:n].copy_(torch.as_tensor(alphas_prev, dtype=F32).reshape(-1)[:n])
         self.idx.fill_(n - 1)   # the loop runs from the last timestep to the first
+        self._idx_zero, self._scal_last = False, None
         self.guidance = _scalar(guidance)
 
     def enqueue_step(self, update_latent=True, advance=False):
@@ -159,6 +175,7 @@ class SamplerEngine:
         b200.check(st, "tf_cfg_ddim_step_f32")
         if advance:
             b200.check(b200.tf_add_int(self.idx.data_ptr(), -1, stream_ptr()), "tf_add_int")
+            self._idx_zero = False
 
     def _scratch(self):
         if not hasattr(self, "_scratch_buf"):
@@ -198,6 +215,7 @@ class SamplerEngine:
             self.enqueue_step(update_latent=True, advance=False)
 
     def run(self, n_steps, use_graph=True):
+        self._idx_zero = False
         if use_graph:
             g = self._graph(True)
             for _ in range(n_steps):
