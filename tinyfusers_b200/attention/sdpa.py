@@ -11,12 +11,22 @@ from ..runtime import F16, F32, require_cuda, standalone_context
 
 def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
     require_cuda(q_cp, "q")
-    if attn_mask is not None:
-        raise RuntimeError("tinyfusers_b200 scaled_dot_product_attention: attn_mask is not built yet "
-                           "(needed only by the CLIP text encoder, SURVEY.md §8f-2)")
     ctx = standalone_context()
     B, NH, Tq, HS = q_cp.shape
     Tk = k_cp.shape[-2]
+    causal = False
+    if attn_mask is not None:
+        # the one mask the reference ever passes is CLIP's causal one (vae/encoder.py:79): additive triu(-inf, k=1), or
+        # its boolean form (sdpa.py:67-68: True = keep). That is a kernel flag; arbitrary masks are not built.
+        m = torch.as_tensor(attn_mask, device=q_cp.device)
+        keep = m.reshape(-1, m.shape[-2], m.shape[-1])[0]
+        keep = keep if keep.dtype == torch.bool else (keep == 0)
+        tril = torch.ones((Tq, Tk), dtype=torch.bool, device=q_cp.device).tril()
+        if Tq != Tk or m.numel() != Tq * Tk or not torch.equal(keep, tril) or \
+                (m.dtype != torch.bool and not torch.isinf(m.reshape(Tq, Tk)[~tril]).all()):
+            raise RuntimeError("tinyfusers_b200 scaled_dot_product_attention: only the causal mask "
+                               "(triu(-inf, k=1) / its boolean form) is built")
+        causal = True
     if HS % 8 != 0 or v_cp.shape[-1] != HS:
         raise RuntimeError(f"tinyfusers_b200 scaled_dot_product_attention: head size {HS} must be a multiple of 8 "
                            "and equal for q/k/v")
@@ -30,6 +40,13 @@ def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
     Vt = torch.zeros((NH, dp, B, Tkp), dtype=F16, device=dev)
     Vt[:, :HS, :, :Tk] = v_cp.permute(1, 3, 0, 2)
     out = torch.empty((B, NH, Tq, HS), dtype=F16, device=dev)
+    if causal:
+        # the causal entry point writes the canonical (B, T, NH*HS) merge; permute back to the reference's (B, NH, T, HS)
+        merged = torch.empty((B, Tq, NH, HS), dtype=F16, device=dev)
+        for b in range(B):
+            ctx.attention_causal(Q[b].data_ptr(), NH * dp, K[b].data_ptr(), NH * dp, Vt[:, :, b].contiguous().data_ptr(), Tkp,
+                                 merged[b].data_ptr(), 1, NH, Tq, Tkp, HS, dp)
+        return merged.permute(0, 2, 1, 3).to(F32)
     ctx.attention(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, Vt.data_ptr(), B * Tkp, out.data_ptr(), B, NH, Tq, Tk,
                   Tkp, HS, dp, head_major=True)
     return out.to(F32)
