@@ -7,11 +7,13 @@
 //                          NHWC input shifted by (r-1, s-1) — out-of-bounds pixels are zero-filled by the
 //                          TMA unit, which *is* the conv padding (reference: tinyfusers/vision/conv2d.py:48-59).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = epilogue
-// (TMEM -> registers -> bias / residual / GEGLU -> global). Accumulators are double-buffered in TMEM
-// (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
-// Tile = 128 x BN x 64, BN in {16..256 step 16} chosen per shape; optional split-K writes fp32 partials
-// that tf_splitk_reduce folds (deep, small-M UNet levels are weight-bandwidth bound at batch 2).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 = epilogue (two per TMEM lane
+// quarter: TMEM -> registers -> bias / residual / GEGLU -> swizzled smem staging -> TMA store). Accumulators are
+// double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Tile = 128 x BN x 64 (256 x BN x 64 for a CTA pair, cta_group::2), BN in {32..256 step 32}; (BN, split-K, pair) per
+// shape from a measured table or a cycle model; split-K writes fp32 partials that tf_splitk_reduce[_stats] folds
+// (deep, small-M UNet levels are weight-bandwidth bound at batch 2). Kernels are chained by programmatic dependent
+// launch; static weight tiles of the first ring fill are fetched before the dependency wait (TF_GEMM_W_STATIC).
 #include <stdlib.h>
 
 #include <map>
@@ -811,10 +813,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   } else {
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
-    static const bool dbg_cluster = getenv("TF_DEBUG_CLUSTER1") != nullptr;   // experiment: single-CTA kernel, cluster launch
-    if (dbg_cluster && grid % 2 == 0)
-      (void)tf_launch_pdl_cluster(tf_gemm_kernel<1>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, p);
-    else
     TF_LAUNCH(tf_gemm_kernel<1>, grid, kThreads, smem, stream, tmA, tmB, tmC, p);
   }
   TF_LAUNCH_CHECK();
