@@ -181,6 +181,11 @@ int tf_gemv_f16w(const float* x, const void* W, const float* bias, const float* 
  * Replaces: UNetModel.input_blocks[0] Conv2d(4,320)  tinyfusers/vision/unet.py:13. */
 int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out, int NI,
                                 int Cin, int H, int W, int Cout, int out_pixel_stride, void* stream);
+/* Same, and additionally leaves the GroupNorm statistics of the fp16 output (layout of tf_conv2d_nhwc_gn_f16: slot = 32
+ * consecutive pixels of one image, unit = gn_unit channels), so the first ResBlock's GroupNorm is one launch. H*W % 32 == 0. */
+int tf_conv3x3_smallcin_gn_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out, int NI,
+                                   int Cin, int H, int W, int Cout, int out_pixel_stride, void* gn_stats, int gn_unit,
+                                   void* stream);
 /* nearest x2. Replaces: Upsample.__call__ broadcast/reshape  tinyfusers/vision/unet.py:81-83. */
 int tf_upsample_nearest2x_nhwc_f16(const void* x, int x_pixel_stride, void* out, int out_pixel_stride, int NI,
                                    int H, int W, int C, void* stream);

@@ -60,10 +60,12 @@ __global__ void gemv_kernel(const float* __restrict__ x, const __half* __restric
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                        __half* __restrict__ out, int NI, int H, int W_, int Cout, int out_stride, int x_images) {
+                        __half* __restrict__ out, int NI, int H, int W_, int Cout, int out_stride, int x_images,
+                        float2* __restrict__ gn_stats, int gn_unit) {
   tf::pdl_trigger();
-  extern __shared__ float ws[];  // [Cout][CIN*9] then [Cout] bias
+  extern __shared__ float ws[];  // [Cout][CIN*9] then [Cout] bias, then [Cout] float2 channel sums (statistics)
   float* bs = ws + Cout * CIN * 9;
+  float2* csum = reinterpret_cast<float2*>(bs + Cout);
   // weights do not depend on the producer kernels: stage them (128-bit loads) before the dependency wait
   {
     const int n4 = (Cout * CIN * 9) >> 2;   // Cout % 8 == 0 -> a whole number of float4
@@ -77,7 +79,7 @@ conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long npix = (long)NI * H * W_;
   const long pix = (long)blockIdx.x * 32 + lane;
-  if (pix >= npix) return;
+  if (pix >= npix && gn_stats == nullptr) return;   // with statistics H*W % 32 == 0 (host-checked): no partial block
   const int xo = (int)(pix % W_);
   const int yo = (int)((pix / W_) % H);
   const int n = (int)(pix / ((long)W_ * H)) % x_images;
@@ -107,6 +109,30 @@ conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w
 #pragma unroll
     for (int j = 0; j < 4; ++j) pk.h2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
     *reinterpret_cast<uint4*>(out + (size_t)pix * out_stride + g * 8) = pk.v;
+    if (gn_stats) {
+      // GroupNorm statistics of the OUTPUT, same layout as the GEMM epilogue's: this block's 32 pixels are one slot;
+      // per channel {sum, sumsq} of the rounded fp16 values over the 32 lanes (fixed xor-shuffle order)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(pk.h2[j]);
+        const float s0 = tf::warp_sum(f.x), q0 = tf::warp_sum(f.x * f.x);
+        const float s1 = tf::warp_sum(f.y), q1 = tf::warp_sum(f.y * f.y);
+        if (lane == 0) {
+          csum[g * 8 + 2 * j] = make_float2(s0, q0);
+          csum[g * 8 + 2 * j + 1] = make_float2(s1, q1);
+        }
+      }
+    }
+  }
+  if (gn_stats) {
+    __syncthreads();
+    const int units = Cout / gn_unit;
+    const long slot_global = blockIdx.x;   // (image, slot) flattened: H*W % 32 == 0
+    for (int u = threadIdx.x; u < units; u += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      for (int k = 0; k < gn_unit; ++k) { a += csum[u * gn_unit + k].x; b += csum[u * gn_unit + k].y; }
+      gn_stats[slot_global * units + u] = make_float2(a, b);
+    }
   }
 }
 
@@ -244,26 +270,41 @@ extern "C" int tf_gemv_f16w(const float* x, const void* W, const float* bias, co
   return TF_OK;
 }
 
-extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out,
-                                           int NI, int Cin, int H, int W, int Cout, int out_pixel_stride,
-                                           void* stream) {
+static int smallcin_impl(const float* x, int x_images, const float* w, const float* bias, void* out, int NI, int Cin, int H,
+                         int W, int Cout, int out_pixel_stride, void* gn_stats, int gn_unit, void* stream) {
   TF_CHECK_ARG(x && w && out && x_images > 0, "tf_conv3x3_smallcin_f32nchw: null pointer");
   TF_CHECK_ARG(Cin == 4, "tf_conv3x3_smallcin_f32nchw: only Cin == 4 is built (got %d)", Cin);
-  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && (Cout * Cin * 9 + Cout) * 4 <= 100 * 1024,
+  const size_t smem = (size_t)(Cout * Cin * 9 + Cout) * sizeof(float) + (gn_stats ? (size_t)Cout * sizeof(float2) : 0);
+  TF_CHECK_ARG(Cout % 8 == 0 && out_pixel_stride % 8 == 0 && smem <= 100 * 1024,
                "tf_conv3x3_smallcin_f32nchw: bad Cout %d", Cout);
+  if (gn_stats)
+    TF_CHECK_ARG(gn_unit > 0 && Cout % gn_unit == 0 && (H * W) % 32 == 0,
+                 "tf_conv3x3_smallcin_gn_f32nchw: statistics need Cout %% unit == 0 and H*W %% 32 == 0");
   const long npix = (long)NI * H * W;
-  const size_t smem = (size_t)(Cout * Cin * 9 + Cout) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     TF_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
   TF_CHECK_ARG(((uintptr_t)w & 15) == 0, "tf_conv3x3_smallcin_f32nchw: weights must be 16-byte aligned");
-  TF_LAUNCH((conv3x3_smallcin_kernel<4>), (unsigned)((npix + 31) / 32), 256, smem, (cudaStream_t)stream, 
-      x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride, x_images);
+  TF_LAUNCH((conv3x3_smallcin_kernel<4>), (unsigned)((npix + 31) / 32), 256, smem, (cudaStream_t)stream,
+            x, w, bias, (__half*)out, NI, H, W, Cout, out_pixel_stride, x_images, (float2*)gn_stats, gn_unit);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
+}
+
+extern "C" int tf_conv3x3_smallcin_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out,
+                                           int NI, int Cin, int H, int W, int Cout, int out_pixel_stride,
+                                           void* stream) {
+  return smallcin_impl(x, x_images, w, bias, out, NI, Cin, H, W, Cout, out_pixel_stride, nullptr, 0, stream);
+}
+
+extern "C" int tf_conv3x3_smallcin_gn_f32nchw(const float* x, int x_images, const float* w, const float* bias, void* out,
+                                              int NI, int Cin, int H, int W, int Cout, int out_pixel_stride,
+                                              void* gn_stats, int gn_unit, void* stream) {
+  TF_CHECK_ARG(gn_stats != nullptr, "tf_conv3x3_smallcin_gn_f32nchw: null statistics buffer");
+  return smallcin_impl(x, x_images, w, bias, out, NI, Cin, H, W, Cout, out_pixel_stride, gn_stats, gn_unit, stream);
 }
 
 extern "C" int tf_upsample_nearest2x_nhwc_f16(const void* x, int x_pixel_stride, void* out, int out_pixel_stride,

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "tf_timestep_embedding_f32": (c_int, [_P, _P, c_int, c_float, _P, _P]),
     "tf_gemv_f16w": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "tf_conv3x3_smallcin_f32nchw": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "tf_conv3x3_smallcin_gn_f32nchw": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "tf_upsample_nearest2x_nhwc_f16": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "tf_nchw_to_nhwc_f16": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),

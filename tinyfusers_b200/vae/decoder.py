@@ -49,7 +49,7 @@ class Decoder:
     def _run(self, ctx, latent_ptr, n, H, W, img_ptr):
         ar = ctx.arena
         ar.reset()
-        x = ctx.new_act(n, H, W, 512)      # conv_in output: no producer statistics -> 3-launch GroupNorm
+        x = ctx.new_act(n, H, W, 512, gn=True, gn_unit=16)      # conv_in emits the first GroupNorm's statistics too
         self.conv_in._run_smallcin(ctx, _F32View(latent_ptr, (n, 4, H, W)), n, x)
         h = ctx.new_act(n, H, W, 512, gn=True, gn_unit=16)
         self.mid._run(ctx, x, h)

@@ -242,8 +242,8 @@ class UNetModel:
         # persistent slice views; each gets its own statistics buffer, the concatenation lists both parts
         svs = [cats[nb - 1 - i].channels(cats[nb - 1 - i].c - in_ch[i], cats[nb - 1 - i].c) for i in range(nb)]
         xvs = [cats[j].channels(0, cats[j].c - in_ch[nb - 1 - j]) for j in range(nb)]
-        for i in range(1, nb):
-            ctx.attach_gn(svs[i])       # svs[0] is written by conv_in (no statistics): its consumers take the 3-launch path
+        for i in range(nb):
+            ctx.attach_gn(svs[i])       # svs[0] is written by conv_in, which emits its statistics too
         for j in range(nb):
             ctx.attach_gn(xvs[j])
             xp, sp = xvs[j].gn, svs[nb - 1 - j].gn
