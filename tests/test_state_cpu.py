@@ -114,3 +114,16 @@ def test_sampler_schedule_matches_reference_loop(oracle):
 def test_flop_count_matches_survey(oracle):
     assert abs(oracle.unet_step_flops(2, 64, 64) / 1e9 - 1606.5) < 0.1
     assert abs(oracle.unet_step_flops(8, 96, 96) / 1e9 - 17184.6) < 1.0
+
+
+def test_reference_import_paths():
+    """`tinyfusers.Tensor` (reference __init__.py:1) and `tinyfusers.tensor.tensor.Tensor` (what the model files import)."""
+    import tinyfusers_b200
+    from tinyfusers_b200.storage.tensor import Tensor as A
+    from tinyfusers_b200.tensor.tensor import Tensor as B
+    assert tinyfusers_b200.Tensor is A is B
+    assert Tensor_sequential_ok(A)
+
+
+def Tensor_sequential_ok(T):
+    return T.sequential([lambda x: x + 1, lambda x: x * 2], 3) == 8

@@ -31,3 +31,12 @@ def set_layernorm_strided(flag: bool):
 
 def get_layernorm_strided() -> bool:
     return _LN_STRIDED
+
+
+def __getattr__(name):
+    # `tinyfusers.Tensor` (reference: tinyfusers/__init__.py:1), resolved lazily: importing the package itself must not
+    # need the built shared library (the build script lives inside the package)
+    if name == "Tensor":
+        from .storage.tensor import Tensor
+        return Tensor
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
