@@ -38,16 +38,25 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int HW, int Cs, in
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
   const __half* base = x + (size_t)n * HW * x_stride + v * 8;
-  for (int p = p0 + pl; p < p1; p += npl) {
+  auto acc = [&](const uint4& vv) {
     tf::Pack16 pk;
-    pk.v = *reinterpret_cast<const uint4*>(base + (size_t)p * x_stride);
+    pk.v = vv;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 f = __half22float2(pk.h2[j]);
       s[2 * j] += f.x; q[2 * j] += f.x * f.x;
       s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
     }
+  };
+  int p = p0 + pl;
+  for (; p + 3 * npl < p1; p += 4 * npl) {   // four independent loads in flight per thread; accumulation order unchanged
+    uint4 v4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v4[k] = *reinterpret_cast<const uint4*>(base + (size_t)(p + k * npl) * x_stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc(v4[k]);
   }
+  for (; p < p1; p += npl) acc(*reinterpret_cast<const uint4*>(base + (size_t)p * x_stride));
   float* ps = gsm;
   float* pq = gsm + npl * Cs;
   float* cs = gsm + 2 * npl * Cs;
@@ -126,10 +135,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, in
   const int p1 = min(HW, p0 + pix_per_block);
   const __half* xin = x + (size_t)n * HW * x_stride + v * 8;
   __half* o = out + (size_t)n * HW * out_stride + c0;
-  for (int p = p0 + pl; p < p1; p += npl) {
-    tf::Pack16 pk;
-    pk.v = *reinterpret_cast<const uint4*>(xin + (size_t)p * x_stride);
-    tf::Pack16 r;
+  auto apply = [&](const uint4& vv, int p) {
+    tf::Pack16 pk, r;
+    pk.v = vv;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 f = __half22float2(pk.h2[j]);
@@ -139,7 +147,16 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int HW, int Cs, in
       r.h2[j] = __floats2half2_rn(y0, y1);
     }
     *reinterpret_cast<uint4*>(o + (size_t)p * out_stride) = r.v;
+  };
+  int p = p0 + pl;
+  for (; p + 3 * npl < p1; p += 4 * npl) {   // long pixel chunks (VAE-size images): four independent loads in flight per thread
+    uint4 v4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v4[k] = *reinterpret_cast<const uint4*>(xin + (size_t)(p + k * npl) * x_stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) apply(v4[k], p + k * npl);
   }
+  for (; p < p1; p += npl) apply(*reinterpret_cast<const uint4*>(xin + (size_t)p * x_stride), p);
 }
 
 // ------------------------------------------------------------------------------------------------
