@@ -1,0 +1,54 @@
+"""tf_attention_v_f16: attention with V in its natural (keys, head dim padded to 64) layout - the MN-major B operand of
+O += P V - against torch on the same random inputs, at the UNet's head sizes (40 / 80 / 160), CLIP's (64, causal) and the
+C4 / C5 grid sizes that take the 3-CTA-per-SM variant. Tolerance: max|a-b| / max|b| <= 3e-3 (fp16 P and V)."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(B, NH, Tq, Tk, d, causal=False, seed=0):
+    from tinyfusers_b200.native.b200.ops import b200
+    b200.init(0)
+    dp = (d + 15) // 16 * 16
+    dvp = (d + 63) // 64 * 64
+    Tkp = (Tk + 7) // 8 * 8
+    g = torch.Generator().manual_seed(seed + Tq + d)
+    q = torch.randn(B, Tq, NH, d, generator=g)
+    k = torch.randn(B, Tk, NH, d, generator=g)
+    v = torch.randn(B, Tk, NH, d, generator=g)
+    Q = torch.zeros(B, Tq, NH, dp, dtype=torch.half, device="cuda"); Q[..., :d] = q.cuda()
+    K = torch.zeros(B, Tkp, NH, dp, dtype=torch.half, device="cuda"); K[:, :Tk, :, :d] = k.cuda()
+    # pad key rows / pad head columns of V must be finite (rows are masked, columns must be ZERO: they host the row sums)
+    V = torch.zeros(B, Tkp, NH, dvp, dtype=torch.half, device="cuda"); V[:, :Tk, :, :d] = v.cuda()
+    out = torch.zeros(B, Tq, NH, d, dtype=torch.half, device="cuda")
+    st = b200.tf_attention_v_f16(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, V.data_ptr(), NH * dvp, out.data_ptr(),
+                                 Tq * NH * d, d, NH * d, B, NH, Tq, Tk, Tkp, d, dp, dvp, 1.0 / math.sqrt(d), 1 if causal else 0,
+                                 torch.cuda.current_stream().cuda_stream)
+    b200.check(st, "tf_attention_v_f16")
+    heads = lambda t: t.cuda().half().float().permute(0, 2, 1, 3)
+    ref = torch.nn.functional.scaled_dot_product_attention(heads(q), heads(k), heads(v), is_causal=causal)
+    return out.float().permute(0, 2, 1, 3), ref
+
+
+@pytest.mark.parametrize("B,NH,Tq,Tk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160),
+                                          (2, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (2, 8, 256, 77, 160),
+                                          (1, 8, 576, 576, 80), (1, 3, 200, 333, 64)])
+def test_natural_v_matches_torch(B, NH, Tq, Tk, d):
+    out, ref = _run(B, NH, Tq, Tk, d)
+    assert rel_err(out, ref) < 3e-3
+
+
+def test_natural_v_three_ctas_per_sm_variant():
+    out, ref = _run(8, 8, 4096, 4096, 40)     # 2048 CTAs -> 64-key blocks, 3 CTAs / SM, L overlaid on O's pad columns
+    assert rel_err(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("T,NH,d", [(77, 12, 64), (200, 4, 64), (640, 2, 40)])
+def test_natural_v_causal(T, NH, d):
+    out, ref = _run(1, NH, T, T, d, causal=True)
+    assert rel_err(out, ref) < 3e-3

@@ -25,6 +25,10 @@ def _pad16(d):
     return (d + 15) // 16 * 16
 
 
+def _pad64(d):
+    return (d + 63) // 64 * 64
+
+
 class CrossAttention:
     def __init__(self, query_dim, context_dim, n_heads, d_head):
         self.to_q = Linear(query_dim, n_heads * d_head, bias=False)
@@ -35,14 +39,17 @@ class CrossAttention:
         self.to_out = [Linear(n_heads * d_head, query_dim)]
 
     def _packed(self):
+        """wq, wk: each head's rows zero-padded to dp (multiple of 16: the QK^T slabs); wv: to dvp (multiple of 64: V is the
+        MN-major operand of P.V, read in its natural layout); wkv = [wk ; wv]; wqkv = [wq ; wk ; wv] (self-attention)."""
         nh, d = self.num_heads, self.head_size
-        dp = _pad16(d)
+        dp, dvp = _pad16(d), _pad64(d)
         def build():
             wq = packing.head_pad(self.to_q.weight, nh, d, dp)
             wk = packing.head_pad(self.to_k.weight, nh, d, dp)
-            wv = packing.head_pad(self.to_v.weight, nh, d, dp)
-            wqk = torch.cat((wq, wk), dim=0).contiguous() if wq.shape[1] == wk.shape[1] else None
-            return wq, wk, wv, wqk
+            wv = packing.head_pad(self.to_v.weight, nh, d, dvp)
+            wkv = torch.cat((wk, wv), dim=0).contiguous()
+            wqkv = torch.cat((wq, wk, wv), dim=0).contiguous() if wq.shape[1] == wk.shape[1] else None
+            return wq, wk, wv, wkv, wqkv
         return packing.cached(self, "attn", (self.to_q.weight, self.to_k.weight, self.to_v.weight), build)
 
     def __call__(self, x, context=None):
@@ -59,21 +66,18 @@ class CrossAttention:
     # h_ptr (B*T, C) is updated:  h <- to_out(attention(...)) (+ h if residual);  xn_ptr = normalised input
     def _run(self, ctx, xn_ptr, B, T, C, h_ptr, context=None, residual=True):
         nh, d = self.num_heads, self.head_size
-        dp = _pad16(d)
-        wq, wk, wv, wqk = self._packed()
+        dp, dvp = _pad16(d), _pad64(d)
+        wq, wk, wv, wkv, wqkv = self._packed()
         mark = ctx.arena.mark()
         M = B * T
         if context is None:
-            # self-attention: one GEMM for [Q | K], one swapped GEMM for V^T
-            qk_ptr = ctx.arena.alloc(2 * M * 2 * nh * dp)
-            ctx.gemm(xn_ptr, C, M, C, wqk.data_ptr(), 2 * nh * dp, qk_ptr, 2 * nh * dp)
-            if T % 8 != 0:
-                raise RuntimeError(f"tinyfusers_b200 self-attention: {T} tokens per image; the B200 kernel needs a "
-                                   "multiple of 8 (latent height*width at every UNet level)")
-            vt_ptr = ctx.arena.alloc(2 * nh * dp * M)
-            ctx.gemm(wv.data_ptr(), C, nh * dp, C, xn_ptr, M, vt_ptr, M, ldw=C, w_static=False)
-            q_ptr, ldq, k_ptr, ldk = qk_ptr, 2 * nh * dp, qk_ptr + 2 * nh * dp, 2 * nh * dp
-            Tk, Tkp, ldvt = T, T, M
+            # self-attention: ONE GEMM for [Q | K | V]; the attention kernel reads V in this natural layout
+            n_all = 2 * nh * dp + nh * dvp
+            qkv_ptr = ctx.arena.alloc(2 * M * n_all)
+            ctx.gemm(xn_ptr, C, M, C, wqkv.data_ptr(), n_all, qkv_ptr, n_all)
+            q_ptr, k_ptr, v_ptr = qkv_ptr, qkv_ptr + 2 * nh * dp, qkv_ptr + 4 * nh * dp
+            ldq = ldk = ldv = n_all
+            Tk, Tkp = T, T
         else:
             Tkp, Cc = context.h, context.c
             Tk = context.valid if context.valid is not None else context.h
@@ -83,16 +87,14 @@ class CrossAttention:
             ldq = nh * dp
             pre = ctx.ctx_kv.get(id(self)) if ctx.ctx_kv else None
             if pre is not None:      # projected once per step for all blocks (UNetModel._ctx_kv_pack)
-                k_ptr, ldk, vt_ptr, ldvt = pre
+                k_ptr, ldk, v_ptr, ldv = pre
             else:
-                k_ptr = ctx.arena.alloc(2 * Mc * nh * dp)
-                ctx.gemm(context.ptr, context.stride, Mc, Cc, wk.data_ptr(), nh * dp, k_ptr, nh * dp)
-                vt_ptr = ctx.arena.alloc(2 * nh * dp * Mc)
-                ctx.gemm(wv.data_ptr(), Cc, nh * dp, Cc, context.ptr, Mc, vt_ptr, Mc, ldw=context.stride,
-                         w_static=False)
-                ldk, ldvt = nh * dp, Mc
+                n_kv = nh * (dp + dvp)
+                kv_ptr = ctx.arena.alloc(2 * Mc * n_kv)
+                ctx.gemm(context.ptr, context.stride, Mc, Cc, wkv.data_ptr(), n_kv, kv_ptr, n_kv)
+                k_ptr, v_ptr, ldk, ldv = kv_ptr, kv_ptr + 2 * nh * dp, n_kv, n_kv
         a_ptr = ctx.arena.alloc(2 * M * nh * d)
-        ctx.attention(q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, a_ptr, B, nh, T, Tk, Tkp, d, dp, head_major=ctx.quirks)
+        ctx.attention_v(q_ptr, ldq, k_ptr, ldk, v_ptr, ldv, a_ptr, B, nh, T, Tk, Tkp, d, dp, dvp, head_major=ctx.quirks)
         wo, bo = self.to_out[0]._packed()
         ctx.gemm(a_ptr, nh * d, M, nh * d, wo.data_ptr(), wo.shape[0], h_ptr, wo.shape[0],
                  bias=bo.data_ptr() if bo is not None else None, residual_ptr=h_ptr if residual else None,
@@ -244,10 +246,8 @@ class AttnBlock:
 
 class CLIPAttention:
     """CLIP self-attention (reference: tinyfusers/attention/attention.py:78-99): 12 heads x 64, q/k/v/out Linears with
-    bias, additive causal mask, heads merged canonically. Fast path: ONE GEMM for [q | k] (bias fused), V^T from a
-    swapped-operand GEMM, causal tcgen05 flash attention, out_proj GEMM (+bias +residual). The V bias never touches
-    the attention: softmax rows sum to 1, so P (V + 1 b_v^T) = P V + b_v^T, and b_v is folded into the out_proj bias
-    (b_o + W_o b_v) when the weights are packed."""
+    bias, additive causal mask, heads merged canonically. Fast path: ONE GEMM for [q | k | v] (bias fused), causal
+    tcgen05 flash attention reading V in that natural layout, out_proj GEMM (+bias +residual)."""
 
     def __init__(self):
         self.embed_dim = 768
@@ -261,12 +261,11 @@ class CLIPAttention:
     def _packed(self):
         mods = (self.q_proj, self.k_proj, self.v_proj, self.out_proj)
         def build():
-            wqk = torch.cat((self.q_proj.weight, self.k_proj.weight), dim=0).to(F16).contiguous()
-            bqk = torch.cat((packing.f32(self.q_proj.bias), packing.f32(self.k_proj.bias))).contiguous()
-            wv = self.v_proj.weight.to(F16).contiguous()
+            wqkv = torch.cat((self.q_proj.weight, self.k_proj.weight, self.v_proj.weight), dim=0).to(F16).contiguous()
+            bqkv = torch.cat([packing.f32(m.bias) for m in (self.q_proj, self.k_proj, self.v_proj)]).contiguous()
             wo = self.out_proj.weight.to(F16).contiguous()
-            bo = (packing.f32(self.out_proj.bias) + packing.f32(self.out_proj.weight) @ packing.f32(self.v_proj.bias)).contiguous()
-            return wqk, bqk, wv, wo, bo
+            bo = packing.f32(self.out_proj.bias)
+            return wqkv, bqkv, wo, bo
         return packing.cached(self, "clipattn", tuple(m.weight for m in mods) + tuple(m.bias for m in mods), build)
 
     def __call__(self, hidden_states, causal_attention_mask=None):
@@ -286,16 +285,15 @@ class CLIPAttention:
             outs.append(h[:T].to(F32))
         return torch.stack(outs)
 
-    # xn: (Tp, E) fp16 normalised input whose rows >= T are zero; h (Tp, E): h <- out_proj(attn) (+ h)
+    # xn: (Tp, E) fp16 normalised input; h (Tp, E): h <- out_proj(attn) (+ h)
     def _run(self, ctx, xn_ptr, h_ptr, T, Tp, residual=True):
         E, NH, D = self.embed_dim, self.num_heads, self.head_dim
-        wqk, bqk, wv, wo, bo = self._packed()
+        wqkv, bqkv, wo, bo = self._packed()
         mark = ctx.arena.mark()
-        qk = ctx.arena.alloc(2 * Tp * 2 * E)
-        ctx.gemm(xn_ptr, E, T, E, wqk.data_ptr(), 2 * E, qk, 2 * E, bias=bqk.data_ptr())
-        vt = ctx.arena.alloc(2 * E * Tp)
-        ctx.gemm(wv.data_ptr(), E, E, E, xn_ptr, Tp, vt, Tp, ldw=E, w_static=False)   # V^T (E, Tp): pad columns are exact zeros
+        qkv = ctx.arena.alloc(2 * Tp * 3 * E)
+        ctx.gemm(xn_ptr, E, T, E, wqkv.data_ptr(), 3 * E, qkv, 3 * E, bias=bqkv.data_ptr())     # [q | k | v], bias fused
         a = ctx.arena.alloc(2 * Tp * E)
-        ctx.attention_causal(qk, 2 * E, qk + 2 * E, 2 * E, vt, Tp, a, 1, NH, T, Tp, D, D)
+        ctx.attention_v(qkv, 3 * E, qkv + 2 * E, 3 * E, qkv + 4 * E, 3 * E, a, 1, NH, T, T, T, D, D, D, head_major=False,
+                        causal=True)
         ctx.gemm(a, E, T, E, wo.data_ptr(), E, h_ptr, E, bias=bo.data_ptr(), residual_ptr=h_ptr if residual else None, ldr=E)
         ctx.arena.release(mark)

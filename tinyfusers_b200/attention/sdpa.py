@@ -1,8 +1,8 @@
 """scaled_dot_product_attention with the reference's signature (reference: tinyfusers/attention/sdpa.py:53-77).
 
 q (B,NH,Tq,HS), k/v (B,NH,Tk,HS) -> (B,NH,Tq,HS) fp32. One fused tcgen05 kernel (tf_attention_f16) instead of
-cuBLAS QK^T -> HBM scores -> softmax_kernel -> cuBLAS PV. The operand re-layout below (head padding,
-V transpose) is container-level data movement for this stand-alone entry point only; inside the UNet
+cuBLAS QK^T -> HBM scores -> softmax_kernel -> cuBLAS PV. The operand re-layout below (head padding)
+is container-level data movement for this stand-alone entry point only; inside the UNet
 the projection GEMMs write these layouts directly."""
 import torch
 
@@ -31,22 +31,16 @@ def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
         raise RuntimeError(f"tinyfusers_b200 scaled_dot_product_attention: head size {HS} must be a multiple of 8 "
                            "and equal for q/k/v")
     dp = (HS + 15) // 16 * 16
+    dvp = (HS + 63) // 64 * 64
     Tkp = (Tk + 7) // 8 * 8
     dev = q_cp.device
     Q = torch.zeros((B, Tq, NH, dp), dtype=F16, device=dev)
     Q[..., :HS] = q_cp.permute(0, 2, 1, 3)
     K = torch.zeros((B, Tkp, NH, dp), dtype=F16, device=dev)
     K[:, :Tk, :, :HS] = k_cp.permute(0, 2, 1, 3)
-    Vt = torch.zeros((NH, dp, B, Tkp), dtype=F16, device=dev)
-    Vt[:, :HS, :, :Tk] = v_cp.permute(1, 3, 0, 2)
+    V = torch.zeros((B, Tkp, NH, dvp), dtype=F16, device=dev)     # natural layout, head dim zero-padded to 64
+    V[:, :Tk, :, :HS] = v_cp.permute(0, 2, 1, 3)
     out = torch.empty((B, NH, Tq, HS), dtype=F16, device=dev)
-    if causal:
-        # the causal entry point writes the canonical (B, T, NH*HS) merge; permute back to the reference's (B, NH, T, HS)
-        merged = torch.empty((B, Tq, NH, HS), dtype=F16, device=dev)
-        for b in range(B):
-            ctx.attention_causal(Q[b].data_ptr(), NH * dp, K[b].data_ptr(), NH * dp, Vt[:, :, b].contiguous().data_ptr(), Tkp,
-                                 merged[b].data_ptr(), 1, NH, Tq, Tkp, HS, dp)
-        return merged.permute(0, 2, 1, 3).to(F32)
-    ctx.attention(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, Vt.data_ptr(), B * Tkp, out.data_ptr(), B, NH, Tq, Tk,
-                  Tkp, HS, dp, head_major=True)
+    ctx.attention_v(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, V.data_ptr(), NH * dvp, out.data_ptr(), B, NH, Tq, Tk, Tkp,
+                    HS, dp, dvp, head_major=True, causal=causal)
     return out.to(F32)

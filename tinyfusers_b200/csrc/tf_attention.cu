@@ -32,6 +32,9 @@ constexpr int BQ = 128;
 
 struct AttnParams {
   int B, NH, Tq, Tk, Tk_pad, d, dp;
+  int dov;      // O columns in TMEM: dp (V^T operand), or the V head dim padded to 64 (natural-layout V operand)
+  int l_off;    // first of the 16 L (= P . 1) columns, relative to O: dov, or dov - 16 when O's zero pad columns can host them
+  int ol_cols;  // columns spanned by O and L together
   int nkv;      // key blocks
   int stages;   // K/V ring depth
   int causal;   // 1: query t only sees keys <= t (CLIP's additive triu(-inf, k=1) mask, vae/encoder.py:79)
@@ -65,7 +68,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw32_kmajor(uint32_t smem_addr) {
 // OCC = CTAs per SM the register allocation is bounded for (3: 64-key blocks, head dim <= 48, long sequences: three
 // resident CTAs keep the MUFU pipe ~85 % busy instead of ~57 %, and 444 slots swallow the 512-CTA grid of a
 // 4096-token SD self-attention in one wave plus a short tail)
-template <int BN, int OCC>
+// MN-major operand (rows = K index, 128 contiguous bytes = 64 elements of the M/N index), 128-byte swizzle:
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp) - 8-row groups are
+// SBO = 1024 B apart, 64-element column blocks LBO apart. This is V in its natural (keys, head dim) layout as the
+// B operand of O += P V: no transposed copy of V has to be produced by anyone.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// VNAT: V is read in its natural layout (B*Tk_pad rows, head h at columns [h*dov, (h+1)*dov), dov = head dim padded to
+// 64 with zero columns) instead of transposed.
+template <int BN, int OCC, bool VNAT>
 __global__ void __launch_bounds__(kAttThreads, OCC)
 tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -79,12 +98,13 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int ST = p.stages;
 
   const uint32_t q_bytes = BQ * p.dp * 2;
-  const uint32_t k_bytes = BN * p.dp * 2;  // K tile and V^T tile have the same size
+  const uint32_t k_bytes = BN * p.dp * 2;
+  const uint32_t v_bytes = BN * p.dov * 2;  // V^T tile: dp rows x BN keys; natural V tile: BN keys x dov columns
   const uint32_t p_bytes = BQ * BN * 2;
   const uint32_t smem_q = smem_base;
   const uint32_t smem_k = smem_q + q_bytes;
   const uint32_t smem_v = smem_k + ST * k_bytes;
-  const uint32_t smem_p = smem_v + ST * k_bytes;
+  const uint32_t smem_p = smem_v + ST * v_bytes;
   const uint32_t smem_ones = smem_p + p_bytes;   // 16 x 64 fp16 ones (one 128B-swizzle atom): the row sums come from the MMA
   const uint32_t bar_base = smem_ones + 2048;
   // barriers
@@ -131,7 +151,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tf::pdl_wait();
   const uint32_t tmem_s0 = tmem_base;            // S: columns [0,BN)
   const uint32_t tmem_o = tmem_base + BN;        // O: dp columns, then 16 columns of L = P . 1 (the softmax denominator)
-  const uint32_t tmem_l = tmem_o + p.dp;
+  const uint32_t tmem_l = tmem_o + p.l_off;
 
   const int nkv = p.nkv;
   const int slabs = p.dp / 16;
@@ -145,19 +165,24 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int s = j % ST;
         const uint32_t u = j / ST;
         tf::mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
-        tf::mbar_expect_tx(kv_full(s), 2 * k_bytes);
+        tf::mbar_expect_tx(kv_full(s), k_bytes + v_bytes);
         const int key0 = b * p.Tk_pad + j * BN;
         tf::tma_load_3d(smem_k + s * k_bytes, &tmK, kv_full(s), 0, key0, h * slabs);
+        if (VNAT) {   // one (BN keys x 64 columns) box per 64-column block of the head
+          for (int nb = 0; nb < p.dov / 64; ++nb)
+            tf::tma_load_2d(smem_v + s * v_bytes + nb * (BN * 128), &tmV, kv_full(s), h * p.dov + nb * 64, key0);
+        } else {
 #pragma unroll
-        for (int i = 0; i < BN / 64; ++i)
-          tf::tma_load_2d(smem_v + s * k_bytes + i * (p.dp * 128), &tmV, kv_full(s), key0 + 64 * i, h * p.dp);
+          for (int i = 0; i < BN / 64; ++i)
+            tf::tma_load_2d(smem_v + s * v_bytes + i * (p.dp * 128), &tmV, kv_full(s), key0 + 64 * i, h * p.dp);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_s = tf::umma_idesc_f16(BQ, BN);
-      const uint32_t idesc_o = tf::umma_idesc_f16(BQ, p.dp);
+      const uint32_t idesc_o = tf::umma_idesc_f16(BQ, p.dov) | (VNAT ? (1u << 16) : 0u);   // bit 16: B is MN-major
       const uint32_t idesc_l = tf::umma_idesc_f16(BQ, 16);
       auto issue_s = [&](int j) {
         const int s = j % ST;
@@ -179,12 +204,13 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tf::mbar_wait(p_full, (uint32_t)j & 1u);
         tf::tcgen05_fence_after();
         const int s = j % ST;
-        const uint32_t vbase = smem_v + s * k_bytes;
+        const uint32_t vbase = smem_v + s * v_bytes;
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           const uint32_t atom = k >> 2, sub = k & 3;
-          tf::umma_f16_ss(tmem_o, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub,
-                          tf::umma_desc_sw128_kmajor(vbase + atom * (p.dp * 128)) + 2u * sub, idesc_o,
+          const uint64_t vdesc = VNAT ? umma_desc_sw128_mnmajor(vbase + k * 2048u, BN * 128u)   // keys 16k .. 16k+15
+                                      : tf::umma_desc_sw128_kmajor(vbase + atom * (p.dp * 128)) + 2u * sub;
+          tf::umma_f16_ss(tmem_o, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub, vdesc, idesc_o,
                           (j > 0 || k > 0) ? 1u : 0u);
           // L += P . ones: the denominator accumulates from the SAME fp16-rounded P the numerator uses
           tf::umma_f16_ss(tmem_l, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub,
@@ -283,7 +309,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       // rescale the running output if any row of this warp moved its max
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        for (int c = 0; c < p.dp + 16; c += 16) {   // O and the L columns
+        for (int c = 0; c < p.ol_cols; c += 16) {   // O and the L columns
           uint32_t o[16];
           tf::tmem_ld_x16(tmem_o + lane_field + c, o);
           tf::tmem_ld_wait();
@@ -311,7 +337,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     const int t = qt * BQ + row;
     __half* orow = p.out + (long long)b * p.osb + (long long)h * p.osh + (long long)t * p.ost;
-    for (int c = 0; c < p.dp; c += 16) {
+    for (int c = 0; c < p.d; c += 16) {
       uint32_t o[16];
       tf::tmem_ld_x16(tmem_o + lane_field + c, o);
       tf::tmem_ld_wait();
@@ -357,19 +383,31 @@ extern "C" int tf_attention_set_tuning(int force_bn) {
   return TF_OK;
 }
 
+// vnat == 0: `vt` is V transposed, (NH*dp, ldvt >= B*Tk_pad). vnat == 1: `vt` is V in its natural layout,
+// (B*Tk_pad, ldvt >= NH*dvp), head h at columns [h*dvp, (h+1)*dvp), dvp % 64 == 0 (zero pad columns).
 static int attention_impl(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
                           long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
-                          int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, int causal, void* stream_) {
+                          int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, int causal, int vnat, int dvp,
+                          void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int dov = vnat ? dvp : dp;   // O columns
+  // V's pad columns are exact zeros, so the PV MMA adds exact zeros to O's pad columns: when at least 16 of them lie beyond
+  // the last 16-column group that holds real head-dim elements, the L = P . 1 accumulator lives there (issued after PV in
+  // every k-step, so the first, non-accumulating PV MMA cannot wipe it) and TMEM needs BN + dov columns instead of + 16 more
+  const int d16 = (d + 15) / 16 * 16;
+  const int l_off = (vnat && dov - 16 >= d16) ? dov - 16 : dov;
+  const int ol_cols = l_off + 16 > dov ? l_off + 16 : dov;
   TF_CHECK_ARG(q && k && vt && out, "tf_attention_f16: null pointer");
   TF_CHECK_ARG(B > 0 && NH > 0 && Tq > 0 && Tk > 0 && Tk_pad >= Tk, "tf_attention_f16: bad dims");
   TF_CHECK_ARG(dp % 16 == 0 && dp >= 16 && dp <= 256 && d <= dp && d % 8 == 0,
                "tf_attention_f16: head dim d=%d (padded %d) unsupported: need d %% 8 == 0, dp %% 16 == 0, dp <= 256", d, dp);
   // Tk_pad % 8: batch b's V^T columns start at b*Tk_pad and a TMA box must start on a 16-byte boundary
-  TF_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && Tk_pad % 8 == 0,
+  TF_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && (vnat || Tk_pad % 8 == 0),
                "tf_attention_f16: leading dims and Tk_pad must be multiples of 8 (ldq=%d ldk=%d ldvt=%d Tk_pad=%d)", ldq,
                ldk, ldvt, Tk_pad);
-  TF_CHECK_ARG(ldq >= NH * dp && ldk >= NH * dp && ldvt >= B * Tk_pad, "tf_attention_f16: leading dims too small");
+  TF_CHECK_ARG(ldq >= NH * dp && ldk >= NH * dp && ldvt >= (vnat ? NH * dvp : B * Tk_pad),
+               "tf_attention_f16: leading dims too small");
+  if (vnat) TF_CHECK_ARG(dvp % 64 == 0 && dvp >= d && dvp <= 256, "tf_attention_v_f16: V head dim must be padded to a multiple of 64 (<= 256), got %d", dvp);
   TF_CHECK_ARG(out_stride_t % 8 == 0 && out_stride_h % 8 == 0 && out_stride_b % 8 == 0,
                "tf_attention_f16: output strides must be multiples of 8");
   TF_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)vt & 15) == 0 &&
@@ -379,8 +417,8 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
   // 128-key blocks when two CTAs per SM still fit (TMEM <= 256 columns, >= 2 K/V stages in half an SM's shared
   // memory) and the sequence is long enough to amortise them; 64-key blocks otherwise
   auto fits2 = [&](int bn) {
-    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * bn * 2 + 4096 + 2 * (size_t)(2 * bn * dp * 2);
-    return bn + dp + 16 <= 256 && need <= (size_t)113 * 1024 - 2048;
+    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * bn * 2 + 4096 + 2 * (size_t)(bn * (dp + dov) * 2);
+    return bn + ol_cols <= 256 && need <= (size_t)113 * 1024 - 2048;
   };
   // measured on B200 (tools/dev_attn_variants.py): 2 CTAs/SM x 128 keys beats 2 x 64 by 1-2 % at 4096 tokens;
   // 1 CTA/SM x 128 keys beats 64 by 23 % when the grid has no second CTA per SM to offer (1024 tokens, d = 80);
@@ -388,39 +426,41 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
   // (a 512-CTA grid on 444 slots runs one slow wave plus a full-length tail)
   const long grid_ctas = (long)ceil_div_i(Tq, BQ) * NH * B;
   auto fits1 = [&](int bn) {
-    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * bn * 2 + 4096 + 2 * (size_t)(2 * bn * dp * 2);
-    return bn + dp + 16 <= 512 && need <= (size_t)227 * 1024 - 2048;
+    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * bn * 2 + 4096 + 2 * (size_t)(bn * (dp + dov) * 2);
+    return bn + ol_cols <= 512 && need <= (size_t)227 * 1024 - 2048;
   };
   auto fits3 = [&]() {
-    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * 64 * 2 + 4096 + 2 * (size_t)(2 * 64 * dp * 2);
-    return 64 + dp + 16 <= 128 && need <= (size_t)75 * 1024 - 1024;
+    const size_t need = (size_t)BQ * dp * 2 + (size_t)BQ * 64 * 2 + 4096 + 2 * (size_t)(64 * (dp + dov) * 2);
+    return 64 + ol_cols <= 170 && need <= (size_t)75 * 1024 - 1024;   // 3 x 170 columns <= 512 (allocations are powers of two: 128)
   };
   int BN = 64, occ = 2;
   if (Tk >= 512 && (fits2(128) || (grid_ctas <= tf_num_sms() && fits1(128)))) BN = 128;
-  if (Tk >= 512 && fits3() && grid_ctas >= 1024) { BN = 64; occ = 3; }
+  if (Tk >= 512 && fits3() && 64 + ol_cols <= 128 && grid_ctas >= 1024) { BN = 64; occ = 3; }
   if (g_force_attn_bn == 64 || g_force_attn_bn == 128) BN = g_force_attn_bn;
-  if (g_force_attn_occ == 2 || (g_force_attn_occ == 3 && BN == 64 && fits3())) occ = g_force_attn_occ;
+  if (g_force_attn_occ == 2 || (g_force_attn_occ == 3 && BN == 64 && fits3() && 64 + ol_cols <= 128)) occ = g_force_attn_occ;
   if (BN == 128) occ = 2;
-  if (BN == 128 && 128 + dp + 16 > 512) BN = 64;
+  if (BN == 128 && 128 + ol_cols > 512) BN = 64;
 
   AttnParams p{};
-  p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp;
+  p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp; p.dov = dov;
+  p.l_off = l_off; p.ol_cols = ol_cols;
   p.nkv = ceil_div_i(Tk, BN);
   p.causal = causal ? 1 : 0;
   p.timeline = g_attn_timeline;
-  uint32_t need = BN + dp + 16, cols = 32;   // S, O, L
+  uint32_t need = BN + ol_cols, cols = 32;   // S, O, L
   while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(out);
   p.osb = out_stride_b; p.osh = out_stride_h; p.ost = out_stride_t;
 
-  const size_t q_bytes = (size_t)BQ * dp * 2, k_bytes = (size_t)BN * dp * 2, p_bytes = (size_t)BQ * BN * 2;
+  const size_t q_bytes = (size_t)BQ * dp * 2, k_bytes = (size_t)BN * dp * 2, v_bytes = (size_t)BN * dov * 2,
+               p_bytes = (size_t)BQ * BN * 2;
   // half an SM's shared memory (two CTAs per SM) when that still holds a K/V ring of >= 2 stages - the MMA warp
   // issues S_{j+1} before PV_j, so block j+1 must land while block j's stage is still in use - else the whole SM
   auto ring = [&](size_t budget) {
     const long room = (long)budget - (long)q_bytes - (long)p_bytes - 2048;
-    return room < 0 ? 0 : (int)(room / (long)(2 * k_bytes));
+    return room < 0 ? 0 : (int)(room / (long)(k_bytes + v_bytes));
   };
   int stages = occ == 3 ? ring((size_t)75 * 1024 - 1024) : (cols <= 256 ? ring((size_t)113 * 1024 - 2048) : 0);
   if (stages < 2 && stages < p.nkv) stages = ring((size_t)227 * 1024 - 2048);
@@ -428,7 +468,7 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
   if (stages > p.nkv) stages = p.nkv < 1 ? 1 : p.nkv;
   TF_CHECK_ARG(stages >= 2 || (stages == 1 && p.nkv == 1), "tf_attention_f16: head dim %d does not fit shared memory", dp);
   p.stages = stages;
-  const size_t smem = q_bytes + p_bytes + 2048 + (size_t)stages * 2 * k_bytes + 2048;
+  const size_t smem = q_bytes + p_bytes + 2048 + (size_t)stages * (k_bytes + v_bytes) + 2048;
 
   CUtensorMap tmQ, tmK, tmV;
   {
@@ -449,7 +489,15 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
                             CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
   }
-  {
+  if (vnat) {
+    uint64_t dims[2] = {(uint64_t)ldvt, (uint64_t)B * Tk_pad};
+    uint64_t strides[1] = {(uint64_t)ldvt * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    uint32_t es[2] = {1, 1};
+    int rc = tf_encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)B * Tk_pad, (uint64_t)NH * dp};
     uint64_t strides[1] = {(uint64_t)ldvt * 2};
     uint32_t box[2] = {64, (uint32_t)dp};
@@ -461,14 +509,23 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
   dim3 grid(ceil_div_i(Tq, BQ), NH, B);
   static bool attr_set = false;
   if (!attr_set) {
-    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<64, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TF_CUDA(cudaFuncSetAttribute(tf_attention_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (BN == 64 && occ == 3) TF_LAUNCH((tf_attention_kernel<64, 3>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
-  else if (BN == 64) TF_LAUNCH((tf_attention_kernel<64, 2>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
-  else TF_LAUNCH((tf_attention_kernel<128, 2>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);
+#define TF_ATT_LAUNCH(BN_, OCC_)                                                                                          \
+  do {                                                                                                                    \
+    if (vnat) TF_LAUNCH((tf_attention_kernel<BN_, OCC_, true>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);        \
+    else TF_LAUNCH((tf_attention_kernel<BN_, OCC_, false>), grid, kAttThreads, smem, stream, tmQ, tmK, tmV, p);            \
+  } while (0)
+  if (BN == 64 && occ == 3) TF_ATT_LAUNCH(64, 3);
+  else if (BN == 64) TF_ATT_LAUNCH(64, 2);
+  else TF_ATT_LAUNCH(128, 2);
+#undef TF_ATT_LAUNCH
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;
@@ -478,7 +535,15 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
                                 long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
                                 int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream) {
   return attention_impl(q, ldq, k, ldk, vt, ldvt, out, out_stride_b, out_stride_h, out_stride_t, B, NH, Tq, Tk, Tk_pad, d, dp,
-                        scale, 0, stream);
+                        scale, 0, 0, 0, stream);
+}
+
+extern "C" int tf_attention_v_f16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                                  long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
+                                  int Tq, int Tk, int Tk_pad, int d, int dp, int dvp, float scale, int causal, void* stream) {
+  if (causal) TF_CHECK_ARG(Tq == Tk, "tf_attention_v_f16: causal masking needs Tq == Tk (got %d, %d)", Tq, Tk);
+  return attention_impl(q, ldq, k, ldk, v, ldv, out, out_stride_b, out_stride_h, out_stride_t, B, NH, Tq, Tk, Tk_pad, d, dp,
+                        scale, causal, 1, dvp, stream);
 }
 
 extern "C" int tf_attention_causal_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
@@ -486,5 +551,5 @@ extern "C" int tf_attention_causal_f16(const void* q, int ldq, const void* k, in
                                        int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream) {
   TF_CHECK_ARG(Tq == Tk, "tf_attention_causal_f16: causal masking needs Tq == Tk (got %d, %d)", Tq, Tk);
   return attention_impl(q, ldq, k, ldk, vt, ldvt, out, out_stride_b, out_stride_h, out_stride_t, B, NH, Tq, Tk, Tk_pad, d, dp,
-                        scale, 1, stream);
+                        scale, 1, 0, 0, stream);
 }

@@ -258,6 +258,20 @@ class Context:
                                                        Tk, Tk_pad, d, dp, 1.0 / math.sqrt(d), stream_ptr()))
         b200.check(st, "tf_attention_f16")
 
+    def attention_v(self, q_ptr, ldq, k_ptr, ldk, v_ptr, ldv, out_ptr, B, NH, Tq, Tk, Tk_pad, d, dp, dvp, head_major, causal=False):
+        """Attention with V in its natural layout (B*Tk_pad rows, head h at columns [h*dvp, (h+1)*dvp))."""
+        if self.skip("attention"):
+            return
+        if head_major:   # reference reshape quirk: (B,NH,T,d) memory read back as (B,T,NH*d)
+            osb, osh, ost = NH * Tq * d, Tq * d, d
+        else:
+            osb, osh, ost = Tq * NH * d, d, NH * d
+        st = self._timed(("attention", B, NH, Tq, Tk, d),
+                         lambda: b200.tf_attention_v_f16(q_ptr, ldq, k_ptr, ldk, v_ptr, ldv, out_ptr, osb, osh, ost, B, NH, Tq,
+                                                         Tk, Tk_pad, d, dp, dvp, 1.0 / math.sqrt(d), 1 if causal else 0,
+                                                         stream_ptr()))
+        b200.check(st, "tf_attention_v_f16")
+
     def attention_causal(self, q_ptr, ldq, k_ptr, ldk, vt_ptr, ldvt, out_ptr, B, NH, T, T_pad, d, dp):
         """Causal self-attention with the canonical head merge (CLIPAttention, reference attention.py:88-99)."""
         if self.skip("attention"):

@@ -166,20 +166,19 @@ class UNetModel:
         return out
 
     def _ctx_kv_pack(self):
-        """Row-concatenated (head-padded) to_k / to_v weights of every cross-attention: the prompt context is the
-        same for all 16 transformer blocks, so their K and V^T projections are two GEMMs per step, not 32."""
+        """Row-concatenated [to_k ; to_v] weights (head-padded) of every cross-attention: the prompt context is the same
+        for all 16 transformer blocks, so their K and V projections are ONE GEMM per step, not 32."""
         atts = self._cross_attns()
         tensors = []
         for a in atts:
             tensors += [a.to_k.weight, a.to_v.weight]
         def build():
-            wk = torch.cat([a._packed()[1] for a in atts], dim=0).contiguous()
-            wv = torch.cat([a._packed()[2] for a in atts], dim=0).contiguous()
+            wkv = torch.cat([a._packed()[3] for a in atts], dim=0).contiguous()
             offs, o = {}, 0
             for a in atts:
-                offs[id(a)] = o
-                o += a._packed()[1].shape[0]
-            return wk, wv, offs, o
+                offs[id(a)] = (o, a._packed()[1].shape[0])     # (first row of this block's K rows, number of K rows)
+                o += a._packed()[3].shape[0]
+            return wkv, offs, o
         return packing.cached(self, "ctxkv", tensors, build)
 
     # ---- fast path ------------------------------------------------------------------------------
@@ -210,14 +209,12 @@ class UNetModel:
         if misc:
             b200.check(b200.tf_pad_tokens_f32_to_f16(context_ptr, cact.ptr, n, ctx_tokens, tkp, 768, S),
                        "tf_pad_tokens_f32_to_f16")
-        # --- K and V^T of every cross-attention in two launches (same context for all blocks) ---
-        wk_all, wv_all, kv_offs, kv_total = self._ctx_kv_pack()
+        # --- K and V of every cross-attention in one launch (same context for all blocks) ---
+        wkv_all, kv_offs, kv_total = self._ctx_kv_pack()
         Mc = n * tkp
-        kall = ar.alloc(2 * Mc * kv_total)
-        vtall = ar.alloc(2 * kv_total * Mc)
-        ctx.gemm(cact.ptr, 768, Mc, 768, wk_all.data_ptr(), kv_total, kall, kv_total)
-        ctx.gemm(wv_all.data_ptr(), 768, kv_total, 768, cact.ptr, Mc, vtall, Mc, ldw=768, w_static=False)
-        ctx.ctx_kv = {key: (kall + 2 * off, kv_total, vtall + 2 * off * Mc, Mc) for key, off in kv_offs.items()}
+        kvall = ar.alloc(2 * Mc * kv_total)
+        ctx.gemm(cact.ptr, 768, Mc, 768, wkv_all.data_ptr(), kv_total, kvall, kv_total)
+        ctx.ctx_kv = {key: (kvall + 2 * off, kv_total, kvall + 2 * (off + nk), kv_total) for key, (off, nk) in kv_offs.items()}
         # --- plan the skip/concat buffers: output block j reads [x | saved[11-j]] ---
         res = [(H, W)]
         in_ch, in_hw = [], []
