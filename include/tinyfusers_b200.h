@@ -90,6 +90,14 @@ int tf_conv2d_nhwc_gn_f16(const void* x, int NI, int H, int W, int Cin, int x_pi
                           int ksize, int stride, void* out, int ldc, const float* bias, const void* residual, int ldr,
                           int flags, void* workspace, size_t ws_bytes, void* gn_stats, int gn_unit, void* stream);
 int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_conv3x3);
+/* out = conv3x3(x, w[:, :9*Cin]) + conv1x1(x2, w[:, 9*Cin:]) + bias in ONE launch (stride 1, pad 1): the 1x1 convolution
+ * of the second source is appended to the implicit GEMM along K (C2/64 extra k-blocks read through a second tensor map).
+ * w: (Cout, 9*Cin + C2) fp16 - OHWI rows of the 3x3 weight followed by the 1x1 weight's row. gn_stats may be NULL.
+ * Replaces: ResBlock `skip_connection(x) + h` with a Conv2d skip (tinyfusers/vision/resnet.py:22,29-30) and ResnetBlock
+ *           `nin_shortcut(x) + h` (resnet.py:39,43-44): a separate cuDNN conv + an elementwise add. */
+int tf_conv2d_nhwc_skip_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* x2, int C2,
+                            int x2_pixel_stride, const void* w, int Cout, void* out, int ldc, const float* bias, int flags,
+                            void* workspace, size_t ws_bytes, void* gn_stats, int gn_unit, void* stream);
 
 /* test / tuning hook: force the N tile and split-K factor of the next GEMM/conv calls (0 = auto) */
 int tf_gemm_set_tuning(int force_bn, int force_splits);

@@ -59,6 +59,8 @@ struct ConvGeom {
 struct GemmParams {
   int M, N, K;
   int bn, m_tiles, n_tiles, splits, k_blocks, kb_per_split, stages;
+  int kb_main;   // k-blocks read from the primary A source; [kb_main, k_blocks) come from the second one (tmA2): the 1x1
+                 // skip convolution of a ResBlock appended to its second 3x3 convolution along K (== k_blocks: none)
   int ctas;   // 1, or 2 = CTA-pair kernel (256-row pair tiles)
   int is_conv;
   ConvGeom g;
@@ -105,7 +107,7 @@ __device__ __forceinline__ int tile_row_to_m(const GemmParams& p, int mt, int r)
 template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   tf::pdl_trigger();
   const long long t_entry = clock64();
@@ -133,6 +135,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     tf::tma_prefetch_desc(&tmA);
+    if (p.kb_main < p.k_blocks) tf::tma_prefetch_desc(&tmA2);
     tf::tma_prefetch_desc(&tmB);
     tf::tma_prefetch_desc(&tmC);
   }
@@ -246,21 +249,32 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       int kb = kb0;
-      // first tile only: the k-blocks whose barrier was armed and whose B tile was issued before the dependency wait
-      // get their A tile now (peeled, so the steady-state loop below keeps its instruction count: it is issue-bound)
-      for (; pre > 0; --pre, ++kb) {
-        if (elected) {
-          if (k2) {
-            if (p.is_conv) tf::tma_load_4d_2sm(a_dst, &tmA, fb, cb * BK, x0 + sx, y0 + r, n0);
-            else tf::tma_load_2d_2sm(a_dst, &tmA, fb, kcol, arow);
-          } else {
-            if (p.is_conv) tf::tma_load_4d(a_dst, &tmA, fbar, cb * BK, x0 + sx, y0 + r, n0);
-            else tf::tma_load_2d(a_dst, &tmA, fbar, kcol, arow);
-          }
+      const int kbm = min(kb1, p.kb_main);   // [kb0, kbm): primary source, [kbm, kb1): second source (1x1 skip conv)
+      auto load_a = [&](uint32_t bar_local, uint32_t bar_leader) {
+        if (k2) {
+          if (p.is_conv) tf::tma_load_4d_2sm(a_dst, &tmA, bar_leader, cb * BK, x0 + sx, y0 + r, n0);
+          else tf::tma_load_2d_2sm(a_dst, &tmA, bar_leader, kcol, arow);
+        } else {
+          if (p.is_conv) tf::tma_load_4d(a_dst, &tmA, bar_local, cb * BK, x0 + sx, y0 + r, n0);
+          else tf::tma_load_2d(a_dst, &tmA, bar_local, kcol, arow);
         }
+      };
+      auto load_a2 = [&](uint32_t bar_local, uint32_t bar_leader) {   // centre tap of the second source (stride 1)
+        const int c2 = (kb - p.kb_main) * BK;
+        if (k2) tf::tma_load_4d_2sm(a_dst, &tmA2, bar_leader, c2, x0 + p.g.pad, y0 + p.g.pad, n0);
+        else tf::tma_load_4d(a_dst, &tmA2, bar_local, c2, x0 + p.g.pad, y0 + p.g.pad, n0);
+      };
+      // first tile only: the k-blocks whose barrier was armed and whose B tile was issued before the dependency wait
+      // get their A tile now (peeled, so the steady-state loops below keep their instruction count: they are issue-bound)
+      for (; pre > 0 && kb < kbm; --pre, ++kb) {
+        if (elected) load_a(fbar, fb);
         advance();
       }
-      for (; kb < kb1; ++kb) {
+      for (; pre > 0; --pre, ++kb) {
+        if (elected) load_a2(fbar, fb);
+        advance();
+      }
+      for (; kb < kbm; ++kb) {
         tf::mbar_wait(ebar, phase ^ 1u);
         if (elected) {
           TF_TRACE_KB(0);
@@ -274,6 +288,22 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tf::mbar_expect_tx(fbar, tx_bytes);
             if (p.is_conv) tf::tma_load_4d(a_dst, &tmA, fbar, cb * BK, x0 + sx, y0 + r, n0);
             else tf::tma_load_2d(a_dst, &tmA, fbar, kcol, arow);
+            tf::tma_load_2d(b_dst, &tmB, fbar, kcol, brow);
+          }
+        }
+        advance();
+      }
+      for (; kb < kb1; ++kb) {   // k-blocks of the appended 1x1 convolution
+        tf::mbar_wait(ebar, phase ^ 1u);
+        if (elected) {
+          if (k2) {
+            if (leader) tf::mbar_expect_tx(fbar, tx_bytes);
+            else tf::mbar_arrive_cluster(fb);
+            load_a2(fbar, fb);
+            tf::tma_load_2d_2sm(b_dst, &tmB, fb, kcol, brow);
+          } else {
+            tf::mbar_expect_tx(fbar, tx_bytes);
+            load_a2(fbar, fb);
             tf::tma_load_2d(b_dst, &tmB, fbar, kcol, brow);
           }
         }
@@ -784,7 +814,9 @@ static long long* g_timeline = nullptr;
 static int g_max_stages = 0;   // debug: cap the smem ring depth (0 = as many as fit)
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams& p,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const CUtensorMap* tmA2p = nullptr) {
+  const CUtensorMap& tmA2 = tmA2p ? *tmA2p : tmA;   // unused unless p.kb_main < p.k_blocks
+  if (!tmA2p) p.kb_main = p.k_blocks;
   static bool attr_set = false;
   if (!attr_set) {
     TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -809,11 +841,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
     const int max_pairs = tf_num_sms() / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-    (void)tf_launch_pdl_cluster(tf_gemm_kernel<2>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, p);
+    (void)tf_launch_pdl_cluster(tf_gemm_kernel<2>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, tmA2, p);
   } else {
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
-    TF_LAUNCH(tf_gemm_kernel<1>, grid, kThreads, smem, stream, tmA, tmB, tmC, p);
+    TF_LAUNCH(tf_gemm_kernel<1>, grid, kThreads, smem, stream, tmA, tmB, tmC, tmA2, p);
   }
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -991,15 +1023,23 @@ extern "C" int tf_gemm_gn_f16(const void* A, int lda, const void* W, int ldw, vo
                    gn_unit, rows_per_image);
 }
 
+// x2 (optional): a second NHWC tensor of the output's geometry with C2 channels whose 1x1 convolution is accumulated into
+// the same output: its weights are the last C2 columns of every row of w, i.e. w is (Cout, 9*Cin + C2).
 static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride,
                                   const void* w, int Cout, int ksize, int stride, void* out, int ldc,
                                   const float* bias, const void* residual, int ldr, int flags,
-                                  void* workspace, size_t ws_bytes, void* stream, void* gn_stats, int gn_unit) {
+                                  void* workspace, size_t ws_bytes, void* stream, void* gn_stats, int gn_unit,
+                                  const void* x2 = nullptr, int C2 = 0, int x2_pixel_stride = 0) {
   TF_CHECK_ARG(x && w && out, "tf_conv2d_nhwc_f16: null pointer");
   TF_CHECK_ARG(ksize == 1 || ksize == 3, "tf_conv2d_nhwc_f16: kernel size %d unsupported (1 or 3)", ksize);
   TF_CHECK_ARG(stride == 1 || stride == 2, "tf_conv2d_nhwc_f16: stride %d unsupported (1 or 2)", stride);
   TF_CHECK_ARG(NI > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "tf_conv2d_nhwc_f16: bad dims");
   TF_CHECK_ARG(x_pixel_stride >= Cin && x_pixel_stride % 8 == 0, "tf_conv2d_nhwc_f16: bad pixel stride");
+  if (x2) {
+    TF_CHECK_ARG(ksize == 3 && stride == 1, "tf_conv2d_nhwc_skip_f16: the appended 1x1 convolution needs a 3x3 stride-1 main convolution");
+    TF_CHECK_ARG(C2 > 0 && C2 % BK == 0 && x2_pixel_stride >= C2 && x2_pixel_stride % 8 == 0 && ((uintptr_t)x2 & 15) == 0,
+                 "tf_conv2d_nhwc_skip_f16: second source needs C2 %% 64 == 0 (got %d), stride %% 8 == 0, 16-byte alignment", C2);
+  }
   if (ksize == 1 && stride == 1) {
     return gemm_impl(x, x_pixel_stride, w, Cin, out, ldc, NI * H * W, Cout, Cin, bias, residual, ldr,
                      flags, workspace, ws_bytes, stream, gn_stats, gn_unit, H * W);
@@ -1021,7 +1061,7 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   GemmParams p{};
   p.is_conv = 1;
   p.gn_stats = reinterpret_cast<float2*>(gn_stats); p.gn_unit = gn_unit; p.gn_hw = Ho * Wo;
-  p.M = NI * Ho * Wo; p.N = Cout; p.K = 9 * Cin;
+  p.M = NI * Ho * Wo; p.N = Cout; p.K = 9 * Cin + (x2 ? C2 : 0);
   ConvGeom& g = p.g;
   g.H = Ho; g.W = Wo; g.NI = NI; g.cblocks = Cin / BK; g.cscale = stride; g.pad = pad; g.ksize = 3;
   // choose the 128-row tile footprint (TW x TH x TN) with the least padding
@@ -1046,7 +1086,8 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   g.tiles_x = ceil_div_i(Wo, g.TW);
   g.tiles_y = ceil_div_i(Ho, g.TH);
   p.m_tiles = g.tiles_x * g.tiles_y * ceil_div_i(NI, g.TN);
-  p.k_blocks = 9 * g.cblocks;
+  p.kb_main = 9 * g.cblocks;
+  p.k_blocks = p.kb_main + (x2 ? C2 / BK : 0);
   // store box of one epilogue warp = 32 consecutive tile rows (x fastest, then y, then image)
   g.sbw = g.TW >= 32 ? 32 : g.TW;
   g.sbh = g.TW >= 32 ? 1 : (g.TW * g.TH >= 32 ? 32 / g.TW : g.TH);
@@ -1100,6 +1141,18 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
                             dims, strides, box, es, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
+  if (x2) {
+    CUtensorMap tmA2;
+    uint64_t dims[4] = {(uint64_t)C2, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+    uint64_t strides[3] = {(uint64_t)x2_pixel_stride * 2, (uint64_t)W * x2_pixel_stride * 2,
+                           (uint64_t)H * W * x2_pixel_stride * 2};
+    uint32_t box[4] = {BK, (uint32_t)g.TW, (uint32_t)g.TH, (uint32_t)g.TN};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = tf_encode_tmap(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x2, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream), &tmA2);
+  }
   return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1117,6 +1170,15 @@ extern "C" int tf_conv2d_nhwc_gn_f16(const void* x, int NI, int H, int W, int Ci
                                      void* gn_stats, int gn_unit, void* stream) {
   return conv_impl(x, NI, H, W, Cin, x_pixel_stride, w, Cout, ksize, stride, out, ldc, bias, residual, ldr, flags, workspace,
                    ws_bytes, stream, gn_stats, gn_unit);
+}
+
+extern "C" int tf_conv2d_nhwc_skip_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* x2,
+                                       int C2, int x2_pixel_stride, const void* w, int Cout, void* out, int ldc,
+                                       const float* bias, int flags, void* workspace, size_t ws_bytes, void* gn_stats,
+                                       int gn_unit, void* stream) {
+  TF_CHECK_ARG(x2 != nullptr, "tf_conv2d_nhwc_skip_f16: null second source");
+  return conv_impl(x, NI, H, W, Cin, x_pixel_stride, w, Cout, 3, 1, out, ldc, bias, nullptr, 0, flags, workspace, ws_bytes,
+                   stream, gn_stats, gn_unit, x2, C2, x2_pixel_stride);
 }
 
 // 1 if tf_gemm_gn_f16 / tf_conv2d_nhwc_gn_f16 can emit statistics for this output geometry (mirrors the checks above)

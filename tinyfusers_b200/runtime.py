@@ -208,6 +208,16 @@ class Context:
         st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None, gn[1] if gn else 0), fn)
         b200.check(st, "tf_conv2d_nhwc_f16")
 
+    def conv3x3_skip(self, x, x2, w, cout, out, bias=None, gn=None):
+        """out = conv3x3(x) + conv1x1(x2) + bias in one launch; w = [3x3 weight rows | 1x1 weight rows] per output channel."""
+        if self.skip("gemm"):
+            return
+        fn = lambda: b200.tf_conv2d_nhwc_skip_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, x2.ptr, x2.c, x2.stride, w, cout, out.ptr,
+                                                  out.stride, bias, b200.TF_GEMM_W_STATIC, self.ws.data_ptr(), self.ws_bytes,
+                                                  gn[0] if gn else None, gn[1] if gn else 0, stream_ptr())
+        st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, 1, False, gn[1] if gn else 0, x2.c), fn)
+        b200.check(st, "tf_conv2d_nhwc_skip_f16")
+
     def groupnorm(self, x, out, gamma, beta, eps, silu, groups=32):
         parts = x.gn
         if parts is not None and len(parts) in (1, 2) and x.c % groups == 0:

@@ -142,3 +142,29 @@ class Conv2d:
                                               self.weight.shape[0], out.stride, stream_ptr())
         b200.check(st, "tf_conv3x3_smallcin_f32nchw")
         return out
+
+
+def conv3x3_plus_skip(ctx, owner, conv, skip, x, x2, out):
+    """out = conv(x) + skip(x2) with conv a 3x3 stride-1 Conv2d and skip a 1x1 Conv2d, as ONE implicit GEMM: the skip
+    convolution's weight is appended to every row of the 3x3 weight (extra k-blocks read from x2), the biases add.
+    `owner` caches the packed pair. Returns False when the geometry does not qualify (caller falls back to two launches)."""
+    if x2.c % 64 != 0 or x.c % 64 != 0 or conv._geometry() != (3, 1) or skip._geometry() != (1, 1):
+        return False
+    def build():
+        w3, b3 = conv._packed()
+        w1, b1 = skip._packed()
+        cout = w3.shape[0]
+        w = torch.cat((w3.reshape(cout, -1), w1.reshape(w1.shape[0], -1)[:cout]), dim=1).contiguous()
+        b = None
+        if b3 is not None or b1 is not None:
+            b = (b3 if b3 is not None else 0) + (b1[:cout] if b1 is not None else 0)
+            b = b.contiguous()
+        return w, b
+    w, b = packing.cached(owner, "conv_skip", (conv.weight, conv.bias, skip.weight, skip.bias), build)
+    if w.shape[1] != 9 * x.c + x2.c:
+        raise RuntimeError(f"conv3x3_plus_skip: packed weight has {w.shape[1]} columns, expected {9 * x.c + x2.c}")
+    gn = None
+    if out.gn is not None and len(out.gn) == 1 and out.gn[0][0] == 0 and out.gn[0][1] == w.shape[0]:
+        gn = (out.gn[0][2], out.gn[0][3])
+    ctx.conv3x3_skip(x, x2, w.data_ptr(), w.shape[0], out, bias=b.data_ptr() if b is not None else None, gn=gn)
+    return True

@@ -11,7 +11,7 @@ from ..ff.linear import Linear
 from ..native.b200.ops import b200
 from ..runtime import F32, act_to_nchw, nchw_to_act, new_act_tensor, require_cuda, standalone_context, stream_ptr
 from ..storage.tensor import Tensor
-from .conv2d import Conv2d
+from .conv2d import Conv2d, conv3x3_plus_skip
 
 
 class ResBlock:
@@ -62,11 +62,13 @@ class ResBlock:
         h2 = ctx.new_act(x.n, x.h, x.w, self.out_channels)
         self.out_layers[0]._run(ctx, h1, h2, silu=True)
         if isinstance(self.skip_connection, Conv2d):
-            res = ctx.new_act(x.n, x.h, x.w, self.out_channels)
-            self.skip_connection._run(ctx, x, res)
+            # the 1x1 skip convolution rides along the second 3x3 convolution as extra k-blocks (one launch, no residual read)
+            if not conv3x3_plus_skip(ctx, self, self.out_layers[3], self.skip_connection, h2, x, out):
+                res = ctx.new_act(x.n, x.h, x.w, self.out_channels)
+                self.skip_connection._run(ctx, x, res)
+                self.out_layers[3]._run(ctx, h2, out, residual=res)
         else:
-            res = x
-        self.out_layers[3]._run(ctx, h2, out, residual=res)
+            self.out_layers[3]._run(ctx, h2, out, residual=x)
         ctx.arena.release(mark)
         return out
 
@@ -103,10 +105,11 @@ class ResnetBlock:
         h2 = ctx.new_act(x.n, x.h, x.w, self.out_channels)
         self.norm2._run(ctx, h1, h2, silu=True)
         if isinstance(self.nin_shortcut, Conv2d):
-            res = ctx.new_act(x.n, x.h, x.w, self.out_channels)
-            self.nin_shortcut._run(ctx, x, res)
+            if not conv3x3_plus_skip(ctx, self, self.conv2, self.nin_shortcut, h2, x, out):
+                res = ctx.new_act(x.n, x.h, x.w, self.out_channels)
+                self.nin_shortcut._run(ctx, x, res)
+                self.conv2._run(ctx, h2, out, residual=res)
         else:
-            res = x
-        self.conv2._run(ctx, h2, out, residual=res)
+            self.conv2._run(ctx, h2, out, residual=x)
         ctx.arena.release(mark)
         return out
