@@ -101,13 +101,15 @@ def make_case(key):
         klass = (flags & 3) | (4 if gn_unit else 0) | (8 if has_res else 0)
         keep = (A, Ws, bias, out, res, st)
         return [mk(W) for W in Ws], out, (0, M, N, K, klass), (M + 127) // 128, (K + 63) // 64, (math.lcm(32, gn_unit) if gn_unit else 32), not (flags & 2), keep
-    _, n, h, w, cin, cout, stride, has_res, gn_unit = key
+    _, n, h, w, cin, cout, stride, has_res, gn_unit = key[:9]
+    c2 = key[9] if len(key) > 9 else 0     # channels of the appended 1x1 skip convolution's source
     ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
-    M, K = n * ho * wo, 9 * cin
+    M, K = n * ho * wo, 9 * cin + c2
     wbytes = cout * K * 2
     copies = max(2, min(16, math.ceil(300e6 / wbytes)))
     x = torch.randn(n, h, w, cin, device=dev).half()
-    Ws = [(torch.randn(cout, 3, 3, cin, device=dev) / math.sqrt(K)).half() for _ in range(copies)]
+    Ws = [(torch.randn(cout, K, device=dev) / math.sqrt(K)).half() for _ in range(copies)]
+    x2 = torch.randn(n, h, w, c2, device=dev).half() if c2 else None
     bias = torch.randn(cout, device=dev)
     f32 = cout <= 16
     ldc = 16 if cout == 8 and cin == 320 else cout
@@ -116,12 +118,14 @@ def make_case(key):
     st = torch.zeros(max(1, n * (ho * wo // 32) * (cout // gn_unit) * 2), device=dev) if gn_unit else None
     flags = 1 if f32 else 0
     def mk(W):
+        if c2:
+            return lambda: b200.check(b200.tf_conv2d_nhwc_skip_f16(x.data_ptr(), n, h, w, cin, cin, x2.data_ptr(), c2, c2, W.data_ptr(), cout, out.data_ptr(), ldc, bias.data_ptr(), flags, ws.data_ptr(), ws.numel(), st.data_ptr() if gn_unit else None, gn_unit, S()), "conv+skip")
         if gn_unit:
             return lambda: b200.check(b200.tf_conv2d_nhwc_gn_f16(x.data_ptr(), n, h, w, cin, cin, W.data_ptr(), cout, 3, stride, out.data_ptr(), ldc, bias.data_ptr(), res.data_ptr() if has_res else None, cout, flags, ws.data_ptr(), ws.numel(), st.data_ptr(), gn_unit, S()), "conv")
         return lambda: b200.check(b200.tf_conv2d_nhwc_f16(x.data_ptr(), n, h, w, cin, cin, W.data_ptr(), cout, 3, stride, out.data_ptr(), ldc, bias.data_ptr(), res.data_ptr() if has_res else None, cout, flags, ws.data_ptr(), ws.numel(), S()), "conv")
     klass = flags | (4 if gn_unit else 0) | (8 if has_res else 0) | (16 if stride == 2 else 0)
-    keep = (x, Ws, bias, out, res, st)
-    return [mk(W) for W in Ws], out, (1, M, cout, K, klass), (M + 127) // 128, 9 * cin // 64, (math.lcm(32, gn_unit) if gn_unit else 32), True, keep
+    keep = (x, Ws, bias, out, res, st, x2)
+    return [mk(W) for W in Ws], out, (1, M, cout, K, klass), (M + 127) // 128, K // 64, (math.lcm(32, gn_unit) if gn_unit else 32), True, keep
 
 
 def tune(key, count):
