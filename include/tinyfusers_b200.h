@@ -90,6 +90,30 @@ int tf_conv2d_nhwc_gn_f16(const void* x, int NI, int H, int W, int Cin, int x_pi
                           int ksize, int stride, void* out, int ldc, const float* bias, const void* residual, int ldr,
                           int flags, void* workspace, size_t ws_bytes, void* gn_stats, int gn_unit, void* stream);
 int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_conv3x3);
+
+/* tf_gemm_f16 with optional fused extras (NULL pointers = off):
+ *   gn_stats / gn_unit / gn_rows_per_image : as tf_gemm_gn_f16;
+ *   row_stats_out : float2 [M][N/32] = {sum, sumsq} of the rounded fp16 output over each 32-column chunk of each row
+ *                   (N % 32 == 0, plain fp16 epilogue, no split-K) - the statistics a LayerNorm over the row needs;
+ *   ln_stats / ln_chunks / ln_c1 / ln_eps : LayerNorm FOLDED onto the A operand. A holds the un-normalised rows (K = 32 *
+ *                   ln_chunks columns), ln_stats is the row_stats_out of the GEMM that produced A, W must have been
+ *                   pre-multiplied by gamma (W' = W diag(gamma)), ln_c1[n] = sum_k W'[n,k], and `bias` must carry
+ *                   W beta (+ the layer's own bias). The epilogue computes rstd[m] * (acc - mean[m] * c1[n]) + bias[n]:
+ *                   exactly Linear(LayerNorm(A)) without the LayerNorm launch and its read + write pass.
+ * Replaces: LayerNorm.__call__ followed by Linear / GEGLU (tinyfusers/attention/attention.py:50-55, ff/layer_norm.py:8-49). */
+typedef struct tf_gemm_extras {
+  void* gn_stats;
+  int gn_unit;
+  int gn_rows_per_image;
+  void* row_stats_out;
+  const void* ln_stats;
+  int ln_chunks;
+  const float* ln_c1;
+  float ln_eps;
+} tf_gemm_extras;
+int tf_gemm_ex_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M, int N, int K,
+                   const float* bias, const void* residual, int ldr, int flags, void* workspace, size_t ws_bytes,
+                   const tf_gemm_extras* ex, void* stream);
 /* out = conv3x3(x, w[:, :9*Cin]) + conv1x1(x2, w[:, 9*Cin:]) + bias in ONE launch (stride 1, pad 1): the 1x1 convolution
  * of the second source is appended to the implicit GEMM along K (C2/64 extra k-blocks read through a second tensor map).
  * w: (Cout, 9*Cin + C2) fp16 - OHWI rows of the 3x3 weight followed by the 1x1 weight's row. gn_stats may be NULL.

@@ -133,3 +133,32 @@ def test_blocks_match_reference_goldens():
     rb = ResBlock(320, 1280, 640)
     _load(rb, sd, "rb")
     assert rel_err(rb(rnd(602, 2, 320, 8, 8).cuda(), rnd(603, 1, 1280).cuda()), torch.from_numpy(gold["res_block"])) < TOL
+
+
+def test_spatial_transformer_with_layernorm_folded_into_gemms(oracle):
+    """Opt-in path (TINYFUSERS_B200_FUSE_LN=1): norm1 / norm2 folded into the projections that consume them
+    (tf_gemm_ex_f16: row statistics from the producing GEMM, gamma in the weights, mean / rstd applied in the epilogue)."""
+    from tinyfusers_b200.attention.attention import SpatialTransformer
+    from tinyfusers_b200.runtime import standalone_context
+    from tinyfusers_b200.storage.state import update_state
+    import contextlib, io
+    sd = {}
+    oracle.add_spatial_transformer(sd, "st", 640, 768, seed=77)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 640, 16, 16, generator=g)
+    c = torch.randn(2, 77, 768, generator=g)
+    st = SpatialTransformer(640, 768, 8, 80)
+    with contextlib.redirect_stdout(io.StringIO()):
+        update_state(st, sd, "st")
+    with torch.no_grad():
+        ref = oracle.spatial_transformer(sd, "st", x, c, 8, 80, True)
+    ctx = standalone_context()
+    plain = st(x.cuda(), c.cuda())
+    old = ctx.fuse_ln
+    ctx.fuse_ln = True
+    try:
+        folded = st(x.cuda(), c.cuda())
+    finally:
+        ctx.fuse_ln = old
+    assert rel_err(plain, ref) < 1e-2 and rel_err(folded, ref) < 1e-2
+    assert rel_err(folded, plain) < 5e-3 and not torch.equal(folded, plain)     # a different path really ran

@@ -29,6 +29,11 @@ def _pad64(d):
     return (d + 63) // 64 * 64
 
 
+def fold_norm1(rows):
+    """LayerNorm -> [Q|K|V] projection fold: wins up to 2048-row (batch 2 x 1024 tokens) inputs, loses at 8192 rows."""
+    return rows <= 4096
+
+
 class CrossAttention:
     def __init__(self, query_dim, context_dim, n_heads, d_head):
         self.to_q = Linear(query_dim, n_heads * d_head, bias=False)
@@ -52,6 +57,15 @@ class CrossAttention:
             return wq, wk, wv, wkv, wqkv
         return packing.cached(self, "attn", (self.to_q.weight, self.to_k.weight, self.to_v.weight), build)
 
+    def _packed_ln(self, norm, self_attention):
+        """The first projection with `norm` (the LayerNorm in front of this attention) folded in: (W', c1, c2)."""
+        def build():
+            packs = self._packed()
+            w = packs[4] if self_attention else packs[0]      # [wq ; wk ; wv] or wq
+            return packing.ln_fold(w, norm.weight, norm.bias)
+        return packing.cached(self, "attn_ln_self" if self_attention else "attn_ln_q",
+                              (self.to_q.weight, self.to_k.weight, self.to_v.weight, norm.weight, norm.bias), build)
+
     def __call__(self, x, context=None):
         require_cuda(x, "x")
         ctx = standalone_context()
@@ -64,17 +78,26 @@ class CrossAttention:
         return out.to(F32)
 
     # h_ptr (B*T, C) is updated:  h <- to_out(attention(...)) (+ h if residual);  xn_ptr = normalised input
-    def _run(self, ctx, xn_ptr, B, T, C, h_ptr, context=None, residual=True):
+    # ln = (row statistics of the UN-normalised input at xn_ptr, LayerNorm module): the norm is folded into the first GEMM.
+    # h_stats: where the out-projection leaves the row statistics of the updated h (for the next folded LayerNorm).
+    def _run(self, ctx, xn_ptr, B, T, C, h_ptr, context=None, residual=True, ln=None, h_stats=None):
         nh, d = self.num_heads, self.head_size
         dp, dvp = _pad16(d), _pad64(d)
         wq, wk, wv, wkv, wqkv = self._packed()
         mark = ctx.arena.mark()
         M = B * T
+        lnx = None
+        if ln is not None:
+            wf, c1, c2 = self._packed_ln(ln[1], context is None)
+            lnx = (ln[0], C // 32, c1.data_ptr(), float(ln[1].eps.reshape(-1)[0]))
         if context is None:
             # self-attention: ONE GEMM for [Q | K | V]; the attention kernel reads V in this natural layout
             n_all = 2 * nh * dp + nh * dvp
             qkv_ptr = ctx.arena.alloc(2 * M * n_all)
-            ctx.gemm(xn_ptr, C, M, C, wqkv.data_ptr(), n_all, qkv_ptr, n_all)
+            if lnx is not None:
+                ctx.gemm(xn_ptr, C, M, C, wf.data_ptr(), n_all, qkv_ptr, n_all, bias=c2.data_ptr(), ln=lnx)
+            else:
+                ctx.gemm(xn_ptr, C, M, C, wqkv.data_ptr(), n_all, qkv_ptr, n_all)
             q_ptr, k_ptr, v_ptr = qkv_ptr, qkv_ptr + 2 * nh * dp, qkv_ptr + 4 * nh * dp
             ldq = ldk = ldv = n_all
             Tk, Tkp = T, T
@@ -83,7 +106,10 @@ class CrossAttention:
             Tk = context.valid if context.valid is not None else context.h
             Mc = B * Tkp
             q_ptr = ctx.arena.alloc(2 * M * nh * dp)
-            ctx.gemm(xn_ptr, C, M, C, wq.data_ptr(), nh * dp, q_ptr, nh * dp)
+            if lnx is not None:
+                ctx.gemm(xn_ptr, C, M, C, wf.data_ptr(), nh * dp, q_ptr, nh * dp, bias=c2.data_ptr(), ln=lnx)
+            else:
+                ctx.gemm(xn_ptr, C, M, C, wq.data_ptr(), nh * dp, q_ptr, nh * dp)
             ldq = nh * dp
             pre = ctx.ctx_kv.get(id(self)) if ctx.ctx_kv else None
             if pre is not None:      # projected once per step for all blocks (UNetModel._ctx_kv_pack)
@@ -98,7 +124,7 @@ class CrossAttention:
         wo, bo = self.to_out[0]._packed()
         ctx.gemm(a_ptr, nh * d, M, nh * d, wo.data_ptr(), wo.shape[0], h_ptr, wo.shape[0],
                  bias=bo.data_ptr() if bo is not None else None, residual_ptr=h_ptr if residual else None,
-                 ldr=wo.shape[0])
+                 ldr=wo.shape[0], row_stats=h_stats)
         ctx.arena.release(mark)
 
 
@@ -123,16 +149,33 @@ class BasicTransformerBlock:
         self._run(ctx, h.data_ptr(), B, T, C, ca)
         return h.to(F32)
 
-    # h (B*T, C) fp16 updated in place
-    def _run(self, ctx, h_ptr, B, T, C, context):
+    # h (B*T, C) fp16 updated in place. h_stats: row statistics of h left by its producer (tf_gemm_ex_f16 row_stats_out):
+    # with them the three LayerNorms are folded into the GEMMs that consume them (no LayerNorm launch, no xn buffer).
+    def _run(self, ctx, h_ptr, B, T, C, context, h_stats=None):
         mark = ctx.arena.mark()
-        xn = ctx.arena.alloc(2 * B * T * C)
-        self.norm1._run(ctx, h_ptr, xn, B, T, C)
-        self.attn1._run(ctx, xn, B, T, C, h_ptr)
-        self.norm2._run(ctx, h_ptr, xn, B, T, C)
-        self.attn2._run(ctx, xn, B, T, C, h_ptr, context=context)
-        self.norm3._run(ctx, h_ptr, xn, B, T, C)
-        self.ff._run(ctx, xn, h_ptr, B * T, C)
+        if h_stats is not None and ctx.fuse_ln and not ctx.ln_strided and C % 32 == 0:
+            # Measured per shape (tools/shape_table.py): the fold costs the consumer's epilogue a per-tile statistics fold
+            # plus two FMAs per element, which pays for the narrow Q projection everywhere (norm2) and for the [Q|K|V]
+            # projection below 4096 tokens (norm1), but not for the epilogue-bound GEGLU projection (norm3 stays a kernel).
+            xn = None
+            if fold_norm1(B * T):
+                self.attn1._run(ctx, h_ptr, B, T, C, h_ptr, ln=(h_stats, self.norm1), h_stats=h_stats)
+            else:
+                xn = ctx.arena.alloc(2 * B * T * C)
+                self.norm1._run(ctx, h_ptr, xn, B, T, C)
+                self.attn1._run(ctx, xn, B, T, C, h_ptr, h_stats=h_stats)
+            self.attn2._run(ctx, h_ptr, B, T, C, h_ptr, context=context, ln=(h_stats, self.norm2))
+            xn = ctx.arena.alloc(2 * B * T * C) if xn is None else xn
+            self.norm3._run(ctx, h_ptr, xn, B, T, C)
+            self.ff._run(ctx, xn, h_ptr, B * T, C)
+        else:
+            xn = ctx.arena.alloc(2 * B * T * C)
+            self.norm1._run(ctx, h_ptr, xn, B, T, C)
+            self.attn1._run(ctx, xn, B, T, C, h_ptr)
+            self.norm2._run(ctx, h_ptr, xn, B, T, C)
+            self.attn2._run(ctx, xn, B, T, C, h_ptr, context=context)
+            self.norm3._run(ctx, h_ptr, xn, B, T, C)
+            self.ff._run(ctx, xn, h_ptr, B * T, C)
         ctx.arena.release(mark)
 
 
@@ -175,9 +218,12 @@ class SpatialTransformer:
         hn = ctx.new_act(x.n, x.h, x.w, C)
         self.norm._run(ctx, x, hn, silu=False)
         h = ctx.new_act(x.n, x.h, x.w, C)
-        self.proj_in._run(ctx, hn, h)
+        h_stats = None
+        if ctx.fuse_ln and not ctx.ln_strided and C % 32 == 0:
+            h_stats = ctx.arena.alloc(8 * B * T * (C // 32))     # float2 per 32-column chunk of every token row
+        self.proj_in._run(ctx, hn, h, row_stats=h_stats if fold_norm1(B * T) else None)
         for block in self.transformer_blocks:
-            block._run(ctx, h.ptr, B, T, C, context)
+            block._run(ctx, h.ptr, B, T, C, context, h_stats=h_stats)
         self.proj_out._run(ctx, h, out, residual=x)
         ctx.arena.release(mark)
         return out

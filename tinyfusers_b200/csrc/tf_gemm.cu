@@ -43,7 +43,12 @@ constexpr uint32_t kAccStride = 256;  // columns between the two accumulator buf
 constexpr int kEpiStageBytes = 32 * 128;                    // per warp, 1024-aligned (swizzle atom)
 constexpr int kEpiBiasFloats = 256;
 constexpr int kEpiColsumBytes = 256 * 8;                    // per warp: {sum, sumsq} of each tile column (GroupNorm statistics)
-constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes + kEpiWarps * kEpiBiasFloats * 4 + 4 * kEpiColsumBytes;  // 49152
+// kX (the kernel's second template parameter) = the variant with row statistics out / LayerNorm fold in: it carries a
+// second per-warp float array (the c1 slice) and extra epilogue code; the plain variant stays as lean as it was - the
+// epilogue of these short GEMMs is sensitive to every instruction and register (a shared kernel cost ~0.4 us per launch).
+__host__ __device__ constexpr int epi_bytes(bool x) {
+  return kEpiWarps * kEpiStageBytes + (x ? 2 : 1) * kEpiWarps * kEpiBiasFloats * 4 + 4 * kEpiColsumBytes;   // 49152 | 57344
+}
 
 struct ConvGeom {
   int H, W, NI;          // OUTPUT height/width, images
@@ -77,6 +82,17 @@ struct GemmParams {
   float2* gn_stats;
   int gn_unit;      // channels per statistics unit; bn % gn_unit == 0
   int gn_hw;        // rows (pixels) per image; % 32 == 0
+  // optional per-row statistics of the OUTPUT (plain fp16 epilogue): row_stats[m][chunk] = {sum, sumsq} of the rounded
+  // values of columns [32*chunk, 32*chunk + 32) - what a LayerNorm folded into the consuming GEMM needs
+  float2* row_stats;
+  int rs_ld;        // chunks per row = N / 32
+  // optional LayerNorm folded onto the A operand: A holds the UN-normalised rows, W was pre-multiplied by gamma, and
+  //   out = rstd[m] * (acc - mean[m] * c1[n]) + bias[n]      (c1[n] = sum_k W'[n,k]; bias carries W.beta)
+  // with mean / rstd of row m folded from ln_stats[m][0..ln_np) (the producer's row_stats), C = ln_np * 32 columns
+  const float2* ln_stats;
+  int ln_np;
+  const float* ln_c1;
+  float ln_eps;
 };
 
 // tile-local row (0..127) -> global output row (pixel index for conv), or -1 if padding
@@ -104,7 +120,7 @@ __device__ __forceinline__ int tile_row_to_m(const GemmParams& p, int mt, int r)
 // HALF of the weight tile, so the L2 -> SM operand traffic per FLOP (the measured limiter of these kernels)
 // drops by (128 + bn) / (128 + bn/2). Producer and epilogue run in both CTAs; the leader owns the `full`
 // and `tmem empty` barriers, commits are multicast to both CTAs.
-template <int kCtas>
+template <int kCtas, bool kX>
 __global__ void __launch_bounds__(kThreads, 1)
 tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2, const GemmParams p) {
@@ -123,6 +139,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + p.stages * A_STAGE_BYTES;
   const uint32_t epi_base = smem_b + p.stages * b_stage_bytes;
+  constexpr int kEpiBytes = epi_bytes(kX);
   const uint32_t bar_base = epi_base + kEpiBytes;
   const int S = p.stages;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -380,13 +397,16 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;
     const uint32_t stg = epi_base + ew * kEpiStageBytes;
     float* bsm = reinterpret_cast<float*>(smem_raw + (epi_base + kEpiWarps * kEpiStageBytes - raw_u32)) + ew * kEpiBiasFloats;
+    float* c1sm = bsm + kEpiWarps * kEpiBiasFloats;   // this warp's copy of the tile's c1 slice (LayerNorm fold; kX only)
+    const bool ln = kX && p.ln_stats != nullptr && !(p.partial != nullptr);
+    const bool rowst = kX && p.row_stats != nullptr && !(p.partial != nullptr);
     const bool partial = p.partial != nullptr;
     const bool geglu = (p.flags & TF_EPI_GEGLU) != 0 && !partial;
     const bool out_f32 = (p.flags & TF_EPI_OUT_F32) != 0 || partial;
     const bool use_bias = p.bias != nullptr && !partial;
     const bool use_res = p.residual != nullptr && !partial;
     const bool gn = p.gn_stats != nullptr && !partial;
-    float2* colsum = reinterpret_cast<float2*>(smem_raw + (epi_base + kEpiWarps * kEpiStageBytes + kEpiWarps * kEpiBiasFloats * 4 - raw_u32)) +
+    float2* colsum = reinterpret_cast<float2*>(smem_raw + (epi_base + kEpiWarps * kEpiStageBytes + (kX ? 2 : 1) * kEpiWarps * kEpiBiasFloats * 4 - raw_u32)) +
                      q * (kEpiColsumBytes / 8);   // shared by the quarter's two warps (disjoint columns)
     // swizzle of 16-byte chunk j in row r (row = lane): fp32 rows are 128 B (SW128), fp16 64 B (SW64), GEGLU 32 B (SW32)
     const uint32_t row_bytes = out_f32 ? 128u : (geglu ? 32u : 64u);
@@ -419,6 +439,20 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < kEpiBiasFloats / 32; ++j) {
         const int nn = n_tile + j * 32 + lane;
         bsm[j * 32 + lane] = (use_bias && j * 32 < p.bn && nn < p.N) ? __ldg(p.bias + nn) : 0.f;
+        if (ln) c1sm[j * 32 + lane] = (j * 32 < p.bn && nn < p.N) ? __ldg(p.ln_c1 + nn) : 0.f;
+      }
+      // LayerNorm fold: this row's mean / rstd from the producer's per-chunk statistics (fixed order), as the two
+      // coefficients of  out = ln_a * acc + ln_b * c1 + bias
+      float ln_a = 1.f, ln_b = 0.f;
+      if (ln && m_own >= 0) {
+        const float2* rs = p.ln_stats + (size_t)m_own * p.ln_np;
+        float sm = 0.f, sq = 0.f;
+        for (int i = 0; i < p.ln_np; ++i) { const float2 t2 = __ldg(rs + i); sm += t2.x; sq += t2.y; }
+        const float inv_c = 1.0f / (32.0f * (float)p.ln_np);
+        const float mean = sm * inv_c;
+        const float rstd = rsqrtf(fmaxf(sq * inv_c - mean * mean, 0.f) + p.ln_eps);
+        ln_a = rstd;
+        ln_b = -rstd * mean;
       }
       // residual chunk: 32 halfs of this thread's row (zeros outside the tensor), prefetched one chunk ahead
       const __half* res_row = (use_res && m_own >= 0) ? p.residual + (size_t)m_own * p.ldr + n_tile : nullptr;
@@ -470,8 +504,12 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const float val = __uint_as_float(v[j + i]) + bsm[c + j + i];
-              const float gate = __uint_as_float(v[16 + j + i]) + bsm[c + 16 + j + i];
+              float val = __uint_as_float(v[j + i]) + bsm[c + j + i];
+              float gate = __uint_as_float(v[16 + j + i]) + bsm[c + 16 + j + i];
+              if (ln) {
+                val = fmaf(__uint_as_float(v[j + i]), ln_a, fmaf(ln_b, c1sm[c + j + i], bsm[c + j + i]));
+                gate = fmaf(__uint_as_float(v[16 + j + i]), ln_a, fmaf(ln_b, c1sm[c + 16 + j + i], bsm[c + 16 + j + i]));
+              }
               f[i] = val * tf::gelu_tanh_f(gate);
             }
             __half2 hh = __floats2half2_rn(f[0], f[1]);
@@ -486,14 +524,27 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float f[32];
           const __half2* r2 = reinterpret_cast<const __half2*>(rr);
           const float4* b4 = reinterpret_cast<const float4*>(bsm + c);   // 128-bit broadcast reads
+          if (ln) {
+            const float4* c4 = reinterpret_cast<const float4*>(c1sm + c);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = b4[j >> 2];
-            const float2 r0 = __half22float2(r2[j >> 1]), r1 = __half22float2(r2[(j >> 1) + 1]);
-            f[j] = __uint_as_float(v[j]) + bv.x + r0.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + bv.y + r0.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + bv.z + r1.x;
-            f[j + 3] = __uint_as_float(v[j + 3]) + bv.w + r1.y;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = b4[j >> 2], cv = c4[j >> 2];
+              const float2 r0 = __half22float2(r2[j >> 1]), r1 = __half22float2(r2[(j >> 1) + 1]);
+              f[j] = fmaf(__uint_as_float(v[j]), ln_a, fmaf(ln_b, cv.x, bv.x)) + r0.x;
+              f[j + 1] = fmaf(__uint_as_float(v[j + 1]), ln_a, fmaf(ln_b, cv.y, bv.y)) + r0.y;
+              f[j + 2] = fmaf(__uint_as_float(v[j + 2]), ln_a, fmaf(ln_b, cv.z, bv.z)) + r1.x;
+              f[j + 3] = fmaf(__uint_as_float(v[j + 3]), ln_a, fmaf(ln_b, cv.w, bv.w)) + r1.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = b4[j >> 2];
+              const float2 r0 = __half22float2(r2[j >> 1]), r1 = __half22float2(r2[(j >> 1) + 1]);
+              f[j] = __uint_as_float(v[j]) + bv.x + r0.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + bv.y + r0.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + bv.z + r1.x;
+              f[j + 3] = __uint_as_float(v[j + 3]) + bv.w + r1.y;
+            }
           }
           if (out_f32) {
 #pragma unroll
@@ -509,6 +560,17 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
               h[j] = *reinterpret_cast<uint32_t*>(&hh);
               if (gn && m_own < 0) h[j] = 0u;   // rows outside the tensor (clipped by the store) must not count
+            }
+            if (rowst && m_own >= 0 && n_tile + c < p.N) {
+              // statistics of this row's 32 rounded values (a LayerNorm folded into the consumer GEMM reads them)
+              float rs_s = 0.f, rs_q = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+                rs_s += hv.x + hv.y;
+                rs_q = fmaf(hv.x, hv.x, fmaf(hv.y, hv.y, rs_q));
+              }
+              p.row_stats[(size_t)m_own * p.rs_ld + ((n_tile + c) >> 5)] = make_float2(rs_s, rs_q);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -819,11 +881,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (!tmA2p) p.kb_main = p.k_blocks;
   static bool attr_set = false;
   if (!attr_set) {
-    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   const int stage_bytes = A_STAGE_BYTES + p.bn * 128 / p.ctas;
+  const bool extras = p.row_stats != nullptr || p.ln_stats != nullptr;
+  const int kEpiBytes = epi_bytes(extras);
   int stages = (kSmemBudget - 2048 - kEpiBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (g_max_stages >= 2 && stages > g_max_stages) stages = g_max_stages;
@@ -841,11 +907,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
     const int max_pairs = tf_num_sms() / 2;
     const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-    (void)tf_launch_pdl_cluster(tf_gemm_kernel<2>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, tmA2, p);
+    if (extras) (void)tf_launch_pdl_cluster(tf_gemm_kernel<2, true>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, tmA2, p);
+    else (void)tf_launch_pdl_cluster(tf_gemm_kernel<2, false>, dim3(grid), dim3(kThreads), smem, stream, 2u, tmA, tmB, tmC, tmA2, p);
   } else {
     const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
     const int grid = total_tiles < tf_num_sms() ? total_tiles : tf_num_sms();
-    TF_LAUNCH(tf_gemm_kernel<1>, grid, kThreads, smem, stream, tmA, tmB, tmC, tmA2, p);
+    if (extras) TF_LAUNCH((tf_gemm_kernel<1, true>), grid, kThreads, smem, stream, tmA, tmB, tmC, tmA2, p);
+    else TF_LAUNCH((tf_gemm_kernel<1, false>), grid, kThreads, smem, stream, tmA, tmB, tmC, tmA2, p);
   }
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
@@ -936,7 +1004,9 @@ static int gn_check(const void* gn_stats, int gn_unit, int gn_hw, int M, int N, 
 
 static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M,
                            int N, int K, const float* bias, const void* residual, int ldr, int flags,
-                           void* workspace, size_t ws_bytes, void* stream, void* gn_stats, int gn_unit, int gn_hw) {
+                           void* workspace, size_t ws_bytes, void* stream, void* gn_stats, int gn_unit, int gn_hw,
+                           void* row_stats = nullptr, const void* ln_stats = nullptr, int ln_chunks = 0,
+                           const float* ln_c1 = nullptr, float ln_eps = 0.f) {
   TF_CHECK_ARG(A && W && out, "tf_gemm_f16: null pointer");
   TF_CHECK_ARG(M > 0 && N > 0 && K > 0, "tf_gemm_f16: bad dims M=%d N=%d K=%d", M, N, K);
   TF_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "tf_gemm_f16: K, lda, ldw must be multiples of 8");
@@ -956,7 +1026,16 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   p.gn_stats = reinterpret_cast<float2*>(gn_stats); p.gn_unit = gn_unit; p.gn_hw = gn_hw;
   p.m_tiles = ceil_div_i(M, BM);
   p.k_blocks = ceil_div_i(K, BK);
-  const bool allow_split = !(flags & TF_EPI_GEGLU) && workspace != nullptr;
+  if (row_stats)
+    TF_CHECK_ARG(N % 32 == 0 && !(flags & (TF_EPI_GEGLU | TF_EPI_OUT_F32)),
+                 "tf_gemm_ex_f16: row statistics need N %% 32 == 0 and the plain fp16 epilogue (N=%d)", N);
+  if (ln_stats)
+    TF_CHECK_ARG(ln_c1 != nullptr && ln_chunks > 0 && K == 32 * ln_chunks,
+                 "tf_gemm_ex_f16: LayerNorm fold needs c1 and statistics over exactly K = %d columns (got %d chunks)", K, ln_chunks);
+  p.row_stats = reinterpret_cast<float2*>(row_stats); p.rs_ld = N / 32;
+  p.ln_stats = reinterpret_cast<const float2*>(ln_stats); p.ln_np = ln_chunks; p.ln_c1 = ln_c1; p.ln_eps = ln_eps;
+  // the split-K fold kernels know neither trick: these launches keep the whole K range in one CTA
+  const bool allow_split = !(flags & TF_EPI_GEGLU) && workspace != nullptr && !row_stats && !ln_stats;
   const int klass = (flags & 3) | (gn_stats ? 4 : 0) | (residual ? 8 : 0);
   TileChoice tc = choose_tiles(p.m_tiles, N, p.k_blocks, flags, allow_split, ws_bytes, M, g_force_bn,
                                g_force_splits, gn_stats ? lcm_i(32, gn_unit) : 32, TuneKey(0, M, N, K, klass));
@@ -1014,6 +1093,14 @@ extern "C" int tf_gemm_f16(const void* A, int lda, const void* W, int ldw, void*
                            const float* bias, const void* residual, int ldr, int flags, void* workspace,
                            size_t ws_bytes, void* stream) {
   return gemm_impl(A, lda, W, ldw, out, ldc, M, N, K, bias, residual, ldr, flags, workspace, ws_bytes, stream, nullptr, 0, 0);
+}
+
+extern "C" int tf_gemm_ex_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M, int N, int K,
+                              const float* bias, const void* residual, int ldr, int flags, void* workspace,
+                              size_t ws_bytes, const tf_gemm_extras* ex, void* stream) {
+  if (!ex) return gemm_impl(A, lda, W, ldw, out, ldc, M, N, K, bias, residual, ldr, flags, workspace, ws_bytes, stream, nullptr, 0, 0);
+  return gemm_impl(A, lda, W, ldw, out, ldc, M, N, K, bias, residual, ldr, flags, workspace, ws_bytes, stream, ex->gn_stats,
+                   ex->gn_unit, ex->gn_rows_per_image, ex->row_stats_out, ex->ln_stats, ex->ln_chunks, ex->ln_c1, ex->ln_eps);
 }
 
 extern "C" int tf_gemm_gn_f16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, int M, int N, int K,

@@ -28,7 +28,22 @@ class GEGLU:
         self._run(ctx, a.data_ptr(), a.shape[1], a.shape[0], out.data_ptr())
         return out.to(F32).reshape(*x.shape[:-1], self.dim_out)
 
-    def _run(self, ctx, a_ptr, lda, M, out_ptr):
+    def _packed_ln(self, norm):
+        """The projection with the preceding LayerNorm folded in, in the TF_EPI_GEGLU row order: (W', c1, c2)."""
+        def build():
+            wf, c1, c2 = packing.ln_fold(self.proj.weight.to(packing.F16), norm.weight, norm.bias, self.proj.bias)
+            wp, bp = packing.geglu_pack(wf, c2)
+            _, c1p = packing.geglu_pack(wf, c1)
+            return wp, c1p, bp
+        return packing.cached(self, "geglu_ln", (self.proj.weight, self.proj.bias, norm.weight, norm.bias), build)
+
+    def _run(self, ctx, a_ptr, lda, M, out_ptr, ln=None):
+        if ln is not None:
+            w, c1, c2 = self._packed_ln(ln[1])
+            K = w.shape[1]
+            ctx.gemm(a_ptr, lda, M, K, w.data_ptr(), 2 * self.dim_out, out_ptr, self.dim_out, bias=c2.data_ptr(),
+                     flags=b200.TF_EPI_GEGLU, ln=(ln[0], K // 32, c1.data_ptr(), float(ln[1].eps.reshape(-1)[0])))
+            return
         w, b = self._packed()
         K = w.shape[1]
         ctx.gemm(a_ptr, lda, M, K, w.data_ptr(), 2 * self.dim_out, out_ptr, self.dim_out,
@@ -48,11 +63,11 @@ class FeedForward:
         return self.net[2](h)
 
     # fast path: h (M, dim) fp16 in place:  h <- Linear(GEGLU(xn)) + h
-    def _run(self, ctx, xn_ptr, h_ptr, M, dim):
+    def _run(self, ctx, xn_ptr, h_ptr, M, dim, ln=None):
         inner = self.net[0].dim_out
         mark = ctx.arena.mark()
         g_ptr = ctx.arena.alloc(2 * M * inner)
-        self.net[0]._run(ctx, xn_ptr, dim, M, g_ptr)
+        self.net[0]._run(ctx, xn_ptr, dim, M, g_ptr, ln=ln)
         w, b = self.net[2]._packed()
         ctx.gemm(g_ptr, inner, M, inner, w.data_ptr(), dim, h_ptr, dim, bias=b.data_ptr() if b is not None else None,
                  residual_ptr=h_ptr, ldr=dim)

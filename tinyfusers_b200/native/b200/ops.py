@@ -19,6 +19,12 @@ c_int, c_size_t, c_void_p, c_float, c_longlong = (ctypes.c_int, ctypes.c_size_t,
                                                   ctypes.c_float, ctypes.c_longlong)
 _P = c_void_p
 
+class GemmExtras(ctypes.Structure):
+    """tf_gemm_extras (include/tinyfusers_b200.h): optional fused extras of tf_gemm_ex_f16."""
+    _fields_ = [("gn_stats", c_void_p), ("gn_unit", c_int), ("gn_rows_per_image", c_int), ("row_stats_out", c_void_p),
+                ("ln_stats", c_void_p), ("ln_chunks", c_int), ("ln_c1", c_void_p), ("ln_eps", c_float)]
+
+
 # name -> (restype, argtypes). Keep in sync with include/tinyfusers_b200.h (tests/test_abi.py checks it).
 _SIGNATURES = {
     "tf_version": (c_int, []),
@@ -38,6 +44,8 @@ _SIGNATURES = {
                             _P, c_size_t, _P]),
     "tf_conv2d_nhwc_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
                                    _P, _P, c_int, c_int, _P, c_size_t, _P]),
+    "tf_gemm_ex_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
+                               _P, c_size_t, ctypes.POINTER(GemmExtras), _P]),
     "tf_gemm_gn_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int,
                                _P, c_size_t, _P, c_int, c_int, _P]),
     "tf_conv2d_nhwc_gn_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,

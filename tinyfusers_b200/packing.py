@@ -90,3 +90,17 @@ def geglu_pack(w, b):
     wp = w[perm].to(F16).contiguous()
     bp = None if b is None else b.detach()[perm].to(F32).contiguous()
     return wp, bp
+
+
+def ln_fold(w_packed, gamma, beta, bias=None):
+    """LayerNorm folded into a Linear that consumes it (tf_gemm_ex_f16): W' = W diag(gamma) (fp16), c1[n] = sum_k W'[n,k]
+    (from the ROUNDED W', fp32), c2 = W beta (+ bias). `w_packed` is the already packed (rows padded / permuted) fp16 weight."""
+    wf = w_packed.detach().to(F32)
+    g = gamma.detach().to(F32).to(wf.device)
+    b = beta.detach().to(F32).to(wf.device)
+    wp = (wf * g[None, :]).to(F16).contiguous()
+    c1 = wp.to(F32).sum(dim=1).contiguous()
+    c2 = wf @ b
+    if bias is not None:
+        c2 = c2 + bias.detach().to(F32)
+    return wp, c1, c2.contiguous()

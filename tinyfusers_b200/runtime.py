@@ -13,7 +13,9 @@ import os
 
 import torch
 
-from .native.b200.ops import b200
+import ctypes
+
+from .native.b200.ops import GemmExtras, b200
 
 F16 = torch.float16
 F32 = torch.float32
@@ -126,6 +128,11 @@ class Context:
         self.context = None        # Act view of the zero-padded fp16 prompt context (B, Tpad, 768)
         self.context_tokens = 0
         self.fuse_gn = os.environ.get("TINYFUSERS_B200_FUSE_GN", "1") != "0"
+        # LayerNorm folded into the consuming GEMM (row statistics from the producing GEMM's epilogue). Correct and tested,
+        # but measured a net loss on the SD1.5 step at batch 2 (259.4 vs 261.0 steps/s: the producers' statistics and the
+        # consumers' per-tile fold cost the GEMM epilogues 0.13 ms, the 27 removed LayerNorm launches save 0.09 ms), so it
+        # is opt-in: TINYFUSERS_B200_FUSE_LN=1.
+        self.fuse_ln = os.environ.get("TINYFUSERS_B200_FUSE_LN", "0") == "1"
         self.ctx_kv = None         # dict: id(CrossAttention) -> (k_ptr, ldk, vt_ptr, ldvt) projected once per forward
         self.gn_fuse_max_hw = 16384
 
@@ -173,22 +180,31 @@ class Context:
         return self.dry or (self.only is not None and kind not in self.only)
 
     def gemm(self, a_ptr, lda, M, K, w, N, out_ptr, ldc, bias=None, residual_ptr=None, ldr=0, flags=0, ldw=None, gn=None,
-             w_static=True):
+             w_static=True, row_stats=None, ln=None):
         """gn = (stats_ptr, unit, rows_per_image): also emit the GroupNorm statistics of the output.
+        row_stats = ptr: also emit {sum, sumsq} per 32-column chunk of every output row (float2 [M][N/32]).
+        ln = (stats_ptr, chunks, c1_ptr, eps): LayerNorm folded onto A (see tf_gemm_ex_f16); `w` / `bias` are the folded ones.
         w_static: `w` is a packed weight (packing.cached synchronises after building it), so the kernel may fetch it
         before waiting for the preceding kernel; False for swapped-operand calls whose W slot holds an activation."""
         if self.skip("gemm"):
             return
         if w_static:
             flags |= b200.TF_GEMM_W_STATIC
-        if gn is None:
-            fn = lambda: b200.tf_gemm_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
+        ldw = K if ldw is None else ldw
+        if row_stats is not None or ln is not None:
+            ex = GemmExtras(gn[0] if gn else None, gn[1] if gn else 0, gn[2] if gn else 0, row_stats,
+                            ln[0] if ln else None, ln[1] if ln else 0, ln[2] if ln else None, ln[3] if ln else 0.0)
+            fn = lambda: b200.tf_gemm_ex_f16(a_ptr, lda, w, ldw, out_ptr, ldc, M, N, K, bias, residual_ptr, ldr, flags,
+                                             self.ws.data_ptr(), self.ws_bytes, ctypes.byref(ex), stream_ptr())
+        elif gn is None:
+            fn = lambda: b200.tf_gemm_f16(a_ptr, lda, w, ldw, out_ptr, ldc, M, N, K, bias,
                                           residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, stream_ptr())
         else:
-            fn = lambda: b200.tf_gemm_gn_f16(a_ptr, lda, w, K if ldw is None else ldw, out_ptr, ldc, M, N, K, bias,
+            fn = lambda: b200.tf_gemm_gn_f16(a_ptr, lda, w, ldw, out_ptr, ldc, M, N, K, bias,
                                              residual_ptr, ldr, flags, self.ws.data_ptr(), self.ws_bytes, gn[0], gn[1], gn[2],
                                              stream_ptr())
-        st = self._timed(("gemm", M, N, K, flags & 3, residual_ptr is not None, gn[1] if gn else 0, gn[2] if gn else 0), fn)
+        st = self._timed(("gemm", M, N, K, flags & 3, residual_ptr is not None, gn[1] if gn else 0, gn[2] if gn else 0,
+                          (1 if row_stats is not None else 0) | (2 if ln is not None else 0)), fn)
         b200.check(st, "tf_gemm_f16")
 
     def conv3x3(self, x, w, cout, out, bias=None, residual=None, stride=1, flags=0, gn=None, w_static=True):

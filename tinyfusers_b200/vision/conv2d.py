@@ -29,7 +29,7 @@ def _check_supported(ksize, stride, padding, dilation):
     return k[0], s[0]
 
 
-def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=None, flags=0, w_static=True):
+def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=None, flags=0, w_static=True, row_stats=None):
     # the output's GroupNorm statistics are produced by this launch when `out` carries a (single-part) buffer
     gn = None
     if out.gn is not None and len(out.gn) == 1 and out.gn[0][0] == 0 and out.gn[0][1] == cout_p and flags == 0:
@@ -41,7 +41,7 @@ def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=
         ctx.gemm(x.ptr, x.stride, x.rows, x.c, w_packed.data_ptr(), cout_p, out.ptr, out.stride, bias=bias_ptr,
                  residual_ptr=residual.ptr if residual is not None else None,
                  ldr=residual.stride if residual is not None else 0, flags=flags,
-                 gn=(gn[0], gn[1], out.h * out.w) if gn else None, w_static=w_static)
+                 gn=(gn[0], gn[1], out.h * out.w) if gn else None, w_static=w_static, row_stats=row_stats)
 
 
 def conv_2d(X_gpu, W_gpu, padding, stride, dilation):
@@ -112,14 +112,14 @@ class Conv2d:
         return act_to_nchw(out, O)
 
     # fast path: NHWC fp16 Act -> NHWC fp16 (or fp32 with TF_EPI_OUT_F32) Act, epilogue fused
-    def _run(self, ctx, x, out, residual=None, bias_ptr="own", flags=0):
+    def _run(self, ctx, x, out, residual=None, bias_ptr="own", flags=0, row_stats=None):
         k, s = self._geometry()
         w, b = self._packed()
         if bias_ptr == "own":
             bias_ptr = b.data_ptr() if b is not None else None
         if x.c != w.shape[-1] and k == 3:
             raise RuntimeError(f"Conv2d fast path: activation has {x.c} channels, packed weight expects {w.shape[-1]}")
-        _conv_act(ctx, x, w, w.shape[0], k, s, out, bias_ptr, residual, flags)
+        _conv_act(ctx, x, w, w.shape[0], k, s, out, bias_ptr, residual, flags, row_stats=row_stats if k == 1 else None)
         return out
 
     # Cin = 4 input convolution straight from the fp32 NCHW latent (UNet conv_in)
