@@ -93,8 +93,9 @@ int tf_gn_stats_supported(int NI, int Ho, int Wo, int C, int gn_unit, int is_con
 
 /* tf_gemm_f16 with optional fused extras (NULL pointers = off):
  *   gn_stats / gn_unit / gn_rows_per_image : as tf_gemm_gn_f16;
- *   row_stats_out : float2 [M][N/32] = {sum, sumsq} of the rounded fp16 output over each 32-column chunk of each row
- *                   (N % 32 == 0, plain fp16 epilogue, no split-K) - the statistics a LayerNorm over the row needs;
+ *   row_stats_out : float2 buffer of >= M * (N/32) entries; receives {sum, sumsq} of every output row per N-tile of this
+ *                   launch (the library remembers the per-row entry count for the consumer; N % 32 == 0, plain fp16
+ *                   epilogue, no split-K) - the statistics a LayerNorm over the row needs;
  *   ln_stats / ln_chunks / ln_c1 / ln_eps : LayerNorm FOLDED onto the A operand. A holds the un-normalised rows (K = 32 *
  *                   ln_chunks columns), ln_stats is the row_stats_out of the GEMM that produced A, W must have been
  *                   pre-multiplied by gamma (W' = W diag(gamma)), ln_c1[n] = sum_k W'[n,k], and `bias` must carry

@@ -153,12 +153,13 @@ def test_spatial_transformer_with_layernorm_folded_into_gemms(oracle):
     with torch.no_grad():
         ref = oracle.spatial_transformer(sd, "st", x, c, 8, 80, True)
     ctx = standalone_context()
-    plain = st(x.cuda(), c.cuda())
-    old = ctx.fuse_ln
-    ctx.fuse_ln = True
+    old = (ctx.fuse_ln, ctx.fuse_ln_all)
     try:
+        ctx.fuse_ln, ctx.fuse_ln_all = False, False
+        plain = st(x.cuda(), c.cuda())
+        ctx.fuse_ln, ctx.fuse_ln_all = True, True      # all three norms folded (norm3 into the GEGLU projection too)
         folded = st(x.cuda(), c.cuda())
     finally:
-        ctx.fuse_ln = old
+        ctx.fuse_ln, ctx.fuse_ln_all = old
     assert rel_err(plain, ref) < 1e-2 and rel_err(folded, ref) < 1e-2
     assert rel_err(folded, plain) < 5e-3 and not torch.equal(folded, plain)     # a different path really ran

@@ -157,6 +157,12 @@ class BasicTransformerBlock:
             # Measured per shape (tools/shape_table.py): the fold costs the consumer's epilogue a per-tile statistics fold
             # plus two FMAs per element, which pays for the narrow Q projection everywhere (norm2) and for the [Q|K|V]
             # projection below 4096 tokens (norm1), but not for the epilogue-bound GEGLU projection (norm3 stays a kernel).
+            if ctx.fuse_ln_all:
+                self.attn1._run(ctx, h_ptr, B, T, C, h_ptr, ln=(h_stats, self.norm1), h_stats=h_stats)
+                self.attn2._run(ctx, h_ptr, B, T, C, h_ptr, context=context, ln=(h_stats, self.norm2), h_stats=h_stats)
+                self.ff._run(ctx, h_ptr, h_ptr, B * T, C, ln=(h_stats, self.norm3))
+                ctx.arena.release(mark)
+                return
             xn = None
             if fold_norm1(B * T):
                 self.attn1._run(ctx, h_ptr, B, T, C, h_ptr, ln=(h_stats, self.norm1), h_stats=h_stats)
@@ -221,7 +227,7 @@ class SpatialTransformer:
         h_stats = None
         if ctx.fuse_ln and not ctx.ln_strided and C % 32 == 0:
             h_stats = ctx.arena.alloc(8 * B * T * (C // 32))     # float2 per 32-column chunk of every token row
-        self.proj_in._run(ctx, hn, h, row_stats=h_stats if fold_norm1(B * T) else None)
+        self.proj_in._run(ctx, hn, h, row_stats=h_stats if (fold_norm1(B * T) or ctx.fuse_ln_all) else None)
         for block in self.transformer_blocks:
             block._run(ctx, h.ptr, B, T, C, context, h_stats=h_stats)
         self.proj_out._run(ctx, h, out, residual=x)

@@ -82,13 +82,13 @@ struct GemmParams {
   float2* gn_stats;
   int gn_unit;      // channels per statistics unit; bn % gn_unit == 0
   int gn_hw;        // rows (pixels) per image; % 32 == 0
-  // optional per-row statistics of the OUTPUT (plain fp16 epilogue): row_stats[m][chunk] = {sum, sumsq} of the rounded
-  // values of columns [32*chunk, 32*chunk + 32) - what a LayerNorm folded into the consuming GEMM needs
+  // optional per-row statistics of the OUTPUT (plain fp16 epilogue): row_stats[m][n_tile] = {sum, sumsq} of row m over the
+  // columns of N-tile n_tile - what a LayerNorm folded into the consuming GEMM needs
   float2* row_stats;
-  int rs_ld;        // chunks per row = N / 32
+  int rs_ld;        // entries per row = this launch's n_tiles
   // optional LayerNorm folded onto the A operand: A holds the UN-normalised rows, W was pre-multiplied by gamma, and
   //   out = rstd[m] * (acc - mean[m] * c1[n]) + bias[n]      (c1[n] = sum_k W'[n,k]; bias carries W.beta)
-  // with mean / rstd of row m folded from ln_stats[m][0..ln_np) (the producer's row_stats), C = ln_np * 32 columns
+  // with mean / rstd of row m folded from ln_stats[m][0..ln_np) (the producer's row_stats) over K columns
   const float2* ln_stats;
   int ln_np;
   const float* ln_c1;
@@ -413,6 +413,7 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t swz = out_f32 ? (uint32_t)(lane & 7) : (geglu ? (uint32_t)((lane >> 2) & 1) : (uint32_t)((lane >> 1) & 3));
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t stg_tile = 0;   // tiles this warp has finished (row-statistics exchange slot parity)
     const uint32_t tempty_remote0 = k2 ? tf::mapa_shared(tempty_bar(0), 0) : 0u;   // the leader's barriers
     const uint32_t tempty_remote1 = k2 ? tf::mapa_shared(tempty_bar(1), 0) : 0u;
     for (int t = t_first; t < total_tiles; t += t_step) {
@@ -441,14 +442,16 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bsm[j * 32 + lane] = (use_bias && j * 32 < p.bn && nn < p.N) ? __ldg(p.bias + nn) : 0.f;
         if (ln) c1sm[j * 32 + lane] = (j * 32 < p.bn && nn < p.N) ? __ldg(p.ln_c1 + nn) : 0.f;
       }
-      // LayerNorm fold: this row's mean / rstd from the producer's per-chunk statistics (fixed order), as the two
+      float rs_s = 0.f, rs_q = 0.f;   // row statistics of this tile (kX, producer side)
+      // LayerNorm fold: this row's mean / rstd from the producer's per-tile statistics (fixed order), as the two
       // coefficients of  out = ln_a * acc + ln_b * c1 + bias
       float ln_a = 1.f, ln_b = 0.f;
       if (ln && m_own >= 0) {
         const float2* rs = p.ln_stats + (size_t)m_own * p.ln_np;
         float sm = 0.f, sq = 0.f;
+#pragma unroll 4
         for (int i = 0; i < p.ln_np; ++i) { const float2 t2 = __ldg(rs + i); sm += t2.x; sq += t2.y; }
-        const float inv_c = 1.0f / (32.0f * (float)p.ln_np);
+        const float inv_c = 1.0f / (float)p.K;
         const float mean = sm * inv_c;
         const float rstd = rsqrtf(fmaxf(sq * inv_c - mean * mean, 0.f) + p.ln_eps);
         ln_a = rstd;
@@ -561,16 +564,16 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               h[j] = *reinterpret_cast<uint32_t*>(&hh);
               if (gn && m_own < 0) h[j] = 0u;   // rows outside the tensor (clipped by the store) must not count
             }
-            if (rowst && m_own >= 0 && n_tile + c < p.N) {
-              // statistics of this row's 32 rounded values (a LayerNorm folded into the consumer GEMM reads them)
-              float rs_s = 0.f, rs_q = 0.f;
+            if (rowst) {
+              // running {sum, sumsq} of this row over the chunks this warp drains (columns beyond N contribute exact
+              // zeros: zero weights rows / clipped); the fp32 values before rounding are used - the difference to the
+              // rounded ones is far below the statistics' own rounding
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-                rs_s += hv.x + hv.y;
-                rs_q = fmaf(hv.x, hv.x, fmaf(hv.y, hv.y, rs_q));
+              for (int j = 0; j < 32; ++j) {
+                const float fv = (n_tile + c + j < p.N) ? f[j] : 0.f;
+                rs_s += fv;
+                rs_q = fmaf(fv, fv, rs_q);
               }
-              p.row_stats[(size_t)m_own * p.rs_ld + ((n_tile + c) >> 5)] = make_float2(rs_s, rs_q);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -621,6 +624,19 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (t == t_first && threadIdx.x == 64) TF_STAMP(c == c_first ? 10 : 12);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rr[j] = rn[j];
+      }
+      if (rowst) {
+        // the quarter's two warps drained alternate chunks of the same 32 rows: exchange through this warp's (otherwise
+        // unused: a launch is producer or consumer, never both) c1 slot, alternating halves per tile so that a warp running
+        // ahead cannot overwrite what its partner still has to read; warp hsel == 0 publishes the sum
+        float2* mine = reinterpret_cast<float2*>(c1sm) + (stg_tile & 1u) * 32;
+        mine[lane] = make_float2(rs_s, rs_q);
+        asm volatile("bar.sync %0, 64;" ::"r"(5 + q) : "memory");
+        if (hsel == 0 && m_own >= 0) {
+          const float2 other = (reinterpret_cast<const float2*>(c1sm + 4 * kEpiBiasFloats) + (stg_tile & 1u) * 32)[lane];
+          p.row_stats[(size_t)m_own * p.rs_ld + nt] = make_float2(rs_s + other.x, rs_q + other.y);
+        }
+        ++stg_tile;
       }
       if (gn) {
         // fold the quarter's column sums into statistics units and publish slot (image, 32-row block); the two
@@ -812,6 +828,7 @@ typedef std::tuple<int, int, int, int, int> TuneKey;
 static std::map<TuneKey, TileChoice>* g_tune = nullptr;
 static std::mutex g_tune_mutex;
 static TileChoice g_last_choice{0, 0, 0};
+static std::map<const void*, int> g_rowstats_np;   // row-statistics buffer -> entries per row written by its producer
 
 static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool allow_split,
                                size_t ws_bytes, int M, int force_bn, int force_splits, int bn_mult, const TuneKey& key) {
@@ -1030,10 +1047,17 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
     TF_CHECK_ARG(N % 32 == 0 && !(flags & (TF_EPI_GEGLU | TF_EPI_OUT_F32)),
                  "tf_gemm_ex_f16: row statistics need N %% 32 == 0 and the plain fp16 epilogue (N=%d)", N);
   if (ln_stats)
-    TF_CHECK_ARG(ln_c1 != nullptr && ln_chunks > 0 && K == 32 * ln_chunks,
+    TF_CHECK_ARG(ln_c1 != nullptr && (ln_chunks == 0 || K == 32 * ln_chunks),
                  "tf_gemm_ex_f16: LayerNorm fold needs c1 and statistics over exactly K = %d columns (got %d chunks)", K, ln_chunks);
-  p.row_stats = reinterpret_cast<float2*>(row_stats); p.rs_ld = N / 32;
-  p.ln_stats = reinterpret_cast<const float2*>(ln_stats); p.ln_np = ln_chunks; p.ln_c1 = ln_c1; p.ln_eps = ln_eps;
+  p.row_stats = reinterpret_cast<float2*>(row_stats);
+  p.ln_stats = reinterpret_cast<const float2*>(ln_stats); p.ln_c1 = ln_c1; p.ln_eps = ln_eps;
+  if (ln_stats) {
+    // entries per row = the N-tile count of the launch that produced them (remembered per buffer at that launch)
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    auto it = g_rowstats_np.find(ln_stats);
+    TF_CHECK_ARG(it != g_rowstats_np.end(), "tf_gemm_ex_f16: ln_stats was not produced by a row_stats_out launch of this library");
+    p.ln_np = it->second;
+  }
   // the split-K fold kernels know neither trick: these launches keep the whole K range in one CTA
   const bool allow_split = !(flags & TF_EPI_GEGLU) && workspace != nullptr && !row_stats && !ln_stats;
   const int klass = (flags & 3) | (gn_stats ? 4 : 0) | (residual ? 8 : 0);
@@ -1048,6 +1072,11 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   p.out = out; p.ldc = ldc; p.bias = bias;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   p.flags = flags;
+  if (row_stats) {
+    p.rs_ld = p.n_tiles;
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    g_rowstats_np[row_stats] = p.n_tiles;
+  }
 
   CUtensorMap tmA, tmB;
   {

@@ -129,10 +129,11 @@ class Context:
         self.context_tokens = 0
         self.fuse_gn = os.environ.get("TINYFUSERS_B200_FUSE_GN", "1") != "0"
         # LayerNorm folded into the consuming GEMM (row statistics from the producing GEMM's epilogue). Correct and tested,
-        # but measured a net loss on the SD1.5 step at batch 2 (259.4 vs 261.0 steps/s: the producers' statistics and the
-        # consumers' per-tile fold cost the GEMM epilogues 0.13 ms, the 27 removed LayerNorm launches save 0.09 ms), so it
-        # is opt-in: TINYFUSERS_B200_FUSE_LN=1.
-        self.fuse_ln = os.environ.get("TINYFUSERS_B200_FUSE_LN", "0") == "1"
+        # but break-even at best on the SD1.5 step at batch 2 (260.8 vs 261.0 steps/s: the producers' statistics and the
+        # consumers' per-tile fold cost the GEMM epilogues 0.10 ms, the 27 removed LayerNorm launches save 0.09 ms), so it
+        # is opt-in: TINYFUSERS_B200_FUSE_LN=1 (norm2 + sub-4096-token norm1) or =2 (all three norms).
+        self.fuse_ln = os.environ.get("TINYFUSERS_B200_FUSE_LN", "0") in ("1", "2")
+        self.fuse_ln_all = os.environ.get("TINYFUSERS_B200_FUSE_LN", "0") == "2"   # also norm1 at 4096 tokens and norm3 (GEGLU)
         self.ctx_kv = None         # dict: id(CrossAttention) -> (k_ptr, ldk, vt_ptr, ldvt) projected once per forward
         self.gn_fuse_max_hw = 16384
 
