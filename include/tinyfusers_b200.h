@@ -188,8 +188,9 @@ int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void*
                      long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
                      int Tq, int Tk, int Tk_pad, int d, int dp, float scale, void* stream);
 /* Same attention with V in its NATURAL layout: v is (B*Tk_pad, ldv), head h at columns [h*dvp, (h+1)*dvp), dvp = head
- * dim padded to a multiple of 64 with zero columns - what a fused [Q | K | V] projection GEMM writes directly, so no
- * transposed copy of V is produced by anyone (V tiles are the MN-major B operand of O += P V). causal: 0 | 1. */
+ * dim padded with zero columns to a multiple of 16 (tiles use 32-byte swizzle atoms) or of 64 (128-byte atoms) - what a
+ * fused [Q | K | V] projection GEMM writes directly, so no transposed copy of V is produced by anyone (V tiles are the
+ * MN-major B operand of O += P V). causal: 0 | 1. */
 int tf_attention_v_f16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                        long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH, int Tq,
                        int Tk, int Tk_pad, int d, int dp, int dvp, float scale, int causal, void* stream);

@@ -11,11 +11,12 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _run(B, NH, Tq, Tk, d, causal=False, seed=0):
+def _run(B, NH, Tq, Tk, d, causal=False, seed=0, pad64=False):
     from tinyfusers_b200.native.b200.ops import b200
+    from tinyfusers_b200.attention.attention import _pad64
     b200.init(0)
     dp = (d + 15) // 16 * 16
-    dvp = (d + 63) // 64 * 64
+    dvp = (d + 63) // 64 * 64 if pad64 else _pad64(d)     # 128-byte-atom tiles, or the layout the model uses
     Tkp = (Tk + 7) // 8 * 8
     g = torch.Generator().manual_seed(seed + Tq + d)
     q = torch.randn(B, Tq, NH, d, generator=g)
@@ -39,13 +40,15 @@ def _run(B, NH, Tq, Tk, d, causal=False, seed=0):
                                           (2, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (2, 8, 256, 77, 160),
                                           (1, 8, 576, 576, 80), (1, 3, 200, 333, 64)])
 def test_natural_v_matches_torch(B, NH, Tq, Tk, d):
-    out, ref = _run(B, NH, Tq, Tk, d)
-    assert rel_err(out, ref) < 3e-3
+    for pad64 in (False, True):
+        out, ref = _run(B, NH, Tq, Tk, d, pad64=pad64)
+        assert rel_err(out, ref) < 3e-3, pad64
 
 
 def test_natural_v_three_ctas_per_sm_variant():
-    out, ref = _run(8, 8, 4096, 4096, 40)     # 2048 CTAs -> 64-key blocks, 3 CTAs / SM, L overlaid on O's pad columns
-    assert rel_err(out, ref) < 3e-3
+    for pad64 in (False, True):               # 2048 CTAs -> 64-key blocks, 3 CTAs / SM (pad64: L overlaid on O's pad columns)
+        out, ref = _run(8, 8, 4096, 4096, 40, pad64=pad64)
+        assert rel_err(out, ref) < 3e-3, pad64
 
 
 @pytest.mark.parametrize("T,NH,d", [(77, 12, 64), (200, 4, 64), (640, 2, 40)])

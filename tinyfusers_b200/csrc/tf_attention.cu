@@ -33,6 +33,7 @@ constexpr int BQ = 128;
 struct AttnParams {
   int B, NH, Tq, Tk, Tk_pad, d, dp;
   int dov;      // O columns in TMEM: dp (V^T operand), or the V head dim padded to 64 (natural-layout V operand)
+  int v_atom;   // natural-layout V: columns per swizzle atom - 64 (128-byte swizzle) or 16 (32-byte swizzle, dov % 64 != 0)
   int l_off;    // first of the 16 L (= P . 1) columns, relative to O: dov, or dov - 16 when O's zero pad columns can host them
   int ol_cols;  // columns spanned by O and L together
   int nkv;      // key blocks
@@ -79,6 +80,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   d |= (uint64_t)(1024u >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// Same operand with 32-byte swizzle atoms (16 columns): ((2,n),(8,k)):((1,LBO),(2,SBO)) - 8-row groups 256 B apart. Used
+// when the head dim is not worth padding to 64 columns (d = 40 -> 48, d = 80 -> 80).
+__device__ __forceinline__ uint64_t umma_desc_sw32_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(256u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;  // SWIZZLE_32B
   return d;
 }
 
@@ -168,9 +181,10 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tf::mbar_expect_tx(kv_full(s), k_bytes + v_bytes);
         const int key0 = b * p.Tk_pad + j * BN;
         tf::tma_load_3d(smem_k + s * k_bytes, &tmK, kv_full(s), 0, key0, h * slabs);
-        if (VNAT) {   // one (BN keys x 64 columns) box per 64-column block of the head
-          for (int nb = 0; nb < p.dov / 64; ++nb)
-            tf::tma_load_2d(smem_v + s * v_bytes + nb * (BN * 128), &tmV, kv_full(s), h * p.dov + nb * 64, key0);
+        if (VNAT) {   // one (BN keys x v_atom columns) box per column block of the head
+          const int nblk = p.dov / p.v_atom;
+          for (int nb = 0; nb < nblk; ++nb)
+            tf::tma_load_2d(smem_v + s * v_bytes + nb * (BN * p.v_atom * 2), &tmV, kv_full(s), h * p.dov + nb * p.v_atom, key0);
         } else {
 #pragma unroll
           for (int i = 0; i < BN / 64; ++i)
@@ -208,8 +222,9 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
           const uint32_t atom = k >> 2, sub = k & 3;
-          const uint64_t vdesc = VNAT ? umma_desc_sw128_mnmajor(vbase + k * 2048u, BN * 128u)   // keys 16k .. 16k+15
-                                      : tf::umma_desc_sw128_kmajor(vbase + atom * (p.dp * 128)) + 2u * sub;
+          const uint64_t vdesc = !VNAT ? tf::umma_desc_sw128_kmajor(vbase + atom * (p.dp * 128)) + 2u * sub
+                                 : (p.v_atom == 64 ? umma_desc_sw128_mnmajor(vbase + k * 2048u, BN * 128u)   // keys 16k .. 16k+15
+                                                   : umma_desc_sw32_mnmajor(vbase + k * 512u, BN * 32u));
           tf::umma_f16_ss(tmem_o, tf::umma_desc_sw128_kmajor(smem_p + atom * (BQ * 128)) + 2u * sub, vdesc, idesc_o,
                           (j > 0 || k > 0) ? 1u : 0u);
           // L += P . ones: the denominator accumulates from the SAME fp16-rounded P the numerator uses
@@ -407,7 +422,8 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
                ldk, ldvt, Tk_pad);
   TF_CHECK_ARG(ldq >= NH * dp && ldk >= NH * dp && ldvt >= (vnat ? NH * dvp : B * Tk_pad),
                "tf_attention_f16: leading dims too small");
-  if (vnat) TF_CHECK_ARG(dvp % 64 == 0 && dvp >= d && dvp <= 256, "tf_attention_v_f16: V head dim must be padded to a multiple of 64 (<= 256), got %d", dvp);
+  if (vnat) TF_CHECK_ARG(dvp % 16 == 0 && dvp >= d && dvp <= 256, "tf_attention_v_f16: V head dim must be padded to a multiple of 16 (<= 256), got %d", dvp);
+  const int v_atom = (vnat && dvp % 64 == 0) ? 64 : 16;
   TF_CHECK_ARG(out_stride_t % 8 == 0 && out_stride_h % 8 == 0 && out_stride_b % 8 == 0,
                "tf_attention_f16: output strides must be multiples of 8");
   TF_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)vt & 15) == 0 &&
@@ -443,7 +459,7 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
 
   AttnParams p{};
   p.B = B; p.NH = NH; p.Tq = Tq; p.Tk = Tk; p.Tk_pad = Tk_pad; p.d = d; p.dp = dp; p.dov = dov;
-  p.l_off = l_off; p.ol_cols = ol_cols;
+  p.l_off = l_off; p.ol_cols = ol_cols; p.v_atom = v_atom;
   p.nkv = ceil_div_i(Tk, BN);
   p.causal = causal ? 1 : 0;
   p.timeline = g_attn_timeline;
@@ -492,10 +508,10 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
   if (vnat) {
     uint64_t dims[2] = {(uint64_t)ldvt, (uint64_t)B * Tk_pad};
     uint64_t strides[1] = {(uint64_t)ldvt * 2};
-    uint32_t box[2] = {64, (uint32_t)BN};
+    uint32_t box[2] = {(uint32_t)v_atom, (uint32_t)BN};
     uint32_t es[2] = {1, 1};
     int rc = tf_encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt, dims, strides, box, es,
-                            CU_TENSOR_MAP_SWIZZLE_128B);
+                            v_atom == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
   } else {
     uint64_t dims[2] = {(uint64_t)B * Tk_pad, (uint64_t)NH * dp};

@@ -84,7 +84,7 @@ def last_choice():
 def make_case(key):
     """-> (launchers over weight copies, out tensor, table key (is_conv, M, N, K, klass), m_tiles, k_blocks, bn_mult, allow_split)"""
     if key[0] == "gemm":
-        _, M, N, K, flags, has_res, gn_unit, gn_hw = key
+        _, M, N, K, flags, has_res, gn_unit, gn_hw = key[:8]
         wbytes = N * K * 2
         copies = max(2, min(16, math.ceil(300e6 / wbytes)))
         A = torch.randn(M, K, device=dev).half()
