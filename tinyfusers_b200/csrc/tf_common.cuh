@@ -391,13 +391,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 // x * sigmoid(x)   (reference: tinyfusers/storage/tensor.py:64-70)
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// tanh-approximated GELU (reference: tinyfusers/storage/tensor.py:81-82)
+// One MUFU.TANH per value (tanh.approx.f32, max relative error 2^-11: below the fp16 rounding of every result these feed)
+// instead of MUFU.EX2 + MUFU.RCP: the GEGLU epilogue and the GroupNorm+SiLU pass are MUFU / issue bound.
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x) = 0.5 x (1 + tanh(x / 2))   (reference: tinyfusers/storage/tensor.py:64-70)
+__device__ __forceinline__ float silu_f(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx_f(hx), hx);
+}
+// tanh-approximated GELU (reference: tinyfusers/storage/tensor.py:81-82): 0.5 x (1 + tanh(0.79788456 x (1 + 0.044715 x^2)))
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  float u = x * 0.7978845608f * (1.0f + 0.044715f * x * x);
-  // tanh(u) = 1 - 2/(exp(2u)+1); saturates cleanly for |u| large
-  float t = 1.0f - 2.0f / (__expf(2.0f * u) + 1.0f);
-  return 0.5f * x * (1.0f + t);
+  const float u = x * 0.7978845608f * fmaf(0.044715f * x, x, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx_f(u), hx);
 }
 
 union Pack16 {  // 8 halfs <-> one 128-bit vector
