@@ -139,7 +139,7 @@ def tune(key, count):
     best, best_us, tried = default, base_us, 0
     for bn in range(bn_mult, 257, bn_mult):
         n_tiles = (N + bn - 1) // bn
-        if N / (n_tiles * bn) < 0.65: continue
+        if N / (n_tiles * bn) < 0.65 and bn > bn_mult: continue   # the narrowest tile is always a candidate (N = 8 conv_out)
         for ctas in (1, 2):
             if ctas == 2 and m_tiles < 2: continue
             mt = 2 * ((m_tiles + 1) // 2) if ctas == 2 else m_tiles
