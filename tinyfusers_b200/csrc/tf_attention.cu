@@ -16,12 +16,17 @@
 //   Q  : (B*Tq,      ldq)  fp16, head h at columns [h*dp, (h+1)*dp), dp = head dim padded to 16
 //                          (pad columns are exact zeros: the projection weight rows are zero-padded)
 //   K  : (B*Tk_pad,  ldk)  fp16, same head layout
-//   Vt : (NH*dp, B*Tk_pad) fp16, V transposed (tokens contiguous) — written directly by a swapped-operand GEMM
+//   V  : (B*Tk_pad,  ldv)  fp16, NATURAL layout (tf_attention_v_f16, what the models use): head h at columns
+//                          [h*dvp, (h+1)*dvp), dvp = head dim zero-padded to 64 (128-byte swizzle atoms) or 16 (32-byte
+//                          atoms); tiles are the MN-major B operand of O += P V, so the fused [Q | K | V] projection GEMM
+//                          feeds the kernel directly. With dvp - 16 >= round16(d) the L accumulator sits in O's pad columns.
+//   Vt : (NH*dp, B*Tk_pad) fp16, V transposed (tf_attention_f16 / tf_attention_causal_f16: the first layout of the round,
+//                          kept as an entry point) - K-major B operand
 //   O  : fp16, element (b,h,t,j) at b*osb + h*osh + t*ost + j, j < d. The reference's CrossAttention
 //        reshapes (B,NH,T,HS) straight to (B,T,NH*HS) (attention.py:39) — that is osb=NH*T*d, osh=T*d,
 //        ost=d; the canonical head merge is osb=T*NH*d, osh=d, ost=NH*d.
 // Q/K tiles use 32-byte swizzle slabs of 16 head-dim elements (any dp % 16 == 0 without padding to 64);
-// P and V^T use 128-byte swizzle atoms of 64 keys.
+// P and V^T use 128-byte swizzle atoms of 64 keys; natural-layout V uses (keys x 64 | 16 columns) boxes.
 #include "tf_common.cuh"
 #include "tinyfusers_b200.h"
 
