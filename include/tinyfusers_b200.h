@@ -278,6 +278,41 @@ int tf_embedding_f16(const int* ids, const float* table, const float* pos_table,
                      int vocab, void* stream);
 int tf_cast_f16_to_f32(const void* x, float* out, long long n, void* stream);
 
+/* ---- fp32 parity mode (BASELINE.json configs[0]; north star: per-op error <= 1e-5 in fp32 mode) -------------
+ * The reference computes in fp32 throughout; these are the same operators as plain-fp32 CUDA-core kernels in the
+ * reference's own layouts (NCHW / OIHW / (B,T,C)), selected with tinyfusers_b200.set_precision("fp32").
+ * A correctness mode: never on the measured path (csrc/tf_fp32.cu). */
+/* out[z][m][n] = alpha * sum_k A[z][m][k] * W[z][n][k] (+bias[n]) (+residual[z][m][n]).  w_kn != 0: W is [K][N]
+ * (the P.V product).  out_nchw_hw > 0: M = images * hw rows are written (and the residual read) as NCHW (images, N, hw)
+ * - the 1x1 proj_out of SpatialTransformer reading tokens.  Batches: z = zo * batch_inner + zi with element strides
+ * batch_strides = {A_outer, A_inner, W_outer, W_inner, out_outer, out_inner} (host array; heads inside (B,T,C) tokens).
+ * Replaces: cp.dot(x, W.T) + b  tinyfusers/ff/linear.py:119-120; cp.matmul  tinyfusers/attention/sdpa.py:66,76. */
+int tf_gemm_f32(const float* A, long long lda, const float* W, long long ldw, int w_kn, const float* bias,
+                const float* residual, long long ldr, float* out, long long ldc, int M, int N, int K, float alpha,
+                int out_nchw_hw, int batch_outer, int batch_inner, const long long* batch_strides, void* stream);
+/* NCHW x OIHW cross-correlation, square stride / padding, no dilation; + bias[o] + bias_img[image][o] + residual.
+ * out_tokens != 0 writes (images * Ho * Wo, O) rows instead of NCHW (proj_in feeding the transformer block).
+ * Replaces: conv_2d + bias add  tinyfusers/vision/conv2d.py:9-28,55-59; `h + emb_out`  tinyfusers/vision/resnet.py:27. */
+int tf_conv2d_nchw_f32(const float* x, const float* w, const float* bias, const float* bias_img, const float* residual,
+                       float* out, int NI, int C, int H, int W, int O, int R, int S, int stride, int pad, int out_tokens,
+                       void* stream);
+/* literal two-pass GroupNorm on NCHW: (x - mean) * (1 / sqrt(mean((x - mean)^2) + eps)) [* gamma + beta] [-> SiLU].
+ * Replaces: group_norm / GroupNorm.__call__  tinyfusers/ff/group_norm.py:3-21. */
+int tf_groupnorm_nchw_f32(const float* x, const float* gamma, const float* beta, float* out, int NI, int C, int HW,
+                          int groups, float eps, int silu, void* stream);
+/* LayerNorm over the last dimension of (rows, C).  Replaces: layer_norm  tinyfusers/ff/layer_norm.py:8-32. */
+int tf_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, long long rows, int C, float eps,
+                     void* stream);
+/* in-place max-subtracted row softmax.  Replaces: softmax_kernel  tinyfusers/native/cuda/softmax.cu:24-112. */
+int tf_softmax_rows_f32(float* x, long long rows, int cols, void* stream);
+/* op: 0 sigmoid, 1 silu/swish, 2 gelu (tanh approx), 3 quick_gelu with IEEE expf / tanhf.
+ * Replaces: Tensor.sigmoid/silu/gelu/quick_gelu  tinyfusers/storage/tensor.py:64-86. */
+int tf_unary_f32(const float* x, float* out, long long n, int op, void* stream);
+/* out[m][j] = y[m][j] * gelu(y[m][H + j]).  Replaces: GEGLU.__call__  tinyfusers/ff/nn.py:10-12. */
+int tf_geglu_f32(const float* y, long long ldy, float* out, long long M, int H, void* stream);
+/* out = uncond + guidance * (cond - uncond).  Replaces: the CFG combine of get_model_output  tinyfusers/variants/sd.py:44-45. */
+int tf_cfg_combine_f32(const float* uncond, const float* cond, float guidance, float* out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

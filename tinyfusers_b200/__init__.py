@@ -33,6 +33,18 @@ def get_layernorm_strided() -> bool:
     return _LN_STRIDED
 
 
+def set_precision(mode: str):
+    """"fp16" (default: the tcgen05 path, <= 1e-2) or "fp32" (parity mode of BASELINE.json configs[0], <= 1e-5;
+    plain-fp32 kernels in the reference's layouts - tinyfusers_b200/fp32.py, csrc/tf_fp32.cu)."""
+    from . import fp32
+    fp32.set_precision(mode)
+
+
+def get_precision() -> str:
+    from . import fp32
+    return fp32.get_precision()
+
+
 def __getattr__(name):
     # `tinyfusers.Tensor` (reference: tinyfusers/__init__.py:1), resolved lazily: importing the package itself must not
     # need the built shared library (the build script lives inside the package)

@@ -10,7 +10,7 @@ In NHWC the reference's (B,C,HW)->(B,HW,C) transposes (attention.py:70,73) are f
 and the 1x1 proj_in / proj_out convs are plain GEMMs with bias / residual epilogues."""
 import torch
 
-from .. import get_quirks, packing
+from .. import fp32, get_quirks, packing
 from ..ff.group_norm import GroupNorm
 from ..ff.layer_norm import LayerNorm
 from ..ff.linear import Linear
@@ -72,6 +72,8 @@ class CrossAttention:
 
     def __call__(self, x, context=None):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.cross_attention(self, x, context)
         ctx = standalone_context()
         ctx.arena.reset()
         xa = tokens_to_act(x)
@@ -143,6 +145,8 @@ class BasicTransformerBlock:
 
     def __call__(self, x, context=None):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.basic_transformer_block(self, x, context)
         ctx = standalone_context()
         ctx.arena.reset()
         B, T, C = x.shape
@@ -214,6 +218,8 @@ class SpatialTransformer:
 
     def __call__(self, x, context=None):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.spatial_transformer(self, x, context)
         ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=8)

@@ -6,11 +6,14 @@ is container-level data movement for this stand-alone entry point only; inside t
 the projection GEMMs write these layouts directly."""
 import torch
 
+from .. import fp32
 from ..runtime import F16, F32, require_cuda, standalone_context
 
 
 def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
     require_cuda(q_cp, "q")
+    if fp32.enabled():
+        return fp32.scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask)
     ctx = standalone_context()
     B, NH, Tq, HS = q_cp.shape
     Tk = k_cp.shape[-2]

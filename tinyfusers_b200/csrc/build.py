@@ -59,7 +59,9 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        # the fp32 parity kernels need IEEE expf / tanhf / division: no --use_fast_math for that file
+        flags = [f for f in FLAGS if f != "--use_fast_math"] if os.path.basename(src) == "tf_fp32.cu" else FLAGS
+        cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

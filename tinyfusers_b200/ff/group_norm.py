@@ -1,13 +1,15 @@
 """GroupNorm with the reference's signatures (reference: tinyfusers/ff/group_norm.py:3-21)."""
 import torch
 
-from .. import packing
+from .. import fp32, packing
 from ..runtime import F32, act_to_nchw, nchw_to_act, new_act_tensor, standalone_context
 from ..storage.state import _default_device
 
 
 def group_norm(x, num_groups, eps):
     """(x - mean) / sqrt(biased_var + eps) per (n, group); no affine (group_norm.py:3-11)."""
+    if fp32.enabled():
+        return fp32.group_norm(x, num_groups, eps)
     ctx = standalone_context()
     a = nchw_to_act(x, c_pad_to=8)
     C = x.shape[1]
@@ -30,6 +32,8 @@ class GroupNorm:
                               lambda: (packing.f32(self.weight), packing.f32(self.bias)))
 
     def __call__(self, x):
+        if fp32.enabled():
+            return fp32.group_norm(x, self.num_groups, self.eps, self.weight, self.bias)
         ctx = standalone_context()
         a = nchw_to_act(x, c_pad_to=8)
         if a.c != self.num_channels:

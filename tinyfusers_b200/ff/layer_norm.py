@@ -10,7 +10,7 @@ from typing import Tuple, Union
 import numpy as np
 import torch
 
-from .. import get_layernorm_strided, packing
+from .. import fp32, get_layernorm_strided, packing
 from ..runtime import F16, F32, require_cuda, standalone_context
 from ..storage.state import _default_device
 
@@ -18,6 +18,8 @@ from ..storage.state import _default_device
 def layer_norm(x_gpu, scale_gpu, bias_gpu, epsilon_cpu):
     """x_gpu: (1, B, T, C) as in the reference; scale/bias: (1,1,1,C); epsilon_cpu: np.full((1,1,1,1))."""
     require_cuda(x_gpu, "x_gpu")
+    if fp32.enabled():
+        return fp32.layer_norm(x_gpu, scale_gpu.reshape(-1), bias_gpu.reshape(-1), float(np.asarray(epsilon_cpu).reshape(-1)[0]))
     ctx = standalone_context()
     _, B, T, C = x_gpu.shape
     xh = x_gpu.to(F16).contiguous()

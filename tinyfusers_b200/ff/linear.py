@@ -4,7 +4,7 @@
 tcgen05 GEMM, fp16 operands, fp32 accumulate, bias fused in the epilogue."""
 import torch
 
-from .. import packing
+from .. import fp32, packing
 from ..native.b200.ops import b200
 from ..runtime import F16, F32, require_cuda, standalone_context
 from ..storage.state import _default_device
@@ -24,6 +24,8 @@ class Linear:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():      # parity mode: plain fp32 kernels (csrc/tf_fp32.cu)
+            return fp32.linear(x, self.weight, self.bias)
         ctx = standalone_context()
         w, b = self._packed()
         out_f, in_f = self.weight.shape

@@ -5,7 +5,7 @@ Fast path: the GEGLU projection, its bias, the split and `value * gelu_tanh(gate
 (84 MB fp32 at 64x64) never exists. The output projection fuses bias and the transformer residual."""
 import torch
 
-from .. import packing
+from .. import fp32, packing
 from ..native.b200.ops import b200
 from ..runtime import F16, F32, require_cuda, standalone_context
 from .linear import Linear
@@ -22,6 +22,8 @@ class GEGLU:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.geglu(self, x)
         ctx = standalone_context()
         a = x.reshape(-1, x.shape[-1]).to(F16).contiguous()
         out = torch.empty((a.shape[0], self.dim_out), dtype=F16, device=x.device)
@@ -59,6 +61,8 @@ class FeedForward:
         ]
 
     def __call__(self, x):
+        if fp32.enabled():
+            return fp32.feed_forward(self, x)
         h = self.net[0](x)
         return self.net[2](h)
 

@@ -8,6 +8,7 @@ import functools
 
 import torch
 
+from .. import fp32
 from ..native.b200.ops import b200
 from ..runtime import require_cuda, stream_ptr
 
@@ -16,6 +17,8 @@ _OPS = {"sigmoid": 0, "silu": 1, "gelu": 2, "quick_gelu": 3}
 
 def _unary(x, op):
     require_cuda(x, "x")
+    if fp32.enabled():
+        return fp32.unary(x, _OPS[op])
     if x.dtype not in (torch.float32, torch.float16):
         x = x.to(torch.float32)
     x = x.contiguous()

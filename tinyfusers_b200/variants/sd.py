@@ -14,7 +14,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from .. import get_layernorm_strided, get_quirks
+from .. import fp32, get_layernorm_strided, get_quirks
 from ..native.b200.ops import b200
 from ..runtime import F32, require_cuda, stream_ptr
 from ..vae.encoder import CLIPTextTransformer
@@ -52,6 +52,8 @@ class StableDiffusion:
         return x_prev, pred_x0
 
     def get_model_output(self, unconditional_context, context, latent, timestep, unconditional_guidance_scale):
+        if fp32.enabled():
+            return fp32.get_model_output(self, unconditional_context, context, latent, timestep, unconditional_guidance_scale)
         s = self._sampler(latent.shape, context.shape[1])
         s.load(unconditional_context, context, latent)
         s.set_scalars(timestep, 1.0, 1.0, unconditional_guidance_scale)
@@ -73,6 +75,9 @@ class StableDiffusion:
         return out[0] if B == 1 else out
 
     def __call__(self, unconditional_context, context, latent, timestep, alphas, alphas_prev, guidance):
+        if fp32.enabled():      # the reference's own two calls (sd.py:56-59), eager, fp32 kernels
+            e_t = self.get_model_output(unconditional_context, context, latent, timestep, guidance)
+            return self.get_x_prev_and_pred_x0(latent, e_t, alphas, alphas_prev)[0]
         s = self._sampler(latent.shape, context.shape[1])
         s.load(unconditional_context, context, latent)
         s.set_scalars(timestep, alphas, alphas_prev, guidance)

@@ -9,7 +9,7 @@ import operator
 
 import torch
 
-from .. import packing
+from .. import fp32, packing
 from ..native.b200.ops import b200
 from ..runtime import F16, F32, Act, act_to_nchw, nchw_to_act, new_act_tensor, require_cuda, standalone_context, stream_ptr
 from ..storage.state import _default_device
@@ -47,6 +47,10 @@ def _conv_act(ctx, x, w_packed, cout_p, k, stride, out, bias_ptr=None, residual=
 def conv_2d(X_gpu, W_gpu, padding, stride, dilation):
     """NCHW cross-correlation without bias -> NCHW fp32 (reference: conv2d.py:9-28)."""
     require_cuda(X_gpu, "X_gpu")
+    if fp32.enabled():
+        if fp32._sq(dilation, "dilation") != 1:
+            raise RuntimeError("tinyfusers_b200 conv_2d (fp32): dilation has no kernel")
+        return fp32.conv2d(X_gpu, W_gpu, None, fp32._sq(stride, "stride"), fp32._sq(padding, "padding"))
     k, s = _check_supported(W_gpu.shape[2:], stride, padding, dilation)
     ctx = standalone_context()
     O = W_gpu.shape[0]
@@ -97,6 +101,8 @@ class Conv2d:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.conv_module(self, x)
         ctx = standalone_context()
         k, s = self._geometry()
         O, I = self.weight.shape[0], self.weight.shape[1]

@@ -6,6 +6,7 @@ Reference: GN -> silu -> conv3x3 -> (+ Linear(silu(emb))) -> GN -> silu -> conv3
 first conv's bias, the residual (identity or 1x1 skip conv) is added by the second conv's epilogue."""
 import torch
 
+from .. import fp32
 from ..ff.group_norm import GroupNorm
 from ..ff.linear import Linear
 from ..native.b200.ops import b200
@@ -36,6 +37,8 @@ class ResBlock:
 
     def __call__(self, x, emb):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.res_block(self, x, emb)
         ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=8)
@@ -89,6 +92,8 @@ class ResnetBlock:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.resnet_block(self, x)
         ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=8)

@@ -13,7 +13,7 @@ Fast path of one forward (batch 2B for CFG):
 import numpy as np
 import torch
 
-from .. import get_layernorm_strided, get_quirks, packing
+from .. import fp32, get_layernorm_strided, get_quirks, packing
 from ..attention.attention import SpatialTransformer
 from ..ff.group_norm import GroupNorm
 from ..ff.linear import Linear
@@ -30,6 +30,8 @@ class Upsample:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.upsample(self, x)
         ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=64)
@@ -117,6 +119,8 @@ class UNetModel:
     # ---- reference-signature call: x (NB,4,H,W), timesteps 1 element, context (NB,77,768) -> (NB,4,H,W) fp32 ----
     def __call__(self, x, timesteps=None, context=None):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.unet_forward(self, x, timesteps, context)
         NB, _, H, W = x.shape
         eng = self.engine(NB, H, W, n_src=NB, ctx_tokens=context.shape[1])
         return eng.forward_nchw(x, timesteps, context)
