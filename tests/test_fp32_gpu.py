@@ -248,3 +248,20 @@ def test_unet_and_sampler_step_fp32(oracle, unet_sd, sd_model):
     got = sd_model(unc.cuda(), ctx.cuda(), lat.cuda(), torch.tensor([ts[i]]).cuda(), alphas[[i]].cuda(),
                    alphas_prev[[i]].cuda(), torch.tensor([7.5]))
     _check(got, ref, tol=1e-4)
+
+
+# ---- the production fp16 path against the fp32 path ON THE GPU at BASELINE.json's full sizes ------------------------
+# (the CPU oracle needs minutes for a 64x64 / 96x96 UNet; the fp32 mode above is oracle-checked operator by operator and
+# at C1's full size, so it carries the oracle to the sizes the bench runs at)
+
+@pytest.mark.parametrize("hw,t", [(64, 981), (96, 301)])
+def test_fp16_step_matches_fp32_mode_full_size(oracle, sd_model, hw, t):
+    import tinyfusers_b200
+    lat, unc, ctx = oracle.make_inputs(1, hw, seed=11, ctx_seed=12)
+    ts = torch.tensor([t]).cuda()
+    g = torch.tensor([7.5])
+    e32 = sd_model.get_model_output(unc.cuda(), ctx.cuda(), lat.cuda(), ts, g)
+    assert e32.shape == (1, 4, hw, hw) and torch.isfinite(e32).all()
+    tinyfusers_b200.set_precision("fp16")
+    e16 = sd_model.get_model_output(unc.cuda(), ctx.cuda(), lat.cuda(), ts, g)
+    assert rel_err(e16, e32) < 3e-2     # same bound as test_unet_gpu.py's CFG output against the oracle at 32x32
