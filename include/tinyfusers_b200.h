@@ -303,8 +303,13 @@ int tf_groupnorm_nchw_f32(const float* x, const float* gamma, const float* beta,
 /* LayerNorm over the last dimension of (rows, C).  Replaces: layer_norm  tinyfusers/ff/layer_norm.py:8-32. */
 int tf_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, long long rows, int C, float eps,
                      void* stream);
-/* in-place max-subtracted row softmax.  Replaces: softmax_kernel  tinyfusers/native/cuda/softmax.cu:24-112. */
-int tf_softmax_rows_f32(float* x, long long rows, int cols, void* stream);
+/* in-place max-subtracted row softmax; causal_tq > 0: row r is query r % causal_tq and sees keys 0..query only (the
+ * triu(-inf, k=1) mask of tinyfusers/vae/encoder.py:79).  Replaces: softmax_kernel  tinyfusers/native/cuda/softmax.cu:24-112. */
+int tf_softmax_rows_f32(float* x, long long rows, int cols, int causal_tq, void* stream);
+/* out[r, :] = table[ids[r], :] + pos_table[r % T, :] in fp32 (pos_table may be NULL).
+ * Replaces: Embedding.__call__  tinyfusers/ff/embedding.py:15-23, CLIPTextEmbeddings  tinyfusers/vae/encoder.py:66-70. */
+int tf_embedding_f32(const int* ids, const float* table, const float* pos_table, float* out, int rows, int T, int E,
+                     int vocab, void* stream);
 /* op: 0 sigmoid, 1 silu/swish, 2 gelu (tanh approx), 3 quick_gelu with IEEE expf / tanhf.
  * Replaces: Tensor.sigmoid/silu/gelu/quick_gelu  tinyfusers/storage/tensor.py:64-86. */
 int tf_unary_f32(const float* x, float* out, long long n, int op, void* stream);

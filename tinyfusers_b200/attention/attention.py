@@ -272,6 +272,8 @@ class AttnBlock:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.attn_block(self, x)
         ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=8)
@@ -334,6 +336,8 @@ class CLIPAttention:
         """(B, T, 768) -> (B, T, 768). The mask argument is accepted for signature parity; the kernel applies the causal
         mask the reference always passes (vae/encoder.py:79)."""
         require_cuda(hidden_states, "hidden_states")
+        if fp32.enabled():
+            return fp32.clip_attention(self, hidden_states)
         ctx = standalone_context()
         B, T, E = hidden_states.shape
         Tp = (T + 7) // 8 * 8

@@ -12,9 +12,6 @@ from ..runtime import F16, F32, require_cuda, standalone_context
 
 def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
     require_cuda(q_cp, "q")
-    if fp32.enabled():
-        return fp32.scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask)
-    ctx = standalone_context()
     B, NH, Tq, HS = q_cp.shape
     Tk = k_cp.shape[-2]
     causal = False
@@ -30,6 +27,9 @@ def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
             raise RuntimeError("tinyfusers_b200 scaled_dot_product_attention: only the causal mask "
                                "(triu(-inf, k=1) / its boolean form) is built")
         causal = True
+    if fp32.enabled():
+        return fp32.scaled_dot_product_attention(q_cp, k_cp, v_cp, causal)
+    ctx = standalone_context()
     if HS % 8 != 0 or v_cp.shape[-1] != HS:
         raise RuntimeError(f"tinyfusers_b200 scaled_dot_product_attention: head size {HS} must be a multiple of 8 "
                            "and equal for q/k/v")

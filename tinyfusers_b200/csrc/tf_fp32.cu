@@ -268,21 +268,38 @@ __global__ void __launch_bounds__(128) layernorm_f32_kernel(const float* __restr
 }
 
 // one block per row, three passes like the reference kernel (softmax.cu:24-112): max, exp + sum, normalise
-__global__ void __launch_bounds__(256) softmax_rows_f32_kernel(float* __restrict__ x, int cols) {
+// causal_tq > 0: row r is query (r % causal_tq) and sees keys 0..query only - the additive triu(-inf, k=1) mask of CLIP
+// (vae/encoder.py:79); masked entries come out as exact zeros, as exp(-inf) does in the reference
+__global__ void __launch_bounds__(256) softmax_rows_f32_kernel(float* __restrict__ x, int cols, int causal_tq) {
   tf::pdl_prologue();
   __shared__ float red[8];
   float* __restrict__ xp = x + (long)blockIdx.x * cols;
+  const int valid = causal_tq > 0 ? min(cols, (int)(blockIdx.x % causal_tq) + 1) : cols;
   float m = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, xp[c]);
+  for (int c = threadIdx.x; c < valid; c += blockDim.x) m = fmaxf(m, xp[c]);
   m = block_max(m, red);
   float s = 0.f;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+  for (int c = threadIdx.x; c < valid; c += blockDim.x) {
     const float e = expf(xp[c] - m);
     xp[c] = e;
     s += e;
   }
   s = block_sum(s, red);
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) xp[c] = xp[c] / s;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) xp[c] = c < valid ? xp[c] / s : 0.f;
+}
+
+// out[r, :] = table[ids[r], :] + pos[r % T, :]   (ff/embedding.py:15-23 as a row lookup, vae/encoder.py:66-70)
+__global__ void embedding_f32_kernel(const int* __restrict__ ids, const float* __restrict__ table,
+                                     const float* __restrict__ pos, float* __restrict__ out, int rows, int T, int E, int vocab) {
+  tf::pdl_prologue();
+  const long total = (long)rows * E;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / E), e = (int)(i - (long)r * E);
+    const int id = min(max(ids[r], 0), vocab - 1);
+    float v = table[(long)id * E + e];
+    if (pos) v += pos[(long)(r % T) * E + e];
+    out[i] = v;
+  }
 }
 
 __global__ void unary_f32_kernel(const float* __restrict__ x, float* __restrict__ out, long n, int op) {
@@ -389,9 +406,19 @@ extern "C" int tf_layernorm_f32(const float* x, const float* gamma, const float*
   return TF_OK;
 }
 
-extern "C" int tf_softmax_rows_f32(float* x, long long rows, int cols, void* stream) {
-  TF_CHECK_ARG(x && rows > 0 && rows < (1ll << 31) && cols > 0, "tf_softmax_rows_f32: bad arguments");
-  TF_LAUNCH(softmax_rows_f32_kernel, (unsigned)rows, 256, 0, (cudaStream_t)stream, x, cols);
+extern "C" int tf_embedding_f32(const int* ids, const float* table, const float* pos_table, float* out, int rows, int T,
+                                int E, int vocab, void* stream) {
+  TF_CHECK_ARG(ids && table && out && rows > 0 && T > 0 && E > 0 && vocab > 0, "tf_embedding_f32: bad arguments");
+  TF_LAUNCH(embedding_f32_kernel, grid_for((long)rows * E, 256), 256, 0, (cudaStream_t)stream, ids, table, pos_table, out, rows,
+            T, E, vocab);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
+extern "C" int tf_softmax_rows_f32(float* x, long long rows, int cols, int causal_tq, void* stream) {
+  TF_CHECK_ARG(x && rows > 0 && rows < (1ll << 31) && cols > 0 && causal_tq >= 0, "tf_softmax_rows_f32: bad arguments");
+  TF_LAUNCH(softmax_rows_f32_kernel, (unsigned)rows, 256, 0, (cudaStream_t)stream, x, cols, causal_tq);
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   return TF_OK;

@@ -87,6 +87,8 @@ class CLIPMLP:
 
     def __call__(self, hidden_states):
         require_cuda(hidden_states, "hidden_states")
+        if fp32.enabled():
+            return fp32.clip_mlp(self, hidden_states)
         ctx = standalone_context()
         ctx.arena.reset()
         x2 = hidden_states.reshape(-1, 768).to(F16).contiguous()

@@ -142,7 +142,7 @@ def _strides(*v):
     return (ctypes.c_longlong * 6)(*[int(t) for t in v])
 
 
-def _attention(q, ldq, sq, k, ldk, sk, v, ldv, sv, B, NH, Tq, Tk, d, out, ldo, so):
+def _attention(q, ldq, sq, k, ldk, sk, v, ldv, sv, B, NH, Tq, Tk, d, out, ldo, so, causal=False):
     """softmax(scale * Q K^T) V per (batch, head); operands addressed as base + b*s[0] + h*s[1] + t*ld + j.
     Scores are materialised in fp32 like the reference does (attention/sdpa.py:62-76)."""
     dev = q.device
@@ -157,23 +157,23 @@ def _attention(q, ldq, sq, k, ldk, sk, v, ldv, sv, B, NH, Tq, Tk, d, out, ldo, s
         st = b200.tf_gemm_f32(qp, ldq, kp, ldk, 0, None, None, 0, scores.data_ptr(), Tk, Tq, Tk, d, scale, 0, nb, NH,
                               _strides(sq[0], sq[1], sk[0], sk[1], NH * Tq * Tk, Tq * Tk), stream_ptr())
         b200.check(st, "tf_gemm_f32")
-        b200.check(b200.tf_softmax_rows_f32(scores.data_ptr(), nb * NH * Tq, Tk, stream_ptr()), "tf_softmax_rows_f32")
+        b200.check(b200.tf_softmax_rows_f32(scores.data_ptr(), nb * NH * Tq, Tk, Tq if causal else 0, stream_ptr()),
+                   "tf_softmax_rows_f32")
         st = b200.tf_gemm_f32(scores.data_ptr(), Tk, vp, ldv, 1, None, None, 0, op, ldo, Tq, d, Tk, 1.0, 0, nb, NH,
                               _strides(NH * Tq * Tk, Tq * Tk, sv[0], sv[1], so[0], so[1]), stream_ptr())
         b200.check(st, "tf_gemm_f32")
     return out
 
 
-def scaled_dot_product_attention(q, k, v, attn_mask=None):
-    """(B,NH,Tq,HS) x (B,NH,Tk,HS) -> (B,NH,Tq,HS)   (reference: attention/sdpa.py:53-77)."""
-    if attn_mask is not None:
-        raise RuntimeError("scaled_dot_product_attention (fp32 mode): masks are not built (the UNet passes none)")
+def scaled_dot_product_attention(q, k, v, causal=False):
+    """(B,NH,Tq,HS) x (B,NH,Tk,HS) -> (B,NH,Tq,HS)   (reference: attention/sdpa.py:53-77); `causal` = the one mask the
+    reference passes (CLIP's triu(-inf, k=1), recognised by the caller in attention/sdpa.py)."""
     q, k, v = _prep(q, "q"), _prep(k, "k"), _prep(v, "v")
     B, NH, Tq, d = q.shape
     Tk = k.shape[-2]
     out = torch.empty_like(q)
     return _attention(q, d, (NH * Tq * d, Tq * d), k, d, (NH * Tk * d, Tk * d), v, d, (NH * Tk * d, Tk * d), B, NH, Tq, Tk, d,
-                      out, d, (NH * Tq * d, Tq * d))
+                      out, d, (NH * Tq * d, Tq * d), causal=causal)
 
 
 def geglu(m, x):
@@ -334,3 +334,108 @@ def get_model_output(sd_model, unconditional_context, context, latent, timestep,
     b200.check(b200.tf_cfg_combine_f32(u.data_ptr(), c.data_ptr(), g, e_t.data_ptr(), u.numel(), stream_ptr()),
                "tf_cfg_combine_f32")
     return e_t
+
+
+# ---- rows next to the hot path: VAE decoder, CLIP text encoder --------------------------------------
+
+def attn_block(m, x, quirks=None):
+    """reference: attention/attention.py:10-24. quirks: the 4-D (B,C,H,W) q/k/v go straight into SDPA, i.e. NH = C,
+    T = H, HS = W (parity note 3). Canonical (quirks off): one head over the H*W pixels, head dim C - built here (the
+    fp16 attention kernel stops at head dim 256), so `set_quirks(False)` decodes real checkpoints in fp32 mode."""
+    from . import get_quirks
+    quirks = get_quirks() if quirks is None else quirks
+    x = _prep(x)
+    B, C, H, W = x.shape
+    hn = group_norm(x, m.norm.num_groups, m.norm.eps, m.norm.weight, m.norm.bias)
+    if quirks:
+        q, k, v = (conv_module(c, hn) for c in (m.q, m.k, m.v))
+        o = scaled_dot_product_attention(q, k, v)
+        return conv_module(m.proj_out, o, residual=x)
+    T = H * W
+    q, k, v = (conv_module(c, hn, out_tokens=True) for c in (m.q, m.k, m.v))     # (B*T, C) token rows
+    o = torch.empty_like(q)
+    _attention(q, C, (T * C, 0), k, C, (T * C, 0), v, C, (T * C, 0), B, 1, T, T, C, o, C, (T * C, 0))
+    wo, bo = _w(m.proj_out.weight, x), _w(m.proj_out.bias, x)
+    wo2 = wo.reshape(wo.shape[0], -1)
+    out = torch.empty_like(x)
+    st = b200.tf_gemm_f32(o.data_ptr(), C, wo2.data_ptr(), wo2.stride(0), 0, _ptr(bo), x.data_ptr(), 0, out.data_ptr(), 0,
+                          B * T, wo.shape[0], C, 1.0, T, 1, 1, None, stream_ptr())
+    b200.check(st, "tf_gemm_f32")
+    return out
+
+
+def vae_mid(m, x):
+    """reference: vae/mid.py:5-12."""
+    return resnet_block(m.block_2, attn_block(m.attn_1, resnet_block(m.block_1, x)))
+
+
+def vae_decoder(m, x):
+    """reference: vae/decoder.py:22-34."""
+    x = conv_module(m.conv_in, x)
+    x = vae_mid(m.mid, x)
+    for l in m.up[::-1]:
+        for b in l["block"]:
+            x = resnet_block(b, x)
+        if "upsample" in l:
+            bs, c, py, px = x.shape      # nearest x2 (decoder.py:30-31), data movement only
+            x = x.reshape(bs, c, py, 1, px, 1).expand(bs, c, py, 2, px, 2).reshape(bs, c, py * 2, px * 2)
+            x = conv_module(l["upsample"]["conv"], x)
+    n = m.norm_out
+    return conv_module(m.conv_out, group_norm(x, n.num_groups, n.eps, n.weight, n.bias, silu=True))
+
+
+def decode(sd_model, x):
+    """reference: variants/sd.py:48-54 (the hard-coded 512 generalised like the fp16 path): uint8 (H,W,3) | (B,H,W,3)."""
+    fsm = sd_model.first_stage_model
+    z = fsm.post_quant(_prep(x), 1 / 0.18215)
+    img = vae_decoder(fsm.decoder, z)                         # (B, 3, H, W) fp32
+    B, _, H, W = img.shape
+    nhwc = img.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=img.device)
+    b200.check(b200.tf_image_to_u8(nhwc.data_ptr(), 3, out.data_ptr(), B * H * W, 3, stream_ptr()), "tf_image_to_u8")
+    return out[0] if B == 1 else out
+
+
+def clip_attention(m, x, residual=None):
+    """reference: attention/attention.py:78-99 (12 heads x 64, biased projections, causal mask, canonical head merge)."""
+    x = _prep(x)
+    B, T, E = x.shape
+    NH, D = m.num_heads, m.head_dim
+    q, k, v = (linear(x, p.weight, p.bias) for p in (m.q_proj, m.k_proj, m.v_proj))
+    o = torch.empty_like(q)
+    s = (T * E, D)
+    _attention(q, E, s, k, E, s, v, E, s, B, NH, T, T, D, o, E, s, causal=True)
+    return linear(o, m.out_proj.weight, m.out_proj.bias, residual)
+
+
+def clip_mlp(m, x, residual=None):
+    """reference: ff/nn.py:25-34."""
+    h = unary(linear(x, m.fc1.weight, m.fc1.bias), 3)
+    return linear(h, m.fc2.weight, m.fc2.bias, residual)
+
+
+def _ln(n, t):
+    return layer_norm(t, n.weight, n.bias, float(torch.as_tensor(n.eps).reshape(-1)[0]))
+
+
+def clip_encoder_layer(m, x):
+    """reference: vae/encoder.py:53-64."""
+    x = _prep(x)
+    x = clip_attention(m.self_attn, _ln(m.layer_norm1, x), residual=x)
+    return clip_mlp(m.mlp, _ln(m.layer_norm2, x), residual=x)
+
+
+def clip_text_transformer(m, ids):
+    """reference: vae/encoder.py:72-81; ids (B, T) int32 on the device."""
+    B, T = ids.shape
+    tok = m.embeddings.token_embedding.weight
+    pos = m.embeddings.position_embedding.weight
+    tok, pos = _w(tok, tok), _w(pos, tok)
+    ids = ids.to(device=tok.device, dtype=torch.int32).contiguous()
+    x = torch.empty((B, T, tok.shape[1]), dtype=F32, device=tok.device)
+    st = b200.tf_embedding_f32(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), x.data_ptr(), B * T, T, tok.shape[1],
+                               tok.shape[0], stream_ptr())
+    b200.check(st, "tf_embedding_f32")
+    for l in m.encoder.layers:
+        x = clip_encoder_layer(l, x)
+    return _ln(m.final_layer_norm, x)

@@ -91,7 +91,8 @@ _SIGNATURES = {
     "tf_conv2d_nchw_f32": (c_int, [_P, _P, _P, _P, _P, _P] + [c_int] * 10 + [_P]),
     "tf_groupnorm_nchw_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "tf_layernorm_f32": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_float, _P]),
-    "tf_softmax_rows_f32": (c_int, [_P, c_longlong, c_int, _P]),
+    "tf_softmax_rows_f32": (c_int, [_P, c_longlong, c_int, c_int, _P]),
+    "tf_embedding_f32": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_unary_f32": (c_int, [_P, _P, c_longlong, c_int, _P]),
     "tf_geglu_f32": (c_int, [_P, c_longlong, _P, c_longlong, c_int, _P]),
     "tf_cfg_combine_f32": (c_int, [_P, _P, c_float, _P, c_longlong, _P]),

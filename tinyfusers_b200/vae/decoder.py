@@ -7,6 +7,7 @@ in a stack arena sized by a dry run; conv_in reads the fp32 NCHW latent directly
 """
 import torch
 
+from .. import fp32
 from ..ff.group_norm import GroupNorm
 from ..native.b200.ops import b200
 from ..runtime import F32, Act, Context, require_cuda, stream_ptr
@@ -33,6 +34,8 @@ class Decoder:
     def __call__(self, x):
         """(B, 4, h, w) fp32 NCHW latent (already through post_quant_conv) -> (B, 3, 8h, 8w) fp32 NCHW."""
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.vae_decoder(self, x)
         eng = self._engine(tuple(x.shape))
         return eng.decode_nchw(x)
 

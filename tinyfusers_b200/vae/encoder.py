@@ -10,6 +10,7 @@ keys load, and raises when called."""
 import numpy as np
 import torch
 
+from .. import fp32
 from ..attention.attention import CLIPAttention
 from ..ff.embedding import Embedding, _ids_tensor
 from ..ff.group_norm import GroupNorm
@@ -50,6 +51,8 @@ class CLIPEncoderLayer:
 
     def __call__(self, hidden_states, causal_attention_mask=None):
         B, T, E = hidden_states.shape
+        if fp32.enabled():
+            return fp32.clip_encoder_layer(self, hidden_states)
         ctx = standalone_context()
         Tp = (T + 7) // 8 * 8
         outs = []
@@ -105,6 +108,8 @@ class CLIPTextTransformer:
         B, T = ids.shape
         if T > 77:
             raise RuntimeError(f"CLIPTextTransformer: {T} tokens, the position table has 77")
+        if fp32.enabled():
+            return fp32.clip_text_transformer(self, ids)
         Tp = (T + 7) // 8 * 8
         ctx = standalone_context()
         out = torch.empty((B, T, 768), dtype=F32, device=dev)

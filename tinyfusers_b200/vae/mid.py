@@ -1,4 +1,5 @@
 """VAE mid block with the reference's signature (reference: tinyfusers/vae/mid.py:5-12)."""
+from .. import fp32
 from ..attention.attention import AttnBlock
 from ..runtime import act_to_nchw, nchw_to_act, new_act_tensor, require_cuda, standalone_context
 from ..vision.resnet import ResnetBlock
@@ -13,6 +14,8 @@ class Mid:
 
     def __call__(self, x):
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.vae_mid(self, x)
         ctx = standalone_context()
         ctx.arena.reset()
         a = nchw_to_act(x, c_pad_to=8)

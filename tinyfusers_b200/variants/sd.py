@@ -64,6 +64,8 @@ class StableDiffusion:
         """Latent (B,4,h,w) -> uint8 image (8h, 8w, 3) for B = 1 (as the reference), (B, 8h, 8w, 3) otherwise
         (reference: sd.py:48-54, whose reshape(3,512,512) is generalised to the decoded size)."""
         require_cuda(x, "x")
+        if fp32.enabled():
+            return fp32.decode(self, x)
         fsm = self.first_stage_model
         z = fsm.post_quant(x, 1 / 0.18215)
         eng = fsm.decoder._engine(tuple(z.shape))
