@@ -264,6 +264,12 @@ int tf_ddim_step_f32(const float* x, const float* e_t, const float* a_t_dev, con
  *           tinyfusers/attention/sdpa.py:53-77. */
 int tf_plane_attention_f16(const void* q, const void* k, const void* v, void* out, int planes, int H, int W, float scale,
                            void* stream);
+/* probs[r, :] = softmax(scale * scores[r, :]), fp32 (rows, lds) -> fp16 (rows, ldp): the softmax between the QK^T and PV
+ * GEMMs (tf_gemm_f16) of the CANONICAL AttnBlock - one head over the H*W pixels, head dim = channels (512), which the
+ * fused attention kernel (head dim <= 256) does not cover.
+ * Replaces: softmax_kernel  tinyfusers/native/cuda/softmax.cu:24-112 inside  tinyfusers/attention/sdpa.py:53-77. */
+int tf_softmax_rows_f32_to_f16(const float* scores, long long lds, void* probs, long long ldp, long long rows, int cols,
+                               float scale, void* stream);
 /* out[n,co,p] = bias[co] + sum_ci w[co,ci] * (scale * x[n,ci,p]); fp32 NCHW, Cin, Cout <= 8.
  * Replaces: post_quant_conv(1/0.18215 * x)   tinyfusers/variants/sd.py:49, tinyfusers/vae/vae.py:10. */
 int tf_conv1x1_small_f32nchw(const float* x, const float* w, const float* bias, float* out, int NI, int Cin, int Cout,

@@ -132,13 +132,28 @@ def test_attn_block_reference_reading(oracle):
     assert rel_err(_load(AttnBlock(512), sd, "a")(x.cuda()), ref) < 1e-2
 
 
-def test_attn_block_canonical_raises():
+def test_attn_block_and_decoder_canonical(oracle, vae):
+    """set_quirks(False): the canonical LDM AttnBlock (one head over H*W pixels, head dim = C) for real checkpoints -
+    QK^T and PV on the GEMM kernel around tf_softmax_rows_f32_to_f16; stand-alone and inside the decoder."""
     import tinyfusers_b200
     from tinyfusers_b200.attention.attention import AttnBlock
     tinyfusers_b200.set_quirks(False)
     try:
-        with pytest.raises(RuntimeError, match="not built"):
-            AttnBlock(64)(torch.randn(1, 64, 8, 8).cuda())
+        for c, h, w, seed in ((64, 8, 8, 713), (512, 64, 64, 4), (512, 24, 40, 5)):
+            sd = {}
+            oracle.add_attn_block(sd, "a", c, seed=seed)
+            x = rnd(seed + 1, 2 if c == 512 and h == 64 else 1, c, h, w)
+            with torch.no_grad():
+                ref = oracle.attn_block(sd, "a", x, quirks=False)
+            assert rel_err(_load(AttnBlock(c), sd, "a")(x.cuda()), ref) < 1e-2
+        m, vsd = vae
+        z = rnd(57, 1, 4, 16, 16)
+        with torch.no_grad():
+            ref = oracle.vae_decoder(vsd, "first_stage_model.decoder", z, quirks=False)
+        y = m.decoder(z.cuda())
+        assert rel_err(y, ref) < 2e-2
+        with torch.no_grad():
+            assert rel_err(oracle.vae_decoder(vsd, "first_stage_model.decoder", z, quirks=True), ref) > 1e-3   # the two readings differ
     finally:
         tinyfusers_b200.set_quirks(True)
 

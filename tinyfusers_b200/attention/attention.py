@@ -8,15 +8,18 @@ LayerNorm graph builds, ~25 elementwise launches):
   LN -> GEGLU GEMM (fused gate) -> out GEMM (+bias +residual, in place)
 In NHWC the reference's (B,C,HW)->(B,HW,C) transposes (attention.py:70,73) are free reinterpretations,
 and the 1x1 proj_in / proj_out convs are plain GEMMs with bias / residual epilogues."""
+import math
+
 import torch
 
 from .. import fp32, get_quirks, packing
+from ..native.b200.ops import b200
 from ..ff.group_norm import GroupNorm
 from ..ff.layer_norm import LayerNorm
 from ..ff.linear import Linear
 from ..ff.nn import FeedForward
 from ..runtime import (F16, F32, Act, act_to_nchw, nchw_to_act, new_act_tensor, require_cuda, standalone_context,
-                       tokens_to_act)
+                       stream_ptr, tokens_to_act)
 from ..vision.conv2d import Conv2d
 from .sdpa import scaled_dot_product_attention  # noqa: F401  (re-exported like the reference)
 
@@ -252,7 +255,8 @@ class AttnBlock:
     (B, NH = C, T = H, HS = W): every channel plane attends over its own rows (SURVEY.md section 8 parity note 3).
     That is what runs here under `set_quirks(True)` (default): GroupNorm -> ONE GEMM for [q | k | v] (bias fused)
     -> NHWC->NCHW planes -> tf_plane_attention_f16 -> NCHW->NHWC -> proj_out GEMM (+bias +x).
-    The canonical LDM block (one head over H*W pixels, head dim C = 512) is not built: it needs a 512-wide head."""
+    The canonical LDM block (`set_quirks(False)`: one head over H*W pixels, head dim C = 512) runs as two tcgen05 GEMMs
+    around a row softmax (`_attn_block_canonical`): the fused attention kernel stops at head dim 256."""
 
     def __init__(self, in_channels):
         self.norm = GroupNorm(32, in_channels)
@@ -283,8 +287,7 @@ class AttnBlock:
 
     def _run(self, ctx, x, out):
         if not ctx.quirks:
-            raise RuntimeError("tinyfusers_b200 AttnBlock: the canonical single-head block (head dim = channels) is not "
-                               "built; only the reference's per-plane reading (set_quirks(True)) is")
+            return self._run_canonical(ctx, x, out)
         C, H, W = x.c, x.h, x.w
         if C % 8 != 0 or W % 2 != 0:
             raise RuntimeError(f"tinyfusers_b200 AttnBlock: needs channels % 8 == 0 and an even width (C={C}, W={W})")
@@ -306,6 +309,42 @@ class AttnBlock:
         self.proj_out._run(ctx, o, out, residual=x)
         ctx.arena.release(mark)
         return out
+
+
+def _attn_block_canonical(self, ctx, x, out):
+    """The canonical LDM AttnBlock (`set_quirks(False)`, real checkpoints): ONE head over the H*W pixels, head dim = C.
+    C = 512 is beyond the fused attention kernel (head dim <= 256), so it runs as the reference structures SDPA
+    (attention/sdpa.py:62-76) on the tcgen05 GEMM kernel: S = Q K^T (fp32 out), row softmax -> fp16 P, O = P V with V^T
+    from the NHWC->NCHW transpose; per image. 34 GFLOP at 64x64 / C = 512."""
+    C, H, W = x.c, x.h, x.w
+    T = H * W
+    if C % 8 != 0 or T % 8 != 0:
+        raise RuntimeError(f"tinyfusers_b200 AttnBlock (canonical): needs channels % 8 == 0 and H*W % 8 == 0 (C={C}, HW={T})")
+    mark = ctx.arena.mark()
+    hn = ctx.new_act(x.n, H, W, C)
+    self.norm._run(ctx, x, hn, silu=False)
+    w, b = self._packed()
+    qkv = ctx.new_act(x.n, H, W, 3 * C)
+    ctx.gemm(hn.ptr, hn.stride, hn.rows, C, w.data_ptr(), 3 * C, qkv.ptr, 3 * C, bias=b.data_ptr())
+    vt = ctx.arena.alloc(2 * x.n * C * T)                      # (n, C, T): V^T per image
+    ctx.to_nchw_f16(qkv.channels(2 * C, 3 * C), vt)
+    scores = ctx.arena.alloc(4 * T * T)
+    probs = ctx.arena.alloc(2 * T * T)
+    o = ctx.new_act(x.n, H, W, C)
+    scale = 1.0 / math.sqrt(C)
+    for i in range(x.n):
+        q_ptr = qkv.ptr + 2 * i * T * 3 * C
+        ctx.gemm(q_ptr, 3 * C, T, C, q_ptr + 2 * C, T, scores, T, flags=b200.TF_EPI_OUT_F32, ldw=3 * C, w_static=False)
+        if not ctx.skip("misc"):
+            st = b200.tf_softmax_rows_f32_to_f16(scores, T, probs, T, T, T, scale, stream_ptr())
+            b200.check(st, "tf_softmax_rows_f32_to_f16")
+        ctx.gemm(probs, T, T, T, vt + 2 * i * C * T, C, o.ptr + 2 * i * T * o.stride, o.stride, ldw=T, w_static=False)
+    self.proj_out._run(ctx, o, out, residual=x)
+    ctx.arena.release(mark)
+    return out
+
+
+AttnBlock._run_canonical = _attn_block_canonical
 
 
 class CLIPAttention:

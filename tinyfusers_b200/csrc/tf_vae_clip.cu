@@ -132,6 +132,52 @@ int ew_grid(long n, int threads) {
 
 }  // namespace
 
+namespace {
+// Row softmax of the canonical (single-head, head dim = channels) AttnBlock: P[r, :] = softmax(scale * S[r, :]),
+// fp32 scores from the QK^T GEMM -> fp16 probabilities for the PV GEMM. One block per row, three passes over a row
+// that stays in L1/L2 (reference: native/cuda/softmax.cu:24-112 does the same three passes in fp32).
+__global__ void __launch_bounds__(256)
+softmax_f32_to_f16_kernel(const float* __restrict__ S, long lds, __half* __restrict__ P, long ldp, int cols, float scale_log2) {
+  tf::pdl_prologue();
+  __shared__ float red[8];
+  const float* __restrict__ s = S + (long)blockIdx.x * lds;
+  __half* __restrict__ p = P + (long)blockIdx.x * ldp;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, s[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += exp2f((s[c] - m) * scale_log2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += 256) p[c] = __float2half_rn(exp2f((s[c] - m) * scale_log2) * inv);
+}
+}  // namespace
+
+extern "C" int tf_softmax_rows_f32_to_f16(const float* scores, long long lds, void* probs, long long ldp, long long rows,
+                                          int cols, float scale, void* stream) {
+  TF_CHECK_ARG(scores && probs && rows > 0 && rows < (1ll << 31) && cols > 0 && lds >= cols && ldp >= cols && scale > 0.f,
+               "tf_softmax_rows_f32_to_f16: bad arguments");
+  TF_LAUNCH(softmax_f32_to_f16_kernel, (unsigned)rows, 256, 0, (cudaStream_t)stream, scores, (long)lds, (__half*)probs,
+            (long)ldp, cols, scale * 1.4426950408889634f);
+  TF_LAUNCH_CHECK();
+  tf_launch_count_add(1);
+  return TF_OK;
+}
+
 extern "C" int tf_plane_attention_f16(const void* q, const void* k, const void* v, void* out, int planes, int H, int W,
                                       float scale, void* stream) {
   TF_CHECK_ARG(q && k && v && out && planes > 0, "tf_plane_attention_f16: null pointer");

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "tf_attention_causal_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "tf_plane_attention_f16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "tf_softmax_rows_f32_to_f16": (c_int, [_P, c_longlong, _P, c_longlong, c_longlong, c_int, c_float, _P]),
     "tf_conv1x1_small_f32nchw": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     "tf_image_to_u8": (c_int, [_P, c_int, _P, c_longlong, c_int, _P]),
     "tf_embedding_f16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
