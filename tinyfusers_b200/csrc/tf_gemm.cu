@@ -840,7 +840,10 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
       if (it != g_tune->end()) {
         const TileChoice t = it->second;   // validated like the model's candidates: a stale table can never mis-launch
         const int kbs = ceil_div_i(k_blocks, t.splits);
-        const bool ok = t.bn >= bn_mult && t.bn <= 256 && t.bn % bn_mult == 0 && t.splits >= 1 &&
+        // a split-K launch writes fp32 partials and leaves the GroupNorm statistics to the fold kernel, so its tile
+        // width is free of the statistics-unit constraint (any multiple of 32)
+        const int mult = t.splits > 1 ? 32 : bn_mult;
+        const bool ok = t.bn >= mult && t.bn <= 256 && t.bn % mult == 0 && t.splits >= 1 &&
                         (t.splits == 1 || (allow_split && (size_t)t.splits * M * N * sizeof(float) <= ws_bytes &&
                                            (t.splits - 1) * kbs < k_blocks)) &&
                         (t.ctas == 1 || (t.ctas == 2 && m_tiles >= 2 && t.bn % 32 == 0));
@@ -851,16 +854,20 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
   TileChoice best{128, 1, 1};
   double best_cost = 1e30;
   (void)flags;
-  const int step = bn_mult;  // epilogue ships 32-column blocks; GroupNorm statistics units must not straddle tiles
-  for (int bn = step; bn <= 256; bn += step) {
-    if (force_bn > 0 && bn != force_bn) continue;
+  // epilogue ships 32-column blocks; GroupNorm statistics units must not straddle tiles (bn_mult) unless the launch is
+  // split-K (statistics come from the fold). The model only proposes unit-aligned widths; a forced / tabled width
+  // (tools/autotune_gemm.py) may be any multiple of 32 together with splits > 1.
+  for (int bn = 32; bn <= 256; bn += 32) {
+    const bool unit_ok = bn % bn_mult == 0;
+    if (force_bn > 0 ? bn != force_bn : !unit_ok) continue;
     const int n_tiles = ceil_div_i(N, bn);
     // avoid heavily padded N tiles
     const double n_eff = (double)N / (n_tiles * bn);
-    if (n_eff < 0.8 && force_bn <= 0 && bn > step) continue;
+    if (n_eff < 0.8 && force_bn <= 0 && bn > bn_mult) continue;
     const int max_split = allow_split ? 16 : 1;
     for (int sp = 1; sp <= max_split; ++sp) {
       if (force_splits > 0 && sp != force_splits) continue;
+      if (sp == 1 && !unit_ok) continue;
       if (sp > 1) {
         if (k_blocks / sp < 4 && force_splits <= 0) break;
         if ((size_t)sp * M * N * sizeof(float) > ws_bytes) break;

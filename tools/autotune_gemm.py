@@ -17,6 +17,7 @@ ap.add_argument("--configs", default="1x64")
 ap.add_argument("--vae", action="store_true")
 ap.add_argument("--min-gain", type=float, default=0.03)
 ap.add_argument("--out", default="gpurun_out/gemm_tuning.json")
+ap.add_argument("--only-gn", action="store_true", help="only shapes whose launch also emits GroupNorm statistics")
 args = ap.parse_args()
 
 os.environ["TINYFUSERS_B200_TUNING"] = "0"     # measure against the built-in model
@@ -137,13 +138,16 @@ def tune(key, count):
     ref = out.float().clone()
     base_us = chain_us(fns)
     best, best_us, tried = default, base_us, 0
-    for bn in range(bn_mult, 257, bn_mult):
+    for bn in range(32, 257, 32):
+        unit_ok = bn % bn_mult == 0        # split-K launches leave the GroupNorm statistics to the fold: any multiple of 32
+        if not unit_ok and not allow_split: continue
         n_tiles = (N + bn - 1) // bn
         if N / (n_tiles * bn) < 0.65 and bn > bn_mult: continue   # the narrowest tile is always a candidate (N = 8 conv_out)
         for ctas in (1, 2):
             if ctas == 2 and m_tiles < 2: continue
             mt = 2 * ((m_tiles + 1) // 2) if ctas == 2 else m_tiles
             for sp in (1, 2, 3, 4, 5, 6, 8, 10, 12, 14, 16):
+                if sp == 1 and not unit_ok: continue
                 if sp > 1 and (not allow_split or k_blocks // sp < 2): break
                 tiles = mt * n_tiles * sp
                 if tiles > 2.2 * 148 and sp > 1: break
@@ -172,6 +176,8 @@ keys = record_shapes()
 print(f"{len(keys)} unique GEMM / conv shapes", flush=True)
 entries, saved = [], 0.0
 for key, count in sorted(keys.items(), key=lambda kv: str(kv[0])):
+    if args.only_gn and not (key[8] if key[0] == "conv3x3" else key[6]):
+        continue
     tkey, default, base_us, best, best_us, count = tune(key, count)
     if best != default and best_us < (1 - args.min_gain) * base_us:
         entries.append(list(tkey) + list(best) + [round(base_us, 2), round(best_us, 2), count, str(key)])
