@@ -898,8 +898,6 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
 
 static long long* g_timeline = nullptr;
 static int g_max_stages = 0;   // debug: cap the smem ring depth (0 = as many as fit)
-// A/B switch of the split-K fold's block width (TINYFUSERS_B200_FOLD_WIDE=1: always the widest block)
-static const int g_fold_wide = []() { const char* e = getenv("TINYFUSERS_B200_FOLD_WIDE"); return e && e[0] == '1' ? 1 : 0; }();
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams& p,
                        cudaStream_t stream, const CUtensorMap* tmA2p = nullptr) {
@@ -944,16 +942,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   TF_LAUNCH_CHECK();
   tf_launch_count_add(1);
   if (p.splits > 1 && p.gn_stats != nullptr) {
-    // block width: a whole number of statistics units and float4s that divides N, <= 128; the widest one that still
-    // gives every SM a block (a 128-row fold of 1280 columns is 64 blocks at width 80, 128 at width 40)
+    // largest block width <= 128 that is a whole number of statistics units and float4s and divides N (narrower blocks
+    // so that every SM gets one were measured: no gain, profiles/ab_fold_width_r1.log)
     const int l = lcm_i(p.gn_unit, 4);
-    const int row_blocks = ceil_div_i(p.M, 32);
     int bw = 0;
-    for (int w = (128 / l) * l; w >= l; w -= l) {
-      if (p.N % w != 0) continue;
-      bw = w;
-      if ((p.N / w) * row_blocks >= tf_num_sms() || g_fold_wide) break;
-    }
+    for (int w = (128 / l) * l; w >= l; w -= l)
+      if (p.N % w == 0) { bw = w; break; }
     if (bw == 0) {
       tf_set_error("gemm: no split-K reduce block width for N=%d gn_unit=%d", p.N, p.gn_unit);
       return TF_ERR_UNSUPPORTED;
