@@ -2,7 +2,7 @@
 prompt -> CLIP text encoder -> CFG / DDIM sampler loop (one captured CUDA graph replayed per step) -> VAE decode -> PNG.
 
     python -m example.sd1 --steps 50 --seed 42 --guidance 7.5 [--ckpt sd-v1-4.ckpt] [--bpe bpe_simple_vocab_16e6.txt.gz]
-                          [--timing] [--no-graph] [--canonical] [--out rendered.png] [--latent-out latent.npy]
+                          [--timing] [--no-graph] [--canonical] [--fp32] [--out rendered.png] [--latent-out latent.npy]
 
 The reference downloads the checkpoint and the BPE merges file; there is no network here. Without --ckpt the three
 models get seeded synthetic weights (same generators the parity tests use), without --bpe
@@ -43,6 +43,7 @@ def main():
     parser.add_argument('--no-graph', action='store_true', help="launch every step eagerly instead of replaying a CUDA graph")
     parser.add_argument('--canonical', action='store_true', help="canonical head merge (real checkpoints) instead of the reference's reshape")
     parser.add_argument('--latent-out', type=str, default=None, help="also save the final latent as .npy")
+    parser.add_argument('--fp32', action='store_true', help="fp32 parity mode (the reference's dtype; plain-fp32 kernels, slow): tinyfusers_b200.set_precision('fp32')")
     args = parser.parse_args()
 
     import numpy as np
@@ -53,6 +54,8 @@ def main():
 
     if args.canonical:
         tinyfusers_b200.set_quirks(False)
+    if args.fp32:
+        tinyfusers_b200.set_precision("fp32")
     model = StableDiffusion()
 
     # load in weights (reference: sd1.py:38-41)

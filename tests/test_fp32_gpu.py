@@ -265,3 +265,16 @@ def test_fp16_step_matches_fp32_mode_full_size(oracle, sd_model, hw, t):
     tinyfusers_b200.set_precision("fp16")
     e16 = sd_model.get_model_output(unc.cuda(), ctx.cuda(), lat.cuda(), ts, g)
     assert rel_err(e16, e32) < 3e-2     # same bound as test_unet_gpu.py's CFG output against the oracle at 32x32
+
+
+def test_sample_loop_fp32(oracle, unet_sd, sd_model):
+    """StableDiffusion.sample in fp32 mode = the reference's host loop over __call__ (example/sd1.py:68-73)."""
+    lat, unc, ctx = oracle.make_inputs(1, 16, seed=21, ctx_seed=22)
+    ts, alphas, alphas_prev = oracle.sampler_schedule(3)
+    out = sd_model.sample(unc.cuda(), ctx.cuda(), lat.cuda(), ts, alphas, alphas_prev, 7.5)
+    sd64 = _sd64(unet_sd)
+    x = _d(lat)
+    with torch.no_grad():
+        for i in reversed(range(len(ts))):
+            x = oracle.sampler_step(sd64, _d(unc), _d(ctx), x, [ts[i]], _d(alphas[[i]]), _d(alphas_prev[[i]]), 7.5)
+    _check(out, x, tol=2e-4)      # three CFG steps, each ~700 fp32 operators, guidance 7.5

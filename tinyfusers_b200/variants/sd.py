@@ -89,6 +89,13 @@ class StableDiffusion:
     # ---- whole sampler loop on device (graph-captured steps) -----------------------------------------
     def sample(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance, use_graph=True):
         """Runs len(timesteps) DDIM steps, last-to-first like example/sd1.py:68-73, and returns the final latent."""
+        if fp32.enabled():      # parity mode: the reference's own host loop (example/sd1.py:68-73) over __call__, eager
+            a = torch.as_tensor(alphas, dtype=F32).reshape(-1)
+            ap = torch.as_tensor(alphas_prev, dtype=F32).reshape(-1)
+            for i in reversed(range(len(timesteps))):
+                latent = self(unconditional_context, context, latent, torch.tensor([float(timesteps[i])]),
+                              a[i:i + 1], ap[i:i + 1], guidance)
+            return latent
         s = self._sampler(latent.shape, context.shape[1])
         s.load(unconditional_context, context, latent)
         s.set_tables(timesteps, alphas, alphas_prev, guidance)
