@@ -190,11 +190,19 @@ int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, const void*
 /* Same attention with V in its NATURAL layout: v is (B*Tk_pad, ldv), head h at columns [h*dvp, (h+1)*dvp), dvp = head
  * dim padded with zero columns to a multiple of 16 (tiles use 32-byte swizzle atoms) or of 64 (128-byte atoms) - what a
  * fused [Q | K | V] projection GEMM writes directly, so no transposed copy of V is produced by anyone (V tiles are the
- * MN-major B operand of O += P V). causal: 0 | 1. */
+ * MN-major B operand of O += P V). causal = flags: bit 0 (TF_ATTN_CAUSAL) query t only sees keys <= t; bit 1
+ * (TF_ATTN_V_ONES_COLUMN) column d of every V head holds 1.0 in every key row (dvp > d; the projection GEMM's bias writes
+ * it), so the softmax denominator is column d of P V and needs no reduction of its own. */
+#define TF_ATTN_CAUSAL 1
+#define TF_ATTN_V_ONES_COLUMN 2
 int tf_attention_v_f16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                        long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH, int Tq,
                        int Tk, int Tk_pad, int d, int dp, int dvp, float scale, int causal, void* stream);
 int tf_attention_set_tuning(int force_bn);
+/* Kernel variant for tf_attention_v_f16: version 0 = automatic (the two-query-tile ping-pong kernel where whole pairs of
+   128-row query tiles fill the GPU, the one-tile kernel elsewhere), 1 = one-tile kernel only, 2 = ping-pong wherever it
+   applies; emu = exponentials per 8 evaluated on the FMA pipe instead of MUFU.EX2 (0, 2, 4; < 0 keeps the current value). */
+int tf_attention_set_variant(int version, int emu);
 /* debug hook: per-block clock64 stamps of one softmax warp ([64][8] int64; NULL = off; TF_ATT_TRACE builds only) */
 int tf_attention_set_timeline(long long* dev_buf);
 /* Same, under a causal mask: query t attends to keys <= t only (Tq == Tk). Replaces CLIPAttention's

@@ -19,6 +19,17 @@ def rel_err(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
+def rel_err_per_channel(a, b):
+    """The same metric per (image, channel) plane of an NCHW tensor, worst plane: max_c [ max|a_c - b_c| / max|b_c| ]. The
+    global metric normalises by the largest value of the whole tensor, so a wrong low-magnitude channel would pass it."""
+    import torch
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape and a.dim() == 4
+    num = (a - b).abs().amax(dim=(2, 3))
+    den = b.abs().amax(dim=(2, 3)).clamp_min(1e-12)
+    return (num / den).max().item()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import ref_ops

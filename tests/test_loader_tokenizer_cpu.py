@@ -92,3 +92,23 @@ def test_tokenizer_without_vocab_fails_loudly(monkeypatch):
     monkeypatch.delenv("TINYFUSERS_BPE_PATH", raising=False)
     with pytest.raises(RuntimeError, match="merges file"):
         ClipTokenizer()
+
+
+def test_tokenizer_matches_reference_golden_ids(tmp_path):
+    """Ids produced by the reference's OWN tokenizer (tests/golden/tokenizer_golden.json, oracle/make_tokenizer_golden.py imports
+    /root/reference/tinyfusers/tokenizer/clip.py unmodified) on a merges file stored in the golden: ours must give the same 77
+    integers for every prompt - lower-casing, whitespace cleaning, contractions, non-ASCII bytes, repeated symbols, in-text
+    special tokens, truncation at 75, framing and padding. Integer work: bit-exact."""
+    import gzip
+    import json
+    from tinyfusers_b200.tokenizer.clip import ClipTokenizer
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tokenizer_golden.json")))
+    path = os.path.join(tmp_path, "learned_bpe.txt.gz")
+    with gzip.open(path, "wb") as fh:
+        fh.write(gold["merges"].encode("utf-8"))
+    tok = ClipTokenizer(path)
+    assert len(gold["cases"]) >= 10
+    for case in gold["cases"]:
+        assert "ids" in case, case
+        assert tok.encode(case["prompt"]) == case["ids"], case["prompt"]
+        assert len(case["ids"]) == 77 and case["ids"][0] == 49406 and case["ids"][-1] == 49407

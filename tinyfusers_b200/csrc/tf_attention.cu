@@ -385,6 +385,376 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// =====================================================================================================================
+// tf_attention2_kernel: two query tiles per CTA in ping-pong (round 2).
+//
+// What limited tf_attention_kernel on the 4096-token self-attention (profiles/attention_timeline_r1.md): a softmax warp's
+// key block is a ~1800-cycle serial chain of which only ~700 are exponentials - the rest is waiting for S, the shared-memory
+// round trip of P (st.shared + fence.proxy.async), and barrier latency - so two co-resident CTAs keep the XU pipe ~55 % busy.
+// Here one CTA (one per SM, 384 threads) owns TWO 128-row query tiles of the same (batch, head) that share every K/V tile:
+//   warp 0      TMA producer (Q0, Q1, K/V ring)
+//   warp 1      tcgen05.mma issuer
+//   warps 4-7   softmax of tile 0,   warps 8-11  softmax of tile 1   (one thread per query row)
+// * S is double-buffered per tile in TMEM (64-key blocks): S_{j+1} = Q K_{j+1}^T is issued before the P V_j of either tile,
+//   so a softmax warpgroup never waits for the tensor core in steady state - its chain is load, max, exp, store.
+// * P never visits shared memory: the softmax writes fp16 P over the S columns it has just consumed (tcgen05.st) and
+//   O += P V is a TS MMA (A operand from tensor memory). No st.shared, no fence.proxy.async.
+// * EMU of every 8 exponentials run on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, packed FFMA2 /
+//   FADD2), the rest on MUFU.EX2: at head dim 40 the kernel is bound by 16 MUFU lanes per SM, not by the tensor core
+//   (per 128x128 block: ~512 tensor cycles vs 1024 MUFU cycles).
+// TMEM per tile: [S buf 0 (64) | S buf 1 (64) | O, L (ol_cols)]; P_j aliases the first 32 columns of S buffer j % 2.
+// =====================================================================================================================
+constexpr int kA2Threads = 384;
+constexpr int BN2 = 64;
+
+struct Attn2Params {
+  int B, NH, Tq, Tk, Tk_pad, d, dp, dov, v_atom, l_off, ol_cols, nkv, stages, causal;
+  int tile_cols;   // TMEM columns per query tile: 128 + ol_cols
+  int order;       // 1: the two softmax warpgroups take turns on the exponential phase
+  int l_sel;       // position of the row sum inside the 16-column group at l_off (0 or 8)
+  int l_mma;       // 1: row sums by an extra N = 16 MMA against a ones tile (at l_off); 0: V carries a ones column at index d
+  long long* timeline;   // debug (TF_ATT_TRACE build): clock stamps of CTA (0,0,0): [who: softmax 0, softmax 1, MMA][block < 64][8]
+  uint32_t tmem_cols;
+  float scale_log2;
+  __half* out;
+  long long osb, osh, ost;
+};
+
+// 2^x for x <= ~8 on the FMA pipe, two values per instruction: x = n + f, n = round(x) (magic-number add), f in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (max relative error 7.6e-5, below half an fp16 ulp of the P it produces), 2^n by
+// adding n into the exponent field.
+__device__ __forceinline__ void exp2_fma_pair(float& x0, float& x1) {
+  const float kMagic = 12582912.f;   // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = tf::pack_f32x2(x0, x1);
+  const uint64_t t = tf::add_f32x2(x, tf::pack_f32x2(kMagic, kMagic));
+  const uint64_t n = tf::add_f32x2(t, tf::pack_f32x2(-kMagic, -kMagic));
+  const uint64_t f = tf::fma_f32x2(n, tf::pack_f32x2(-1.f, -1.f), x);
+  uint64_t pl = tf::fma_f32x2(f, tf::pack_f32x2(0.05520550534129143f, 0.05520550534129143f),
+                              tf::pack_f32x2(0.24261397123336792f, 0.24261397123336792f));
+  pl = tf::fma_f32x2(pl, f, tf::pack_f32x2(0.6932547688484192f, 0.6932547688484192f));
+  pl = tf::fma_f32x2(pl, f, tf::pack_f32x2(0.9999276995658875f, 0.9999276995658875f));
+  float p0, p1, t0, t1;
+  tf::unpack_f32x2(pl, p0, p1);
+  tf::unpack_f32x2(t, t0, t1);
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+#if TF_ATT_TRACE
+#define ATT2_STAMP(who, i) do { if (p.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) p.timeline[((who) * 64 + j) * 8 + (i)] = clock64(); } while (0)
+#else
+#define ATT2_STAMP(who, i) do { } while (0)
+#endif
+template <int EMU>
+__global__ void __launch_bounds__(kA2Threads, 1)
+tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  tf::pdl_trigger();
+  const uint32_t raw_u32 = tf::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int ST = p.stages;
+
+  const uint32_t q_bytes = BQ * p.dp * 2;
+  const uint32_t k_bytes = BN2 * p.dp * 2;
+  const uint32_t v_bytes = BN2 * p.dov * 2;
+  const uint32_t smem_q = smem_base;                       // two query tiles
+  const uint32_t smem_k = smem_q + 2 * q_bytes;
+  const uint32_t smem_v = smem_k + ST * k_bytes;
+  const uint32_t smem_ones = smem_v + ST * v_bytes;        // 16 x 64 fp16 ones: B operand of L = P . 1
+  const uint32_t bar_base = smem_ones + 2048;
+  auto q_full = [&](int t) { return bar_base + 8u * t; };
+  auto kv_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (2 + ST + s); };
+  auto s_full = [&](int t, int buf) { return bar_base + 8u * (2 + 2 * ST + 2 * t + buf); };
+  auto p_full = [&](int t) { return bar_base + 8u * (6 + 2 * ST + t); };
+  auto pv_done = [&](int t) { return bar_base + 8u * (8 + 2 * ST + t); };
+  const uint32_t tmem_slot = bar_base + 8u * (10 + 2 * ST);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+  if (warp == 0 && lane == 0) {
+    tf::tma_prefetch_desc(&tmQ);
+    tf::tma_prefetch_desc(&tmK);
+    tf::tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int t = 0; t < 2; ++t) {
+      tf::mbar_init(q_full(t), 1);
+      tf::mbar_init(s_full(t, 0), 1);
+      tf::mbar_init(s_full(t, 1), 1);
+      tf::mbar_init(p_full(t), 128);
+      tf::mbar_init(pv_done(t), 1);
+    }
+    for (int s = 0; s < ST; ++s) {
+      tf::mbar_init(kv_full(s), 1);
+      tf::mbar_init(kv_empty(s), 1);
+    }
+    tf::fence_mbar_init();
+  }
+  if (warp == 2) {
+    tf::tmem_alloc(tmem_slot, p.tmem_cols);
+    tf::tmem_relinquish();
+  }
+  if (warp == 3) {   // 2 KB of fp16 1.0
+    for (int i = lane; i < 128; i += 32)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_ones + i * 16u), "r"(0x3C003C00u) : "memory");
+    tf::fence_proxy_async_smem();
+  }
+  tf::tcgen05_fence_before();
+  __syncthreads();
+  tf::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  tf::pdl_wait();
+
+  const int nkv = p.nkv;
+  const int slabs = p.dp / 16;
+  auto tmem_s = [&](int t, int buf) { return tmem_base + (uint32_t)(t * p.tile_cols + buf * BN2); };
+  auto tmem_o = [&](int t) { return tmem_base + (uint32_t)(t * p.tile_cols + 2 * BN2); };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int t = 0; t < 2; ++t) {
+        tf::mbar_expect_tx(q_full(t), q_bytes);
+        tf::tma_load_3d(smem_q + t * q_bytes, &tmQ, q_full(t), 0, b * p.Tq + (2 * qt + t) * BQ, h * slabs);
+      }
+      const int nblk = p.dov / p.v_atom;
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % ST;
+        const uint32_t u = j / ST;
+        tf::mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
+        tf::mbar_expect_tx(kv_full(s), k_bytes + v_bytes);
+        const int key0 = b * p.Tk_pad + j * BN2;
+        tf::tma_load_3d(smem_k + s * k_bytes, &tmK, kv_full(s), 0, key0, h * slabs);
+        for (int nb = 0; nb < nblk; ++nb)   // one (64 keys x v_atom columns) box per column block of the head
+          tf::tma_load_2d(smem_v + s * v_bytes + nb * (BN2 * p.v_atom * 2), &tmV, kv_full(s), h * p.dov + nb * p.v_atom, key0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop converged and one elected lane issues: descriptors, TMEM addresses and barrier
+    // addresses are then warp-uniform (uniform registers feed UTCHMMA directly instead of per-instruction R2UR round
+    // trips), they advance by adds instead of being rebuilt, and stage / phase are counters instead of divisions. A single
+    // lane rebuilding two 64-bit descriptors per instruction needed ~100 cycles per MMA and 22 MMAs per key block: the issue
+    // loop, not the softmax, set the block period of the first version (2650 cycles; tools/dev_attn2_timeline.py).
+    const bool elected = tf::elect_one();
+    const uint32_t idesc_s = tf::umma_idesc_f16(BQ, BN2);
+    const uint32_t idesc_o = tf::umma_idesc_f16(BQ, p.dov) | (1u << 16);   // bit 16: B (V, natural layout) is MN-major
+    const uint32_t idesc_l = tf::umma_idesc_f16(BQ, 16);
+    // descriptor of slab k of query tile t: qd0 + t * q_step + k * 256 (slabs are BQ * 32 bytes apart; the start-address
+    // field counts 16-byte units and never carries out of its 14 bits); of slab k of K stage s: kd0 + s * k_step + k * 128
+    const uint64_t qd0 = umma_desc_sw32_kmajor(smem_q), kd0 = umma_desc_sw32_kmajor(smem_k);
+    const uint64_t q_step = q_bytes >> 4, k_step = k_bytes >> 4, v_step = v_bytes >> 4;
+    const bool v128 = p.v_atom == 64;
+    const uint64_t vd0 = v128 ? umma_desc_sw128_mnmajor(smem_v, BN2 * 128u) : umma_desc_sw32_mnmajor(smem_v, BN2 * 32u);
+    const uint64_t v_kstep = v128 ? (2048u >> 4) : (512u >> 4);            // 16 keys further down the V tile
+    const uint64_t ones_d = tf::umma_desc_sw128_kmajor(smem_ones);
+    const bool l_mma = p.l_mma != 0;
+    const uint32_t ts0 = tmem_base, to0 = tmem_base + 2 * BN2, tcols = (uint32_t)p.tile_cols;
+    int qs = 0;            // K/V stage and phase of the block whose S is issued next
+    uint32_t qphase = 0;
+    uint64_t kd = kd0;
+    auto issue_qk = [&](int jj) {   // S_jj of both tiles; buffer jj % 2 held P_{jj-2}, whose P V MMAs were issued earlier (in order)
+      tf::mbar_wait(kv_full(qs), qphase);
+      tf::tcgen05_fence_after();
+      const uint32_t sb = (uint32_t)(jj & 1) * BN2;
+      if (elected) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          uint64_t qd = qd0 + (uint64_t)t * q_step, kk = kd;
+          for (int k = 0; k < slabs; ++k, qd += 256, kk += 128)
+            tf::umma_f16_ss(ts0 + t * tcols + sb, qd, kk, idesc_s, k > 0 ? 1u : 0u);
+          tf::umma_commit(s_full(t, jj & 1));
+        }
+      }
+      __syncwarp();
+      kd += k_step;
+      if (++qs == ST) { qs = 0; qphase ^= 1u; kd = kd0; }
+    };
+    tf::mbar_wait(q_full(0), 0);
+    tf::mbar_wait(q_full(1), 0);
+    issue_qk(0);
+    int vs = 0;
+    uint64_t vd = vd0;
+    for (int j = 0; j < nkv; ++j) {
+      if (elected) ATT2_STAMP(2, 0);
+      if (j + 1 < nkv) issue_qk(j + 1);
+      if (elected) ATT2_STAMP(2, 1);
+      const uint32_t sb = (uint32_t)(j & 1) * BN2;
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        tf::mbar_wait(p_full(t), (uint32_t)j & 1u);
+        tf::tcgen05_fence_after();
+        if (elected) {
+          ATT2_STAMP(2, 2 + 2 * t);
+          const uint32_t pa = ts0 + t * tcols + sb;   // P_j: 64 fp16 per row in 32 columns
+          const uint32_t od = to0 + t * tcols;
+#pragma unroll
+          for (int k = 0; k < BN2 / 16; ++k) {
+            tf::umma_f16_ts(od, pa + 8u * k, vd + (uint64_t)k * v_kstep, idesc_o, k > 0 ? 1u : acc0);
+            // L += P . ones, from the same fp16 P the numerator uses; issued after P V so a non-accumulating P V cannot
+            // wipe it. Skipped when V itself carries a column of ones (the row sums then ARE column d of O).
+            if (l_mma) tf::umma_f16_ts(od + p.l_off, pa + 8u * k, ones_d + 2u * k, idesc_l, k > 0 ? 1u : acc0);
+          }
+          tf::umma_commit(pv_done(t));
+          ATT2_STAMP(2, 3 + 2 * t);
+        }
+        __syncwarp();
+      }
+      if (elected) tf::umma_commit(kv_empty(vs));
+      __syncwarp();
+      vd += v_step;
+      if (++vs == ST) { vs = 0; vd = vd0; }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax / rescale / epilogue: warps 4-7 tile 0, warps 8-11 tile 1 =====================
+    const int t = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    const int qrow0 = (2 * qt + t) * BQ;
+    const float sc = p.scale_log2;
+    float m_run = -INFINITY;   // reference max of this row (scaled log2 domain); lazily updated (see tf_attention_kernel)
+    const uint32_t o_addr = tmem_o(t) + lane_field;
+    if (p.order && t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");   // tile 0 takes the first turn
+    const bool stamp = q == 0 && lane == 0;
+    for (int j = 0; j < nkv; ++j) {
+      if (stamp) ATT2_STAMP(t, 0);
+      tf::mbar_wait(s_full(t, j & 1), (uint32_t)(j >> 1) & 1u);
+      tf::tcgen05_fence_after();
+      if (stamp) ATT2_STAMP(t, 1);
+      const uint32_t s_addr = tmem_s(t, j & 1) + lane_field;
+      uint32_t v[64];
+      tf::tmem_ld_x32(s_addr, v);
+      tf::tmem_ld_x32(s_addr + 32, v + 32);
+      tf::tmem_ld_wait();
+      if (stamp) ATT2_STAMP(t, 2);
+      int valid = min(BN2, p.Tk - j * BN2);
+      if (p.causal) valid = min(valid, qrow0 + row + 1 - j * BN2);
+      if (valid < BN2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) v[i] = 0xff800000u;   // -inf
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = tf::fmax3(mx4[u], __uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;   // scale > 0
+      float alpha = 1.0f;
+      if (mx > m_run + 8.0f) {          // also taken on the first block (m_run = -inf)
+        alpha = exp2f(m_run - mx);      // 0 on the first block
+        m_run = mx;
+      }
+      const float neg_m = -m_run;
+      uint32_t pk[32];
+      const uint64_t sc2 = tf::pack_f32x2(sc, sc), nm2 = tf::pack_f32x2(neg_m, neg_m);
+      // The exponential phases of the two warpgroups alternate (named barriers 1 / 2, 256 threads each: 128 wait, 128
+      // arrive): while one tile's rows occupy the MUFU pipe the other tile loads S, takes its row max, stores P and waits
+      // for the tensor core. Without the order the two start in lockstep and collide on the pipe (measured on
+      // tf_attention_kernel, profiles/attention_timeline_r1.md).
+      if (stamp) ATT2_STAMP(t, 3);
+      if (p.order) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      if (stamp) ATT2_STAMP(t, 4);
+#pragma unroll
+      for (int i = 0; i < 64; i += 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const uint64_t xx = tf::fma_f32x2(tf::pack_f32x2(__uint_as_float(v[i + u]), __uint_as_float(v[i + u + 1])), sc2, nm2);
+          tf::unpack_f32x2(xx, x[u], x[u + 1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          if (u >= 8 - EMU) {
+            exp2_fma_pair(x[u], x[u + 1]);
+          } else {
+            x[u] = exp2f(x[u]);
+            x[u + 1] = exp2f(x[u + 1]);
+          }
+          __half2 h2v = __floats2half2_rn(x[u], x[u + 1]);
+          pk[(i + u) >> 1] = *reinterpret_cast<uint32_t*>(&h2v);
+        }
+      }
+      if (stamp) ATT2_STAMP(t, 5);
+      if (p.order && (t == 0 || j + 1 < nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // the other tile's turn
+      // P V_{j-1} was issued a whole softmax block ago: this wait is (almost) always already satisfied. It is taken on EVERY
+      // block so that this thread observes every phase of pv_done in order - a parity wait that skips phases aliases
+      // (phase j-1 and phase j-3 have the same parity) and would let the rescale / epilogue below race the tensor core.
+      if (j > 0) {
+        tf::mbar_wait(pv_done(t), (uint32_t)(j - 1) & 1u);
+        tf::tcgen05_fence_after();
+      }
+      // rescale the running output if any row of this warp moved its max (rare after the first blocks: lazy threshold 2^8)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        for (int c = 0; c < p.ol_cols; c += 16) {   // O and the L columns
+          uint32_t o[16];
+          tf::tmem_ld_x16(o_addr + c, o);
+          tf::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tf::tmem_st_x16(o_addr + c, o);
+        }
+      }
+      if (stamp) ATT2_STAMP(t, 6);
+      tf::tmem_st_x32(s_addr, pk);   // P_j over the first 32 columns of the S buffer this thread has just drained
+      tf::tmem_st_wait();
+      tf::tcgen05_fence_before();
+      tf::mbar_arrive(p_full(t));
+      if (stamp) ATT2_STAMP(t, 7);
+    }
+    // ---- epilogue: O / l -> fp16 -> global ----
+    tf::mbar_wait(pv_done(t), (uint32_t)(nkv - 1) & 1u);
+    tf::tcgen05_fence_after();
+    float inv_l;
+    {
+      uint32_t l16[16];
+      tf::tmem_ld_x16(o_addr + p.l_off, l16);
+      tf::tmem_ld_wait();
+      inv_l = 1.0f / __uint_as_float(p.l_sel ? l16[8] : l16[0]);
+    }
+    const int tq = qrow0 + row;
+    __half* orow = p.out + (long long)b * p.osb + (long long)h * p.osh + (long long)tq * p.ost;
+    for (int c = 0; c < p.d; c += 16) {
+      uint32_t o[16];
+      tf::tmem_ld_x16(o_addr + c, o);
+      tf::tmem_ld_wait();
+      if (tq < p.Tq) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c + g * 8 < p.d) {
+            tf::Pack16 pk8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              pk8.h2[i] = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]) * inv_l,
+                                            __uint_as_float(o[g * 8 + 2 * i + 1]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + g * 8) = pk8.v;
+          }
+        }
+      }
+    }
+  }
+
+  tf::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tf::tcgen05_fence_after();
+    tf::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int g_attn_version = 0;   // 0 auto, 1 tf_attention_kernel only, 2 tf_attention2_kernel wherever it applies
+int g_attn_emu = 2;       // exponentials per 8 evaluated on the FMA pipe (0, 2 or 4)
+int g_attn_order = 1;     // softmax warpgroups alternate on the exponential phase
+
 int g_force_attn_bn = 0;
 int g_force_attn_occ = 0;
 long long* g_attn_timeline = nullptr;
@@ -393,6 +763,14 @@ long long* g_attn_timeline = nullptr;
 
 extern "C" int tf_attention_set_timeline(long long* dev_buf) {
   g_attn_timeline = dev_buf;   // >= 64 * 8 int64; debug only (stamps exist in TF_ATT_TRACE builds)
+  return TF_OK;
+}
+
+extern "C" int tf_attention_set_variant(int version, int emu) {
+  TF_CHECK_ARG(version >= 0 && version <= 2 && (emu < 0 || emu % 10 == 0 || emu % 10 == 2 || emu % 10 == 4) && emu < 20,
+               "tf_attention_set_variant: version in {0 auto, 1, 2}, emu in {0, 2, 4} (+ 10: warpgroup order off; < 0: keep)");
+  g_attn_version = version;
+  if (emu >= 0) { g_attn_emu = emu % 10; g_attn_order = emu < 10 ? 1 : 0; }
   return TF_OK;
 }
 
@@ -408,15 +786,18 @@ extern "C" int tf_attention_set_tuning(int force_bn) {
 static int attention_impl(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,
                           long long out_stride_b, long long out_stride_h, long long out_stride_t, int B,
                           int NH, int Tq, int Tk, int Tk_pad, int d, int dp, float scale, int causal, int vnat, int dvp,
-                          void* stream_) {
+                          void* stream_, int ones_col = 0) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int dov = vnat ? dvp : dp;   // O columns
   // V's pad columns are exact zeros, so the PV MMA adds exact zeros to O's pad columns: when at least 16 of them lie beyond
   // the last 16-column group that holds real head-dim elements, the L = P . 1 accumulator lives there (issued after PV in
   // every k-step, so the first, non-accumulating PV MMA cannot wipe it) and TMEM needs BN + dov columns instead of + 16 more
   const int d16 = (d + 15) / 16 * 16;
-  const int l_off = (vnat && dov - 16 >= d16) ? dov - 16 : dov;
+  // ones_col: column d of every V head holds 1.0 (the projection GEMM's bias puts it there), so column d of O = P V IS the row
+  // sum: tf_attention2_kernel then issues no L MMA at all; tf_attention_kernel keeps its own L columns clear of it
+  const int l_off = ones_col ? dov : ((vnat && dov - 16 >= d16) ? dov - 16 : dov);
   const int ol_cols = l_off + 16 > dov ? l_off + 16 : dov;
+  if (ones_col) TF_CHECK_ARG(vnat && dvp > d, "tf_attention_v_f16: the ones column needs a padded V head (dvp %d > d %d)", dvp, d);
   TF_CHECK_ARG(q && k && vt && out, "tf_attention_f16: null pointer");
   TF_CHECK_ARG(B > 0 && NH > 0 && Tq > 0 && Tk > 0 && Tk_pad >= Tk, "tf_attention_f16: bad dims");
   TF_CHECK_ARG(dp % 16 == 0 && dp >= 16 && dp <= 256 && d <= dp && d % 8 == 0,
@@ -435,6 +816,83 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
                    ((uintptr_t)out & 15) == 0,
                "tf_attention_f16: pointers must be 16-byte aligned");
 
+  // ---- two-tile ping-pong kernel (tf_attention2_kernel): natural-layout V, whole pairs of 128-row query tiles, and a grid
+  // that gives (nearly) every SM a CTA; everything else stays on tf_attention_kernel ----
+  {
+    const long pairs = (long)(Tq / (2 * BQ)) * NH * B;
+    const int ol2 = ones_col ? dov : ol_cols;     // TMEM columns of O (+ L) per tile in the two-tile kernel
+    const bool can2 = vnat && Tq % (2 * BQ) == 0 && Tk >= 2 * BN2 && 2 * BN2 + ol2 <= 256;
+    const bool want2 = g_attn_version == 2 || (g_attn_version == 0 && pairs >= 120);
+    if (can2 && want2) {
+      Attn2Params p2{};
+      p2.B = B; p2.NH = NH; p2.Tq = Tq; p2.Tk = Tk; p2.Tk_pad = Tk_pad; p2.d = d; p2.dp = dp; p2.dov = dov;
+      p2.v_atom = v_atom; p2.causal = causal ? 1 : 0;
+      p2.l_mma = ones_col ? 0 : 1;
+      p2.l_off = ones_col ? (d & ~15) : l_off;      // 16-column group that holds the row sum ...
+      p2.l_sel = ones_col ? (d & 15) : 0;           // ... and its position inside the group (d % 8 == 0: 0 or 8)
+      p2.ol_cols = ol2;
+      p2.nkv = ceil_div_i(Tk, BN2);
+      p2.order = g_attn_order;
+      p2.timeline = g_attn_timeline;
+      p2.tile_cols = 2 * BN2 + ol2;
+      uint32_t cols2 = 32;
+      while (cols2 < 2u * (uint32_t)p2.tile_cols) cols2 <<= 1;
+      p2.tmem_cols = cols2;
+      p2.scale_log2 = scale * 1.4426950408889634f;
+      p2.out = reinterpret_cast<__half*>(out);
+      p2.osb = out_stride_b; p2.osh = out_stride_h; p2.ost = out_stride_t;
+      const size_t qb = (size_t)BQ * dp * 2, kb = (size_t)BN2 * dp * 2, vb = (size_t)BN2 * dov * 2;
+      long room = (long)227 * 1024 - 2048 - (long)(2 * qb) - 2048 - 1024;
+      int st2 = (int)(room / (long)(kb + vb));
+      if (st2 > 6) st2 = 6;
+      if (st2 > p2.nkv) st2 = p2.nkv;
+      if (st2 >= 2) {
+        p2.stages = st2;
+        size_t smem2 = 2 * qb + (size_t)st2 * (kb + vb) + 2048 + 1024 + 1024;
+        if (smem2 < (size_t)120 * 1024) smem2 = (size_t)120 * 1024;   // one CTA per SM: the 512-column TMEM allocation is never contended
+        CUtensorMap tmQ, tmK, tmV;
+        {
+          uint64_t dims[3] = {16, (uint64_t)B * Tq, (uint64_t)(ldq / 16)};
+          uint64_t strides[2] = {(uint64_t)ldq * 2, 32};
+          uint32_t box[3] = {16, BQ, (uint32_t)(dp / 16)};
+          uint32_t es[3] = {1, 1, 1};
+          int rc = tf_encode_tmap(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_32B);
+          if (rc) return rc;
+        }
+        {
+          uint64_t dims[3] = {16, (uint64_t)B * Tk_pad, (uint64_t)(ldk / 16)};
+          uint64_t strides[2] = {(uint64_t)ldk * 2, 32};
+          uint32_t box[3] = {16, (uint32_t)BN2, (uint32_t)(dp / 16)};
+          uint32_t es[3] = {1, 1, 1};
+          int rc = tf_encode_tmap(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, k, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_32B);
+          if (rc) return rc;
+        }
+        {
+          uint64_t dims[2] = {(uint64_t)ldvt, (uint64_t)B * Tk_pad};
+          uint64_t strides[1] = {(uint64_t)ldvt * 2};
+          uint32_t box[2] = {(uint32_t)v_atom, (uint32_t)BN2};
+          uint32_t es[2] = {1, 1};
+          int rc = tf_encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt, dims, strides, box, es,
+                                  v_atom == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
+          if (rc) return rc;
+        }
+        static bool attr2_set = false;
+        if (!attr2_set) {
+          TF_CUDA(cudaFuncSetAttribute(tf_attention2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          TF_CUDA(cudaFuncSetAttribute(tf_attention2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          TF_CUDA(cudaFuncSetAttribute(tf_attention2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          attr2_set = true;
+        }
+        dim3 grid2(Tq / (2 * BQ), NH, B);
+        if (g_attn_emu == 0) TF_LAUNCH((tf_attention2_kernel<0>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
+        else if (g_attn_emu == 4) TF_LAUNCH((tf_attention2_kernel<4>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
+        else TF_LAUNCH((tf_attention2_kernel<2>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
+        TF_LAUNCH_CHECK();
+        tf_launch_count_add(1);
+        return TF_OK;
+      }
+    }
+  }
   // 128-key blocks when two CTAs per SM still fit (TMEM <= 256 columns, >= 2 K/V stages in half an SM's shared
   // memory) and the sequence is long enough to amortise them; 64-key blocks otherwise
   auto fits2 = [&](int bn) {
@@ -562,9 +1020,11 @@ extern "C" int tf_attention_f16(const void* q, int ldq, const void* k, int ldk, 
 extern "C" int tf_attention_v_f16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                                   long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH,
                                   int Tq, int Tk, int Tk_pad, int d, int dp, int dvp, float scale, int causal, void* stream) {
+  const int ones_col = (causal >> 1) & 1;   // flags: bit 0 causal, bit 1 TF_ATTN_V_ONES_COLUMN
+  causal &= 1;
   if (causal) TF_CHECK_ARG(Tq == Tk, "tf_attention_v_f16: causal masking needs Tq == Tk (got %d, %d)", Tq, Tk);
   return attention_impl(q, ldq, k, ldk, v, ldv, out, out_stride_b, out_stride_h, out_stride_t, B, NH, Tq, Tk, Tk_pad, d, dp,
-                        scale, causal, 1, dvp, stream);
+                        scale, causal, 1, dvp, stream, ones_col);
 }
 
 extern "C" int tf_attention_causal_f16(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* out,

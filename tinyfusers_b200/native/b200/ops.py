@@ -64,6 +64,7 @@ _SIGNATURES = {
     "tf_attention_v_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "tf_attention_set_tuning": (c_int, [c_int]),
+    "tf_attention_set_variant": (c_int, [c_int, c_int]),
     "tf_attention_set_timeline": (c_int, [_P]),
     "tf_attention_causal_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),

@@ -6,23 +6,63 @@ import torch
 F16, F32 = torch.float16, torch.float32
 
 
-def _key(*tensors):
-    return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+import weakref
+
+# Bumped whenever any packed weight is (re)built and by storage.state.update_state: captured CUDA graphs bake in the
+# addresses of packed weights, so whoever holds a graph (variants.sd.SamplerEngine, vae.decoder.DecoderEngine) records the
+# generation at capture time and re-captures when it has moved.
+_generation = 0
+
+
+def generation():
+    return _generation
+
+
+def bump_generation():
+    global _generation
+    _generation += 1
+    return _generation
+
+
+def _version(t):
+    try:
+        return t._version
+    except Exception:   # tensors created under torch.inference_mode() have no version counter
+        return 0
+
+
+def _same(entry_refs, tensors):
+    """Identity + in-place-version comparison. Source tensors are held by weak reference, so a freed-and-reallocated
+    address (same data_ptr, version 0, same shape) can never be mistaken for the tensor that was packed."""
+    if len(entry_refs) != len(tensors):
+        return False
+    for (ref, ver), t in zip(entry_refs, tensors):
+        if t is None:
+            if ref is not None:
+                return False
+            continue
+        if ref is None or ref() is not t or ver != _version(t):
+            return False
+    return True
 
 
 def cached(obj, name, tensors, builder):
     """Cache `builder()` on `obj` until any of `tensors` is replaced or modified in place."""
-    key = _key(*tensors)
     slot = "_pk_" + name
     hit = obj.__dict__.get(slot)
-    if hit is not None and hit[0] == key:
+    if hit is not None and _same(hit[0], tensors):
         return hit[1]
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("tinyfusers_b200: weights changed while a CUDA graph was being captured; run one eager step "
+                           "(or call update_state before the first call) so that packing happens outside the capture")
     val = builder()
     if torch.cuda.is_available():
         # the packed tensors are handed to kernels as STATIC weights (TF_GEMM_W_STATIC: fetched before the dependency
         # wait of programmatic dependent launch), so they must be complete in memory before anything else is enqueued
         torch.cuda.current_stream().synchronize()
-    obj.__dict__[slot] = (key, val)
+    refs = tuple((None, 0) if t is None else (weakref.ref(t), _version(t)) for t in tensors)
+    obj.__dict__[slot] = (refs, val)
+    bump_generation()
     return val
 
 

@@ -8,6 +8,8 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
+from .. import packing
+
 
 def _default_device():
     return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
@@ -40,6 +42,7 @@ def update_state(obj, state_dict, prefix=''):
                     print(f"skipped: {key}")
                     continue
                 obj[k] = _to_device_tensor(state_dict[key], _default_device())
+                packing.bump_generation()   # captured sampler graphs bake in packed-weight addresses: they re-capture
             else:
                 pre = f"{prefix}.{k}" if prefix != '' else f"{k}"
                 update_state(v, state_dict, f"{pre}")

@@ -52,15 +52,17 @@ class ClipTokenizer:
         opener = gzip.open if str(bpe_path).endswith(".gz") else open
         with opener(bpe_path, "rb") as fh:
             lines = fh.read().decode("utf-8").split("\n")
-        rules = [tuple(l.split()) for l in lines[1:_N_MERGES + 1]]       # line 0 is the file's version header
-        rules = [r for r in rules if len(r) == 2]
+        # line 0 is the file's version header. Every line of the slice takes a vocabulary slot, as in the reference
+        # (clip.py:13-19) - including an empty last line when the file is shorter than the slice - so ids agree for any file
+        rules = [tuple(l.split()) for l in lines[1:_N_MERGES + 1]]
         self.byte_encoder = bytes_to_unicode()
         symbols = list(self.byte_encoder.values())
-        vocab = symbols + [s + _EOW for s in symbols] + [a + b for a, b in rules]
-        # ids of the special tokens are fixed (49406 / 49407) whatever the number of rules in the file
+        # the two special tokens close the vocabulary (reference clip.py:20): with the full 48 894-rule file they land on
+        # 49406 / 49407, the ids `encode` frames every prompt with; with a shorter file an in-text "<|endoftext|>" gets the
+        # position the file implies, exactly as in the reference
+        vocab = symbols + [s + _EOW for s in symbols] + ["".join(r) for r in rules] + ["<|startoftext|>", "<|endoftext|>"]
         self.encoder = {tok: i for i, tok in enumerate(vocab)}
-        self.encoder["<|startoftext|>"], self.encoder["<|endoftext|>"] = BOS, EOS
-        self.bpe_ranks = {r: i for i, r in enumerate(rules)}
+        self.bpe_ranks = {r: i for i, r in enumerate(rules) if len(r) == 2}
         self.cache = {"<|startoftext|>": "<|startoftext|>", "<|endoftext|>": "<|endoftext|>"}
         self.pat = re.compile(r"<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[^\s]+", re.IGNORECASE)
 

@@ -14,7 +14,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from .. import fp32, get_layernorm_strided, get_quirks
+from .. import fp32, get_layernorm_strided, get_quirks, packing
 from ..native.b200.ops import b200
 from ..runtime import F32, require_cuda, stream_ptr
 from ..vae.encoder import CLIPTextTransformer
@@ -101,6 +101,13 @@ class StableDiffusion:
         s.set_tables(timesteps, alphas, alphas_prev, guidance)
         s.run(len(timesteps), use_graph=use_graph)
         return s.latent.clone()
+
+    def sample_dp(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance, group=None):
+        """`sample` sharded by image over the ranks of an initialised torch.distributed group (one process per GPU, one
+        UNet replica each; the only collective is the all-gather of the final latents, tinyfusers_b200/dp.py). Every rank
+        passes the full batch and receives all final latents. Reference: the loop of example/sd1.py:68-73 per image."""
+        from .. import dp
+        return dp.sample_sharded(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance, group)
 
     def _sampler(self, latent_shape, ctx_tokens):
         B, C, H, W = latent_shape
@@ -201,7 +208,7 @@ class SamplerEngine:
         device step index (sampler loop); advance=False is the graph behind the drop-in __call__."""
         if not getattr(self, "_warm", False):
             lat, idx = self.latent.clone(), self.idx.clone()
-            self.enqueue_step(advance=False)  # eager warm-up: lazy attribute setup, weight packing
+            self.enqueue_step(advance=False)  # eager warm-up: lazy attribute setup, weight packing (never inside a capture)
             torch.cuda.synchronize()
             self.latent.copy_(lat)
             self.idx.copy_(idx)
@@ -214,12 +221,20 @@ class SamplerEngine:
         return g
 
     def _graph(self, advance):
+        """The captured step for (advance, guidance), valid for the CURRENT weights: a graph bakes in the addresses of the
+        packed fp16 weights, so when `packing.generation()` has moved since capture (update_state, a weight assigned and
+        repacked by an eager call) every graph of this engine is dropped and the step is re-captured after an eager
+        warm-up that repacks - a stale graph would replay old (or freed) weights."""
+        gen = packing.generation()
+        if getattr(self, "_graphs_gen", None) != gen:
+            self._graphs, self._warm = {}, False
         key = (advance, self.guidance)
-        if not hasattr(self, "_graphs"):
-            self._graphs = {}
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = self.capture(advance)
+            # the warm-up step inside capture() may have repacked (bumping the generation): the graphs are valid for the
+            # generation seen AFTER it, provided nothing moved during the capture itself (packing.cached raises there)
+            self._graphs_gen = packing.generation()
         return g
 
     def step_once(self, use_graph=True):
