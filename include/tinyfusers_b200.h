@@ -128,6 +128,10 @@ int tf_conv2d_nhwc_skip_f16(const void* x, int NI, int H, int W, int Cin, int x_
 int tf_gemm_set_tuning(int force_bn, int force_splits);
 /* test / tuning hook: 0 = auto, 1 = single-CTA tiles only, 2 = CTA-pair (cta_group::2, 256-row) tiles where M > 128 */
 int tf_gemm_set_ctas(int force_ctas);
+/* Split-K folded inside a thread-block cluster through distributed shared memory (1) or through an fp32 workspace + fold
+   kernel (0, the default: measured faster on every shape of the step); < 0 restores the default (environment
+   TINYFUSERS_B200_CLUSTER_SPLITK). */
+int tf_gemm_set_cluster_splitk(int on);
 /* measured tile choices: (is_conv, M, N, K, class) -> (BN, split-K factor, CTAs per tile) overrides the built-in cost
  * model for that shape. class bits: 1 GEGLU, 2 fp32 out, 4 GroupNorm statistics, 8 residual, 16 stride-2 conv. For a
  * conv, M = NI*Ho*Wo, N = Cout, K = 9*Cin. Entries that do not fit a call (workspace too small, ...) are ignored.
@@ -205,6 +209,9 @@ int tf_attention_set_tuning(int force_bn);
 int tf_attention_set_variant(int version, int emu);
 /* debug hook: per-block clock64 stamps of one softmax warp ([64][8] int64; NULL = off; TF_ATT_TRACE builds only) */
 int tf_attention_set_timeline(long long* dev_buf);
+/* debug: pinned host buffer (>= 64 bytes, zeroed) in which a timed-out barrier wait of the attention kernels records
+   {1, code, block x, y, z, warp, key block, parity} before it traps; NULL switches it off */
+int tf_attention_set_debug(void* host_mapped_buf);
 /* Same, under a causal mask: query t attends to keys <= t only (Tq == Tk). Replaces CLIPAttention's
  * scaled_dot_product_attention(q, k, v, attn_mask = triu(full(-inf), k=1))
  *           tinyfusers/attention/attention.py:88-99, tinyfusers/vae/encoder.py:79, attention/sdpa.py:67-68. */
@@ -251,6 +258,24 @@ int tf_pad_tokens_f32_to_f16(const float* x, void* out, int B, int T, int Tpad, 
 int tf_cfg_ddim_step_f32(const float* eps_nhwc, int eps_pixel_stride, const float* latent, float* latent_out,
                          float* e_t_out, const float* alphas_dev, const float* alphas_prev_dev,
                          const int* index_dev, float guidance, int B, int C, int HW, void* stream);
+/* ---- CFG halves on two GPUs (one image; lower latency): GPU 0 evaluates the unconditional half, GPU 1 the conditional half of
+ * get_model_output's batch (tinyfusers/variants/sd.py:27-46) and ONE kernel per GPU exchanges the two noise predictions through
+ * peer-mapped memory over NVLink and applies CFG + DDIM (no NCCL launch on the step path; csrc/tf_p2p.cu).
+ *   tf_p2p_alloc / tf_p2p_free : exchange buffer from cudaMalloc + its 64-byte CUDA IPC handle (zero-filled);
+ *   tf_p2p_open / tf_p2p_close : map the PEER process's buffer from its handle (peer access enabled lazily);
+ *   tf_p2p_blocks              : thread blocks (= flags per slot) the step kernel uses for C*HW elements.
+ * Mailbox = 2 * C*HW floats, flags = 2 * tf_p2p_blocks ints, both per rank and zero-initialised. seq_dev: device counter the
+ * caller increments after every step (tf_add_int). mode: 1 send | 2 wait + update (3 in production). rank: 0 = holds the
+ * unconditional half. eps_nhwc: this rank's UNet output, ONE image, fp32 NHWC. */
+int tf_p2p_blocks(int C, int HW);
+int tf_p2p_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int tf_p2p_open(const void* handle64, void** dev_ptr);
+int tf_p2p_close(void* dev_ptr);
+int tf_p2p_free(void* dev_ptr);
+int tf_cfg_ddim_step_split_f32(const float* eps_nhwc, int eps_pixel_stride, const float* latent, float* latent_out,
+                               float* e_t_out, const float* alphas_dev, const float* alphas_prev_dev, const int* index_dev,
+                               float guidance, int C, int HW, int rank, const void* my_mailbox, void* peer_mailbox,
+                               const void* my_flags, void* peer_flags, const int* seq_dev, int mode, void* stream);
 /* *p_dev += delta (device-resident sampler step counter, so a captured graph can be replayed) */
 int tf_add_int(int* p_dev, int delta, void* stream);
 /* elementwise activation, op: 0 sigmoid, 1 silu/swish, 2 gelu (tanh approx), 3 quick_gelu; fp32 or fp16.

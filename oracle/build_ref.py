@@ -24,7 +24,8 @@ def build(force=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--use_fast_math", "-D__CUDA_NO_HALF_CONVERSIONS__",
-           f"-I{REF_CUDA}", f'-DREF_SOFTMAX_CU="{src}"', "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+           f"-I{REF_CUDA}", f'-DREF_SOFTMAX_CU="{src}"', "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+           "-Xlinker", "-rpath", "-Xlinker", os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64"),
            "-o", OUT, launcher]
     subprocess.check_call(cmd)
     return OUT

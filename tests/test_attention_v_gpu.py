@@ -61,12 +61,12 @@ def test_natural_v_causal(T, NH, d):
     assert rel_err(out, ref) < 3e-3
 
 
-@pytest.mark.parametrize("emu", [0, 2, 4, 12])
+@pytest.mark.parametrize("emu", [0, 2, 4])
 @pytest.mark.parametrize("B,NH,T,d,causal", [(2, 8, 4096, 40, False), (1, 4, 1024, 80, False), (1, 2, 512, 64, True),
                                              (1, 1, 256, 40, False), (1, 3, 768, 96, False)])
 def test_two_tile_pingpong_kernel(B, NH, T, d, causal, emu):
     """tf_attention2_kernel forced on (version 2) in every variant: exponentials all on MUFU / 2 / 4 of 8 on the FMA pipe
-    (degree-3 polynomial, max relative error 7.6e-5 per value), with and without the warpgroup order (emu + 10), row sums by
+    (degree-3 polynomial, max relative error 7.6e-5 per value), row sums by
     the ones-tile MMA or out of a ones column of V. Same tolerance as the one-tile kernel."""
     from tinyfusers_b200.native.b200.ops import b200
     b200.init(0)

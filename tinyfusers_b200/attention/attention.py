@@ -18,8 +18,8 @@ from ..ff.group_norm import GroupNorm
 from ..ff.layer_norm import LayerNorm
 from ..ff.linear import Linear
 from ..ff.nn import FeedForward
-from ..runtime import (F16, F32, Act, act_to_nchw, nchw_to_act, new_act_tensor, require_cuda, standalone_context,
-                       stream_ptr, tokens_to_act)
+from ..runtime import (F16, F32, Act, act_to_nchw, as_f16, as_f32, nchw_to_act, new_act_tensor, require_cuda,
+                       standalone_context, stream_ptr, tokens_to_act)
 from ..vision.conv2d import Conv2d
 from .sdpa import scaled_dot_product_attention  # noqa: F401  (re-exported like the reference)
 
@@ -82,9 +82,9 @@ class CrossAttention:
         xa = tokens_to_act(x)
         ca = None if context is None else _pad_context(ctx, context)
         B, T, C = x.shape
-        out = torch.zeros((B, T, self.to_out[0].weight.shape[0]), dtype=F16, device=x.device)
+        out = torch.empty((B, T, self.to_out[0].weight.shape[0]), dtype=F16, device=x.device)
         self._run(ctx, xa.ptr, B, T, C, out.data_ptr(), context=ca, residual=False)
-        return out.to(F32)
+        return as_f32(out)
 
     # h_ptr (B*T, C) is updated:  h <- to_out(attention(...)) (+ h if residual);  xn_ptr = normalised input
     # ln = (row statistics of the UN-normalised input at xn_ptr, LayerNorm module): the norm is folded into the first GEMM.
@@ -153,12 +153,12 @@ class BasicTransformerBlock:
         ctx = standalone_context()
         ctx.arena.reset()
         B, T, C = x.shape
-        h = x.to(F16).contiguous().clone()
+        h = as_f16(x)            # a new fp16 buffer (tf_* cast): the block updates it in place
         ca = None
         if context is not None:
             ca = _pad_context(ctx, context)
         self._run(ctx, h.data_ptr(), B, T, C, ca)
-        return h.to(F32)
+        return as_f32(h)
 
     # h (B*T, C) fp16 updated in place. h_stats: row statistics of h left by its producer (tf_gemm_ex_f16 row_stats_out):
     # with them the three LayerNorms are folded into the GEMMs that consume them (no LayerNorm launch, no xn buffer).
@@ -203,7 +203,7 @@ def _pad_context(ctx, context):
     B, Tk, Cc = context.shape
     Tkp = (Tk + 7) // 8 * 8
     buf = torch.empty((B, Tkp, Cc), dtype=F16, device=context.device)
-    c32 = context.to(F32).contiguous()
+    c32 = as_f32(context).contiguous()
     st = b200.tf_pad_tokens_f32_to_f16(c32.data_ptr(), buf.data_ptr(), B, Tk, Tkp, Cc, stream_ptr())
     b200.check(st, "tf_pad_tokens_f32_to_f16")
     act = Act(buf.data_ptr(), B, Tkp, 1, Cc, Cc, keep=(buf, c32))
@@ -347,6 +347,24 @@ def _attn_block_canonical(self, ctx, x, out):
 AttnBlock._run_canonical = _attn_block_canonical
 
 
+def _check_causal_mask(mask, T):
+    """None, or the (.., T, T) causal mask the reference builds (additive triu(-inf, 1) or boolean lower-triangular keep)."""
+    if mask is None:
+        return
+    m = torch.as_tensor(mask)
+    if m.numel() != T * T:
+        raise RuntimeError(f"tinyfusers_b200 CLIPAttention: mask of {tuple(m.shape)} for {T} tokens; only the causal mask is built")
+    m = m.reshape(T, T)
+    tril = torch.ones((T, T), dtype=torch.bool, device=m.device).tril()
+    if m.dtype == torch.bool:
+        ok = torch.equal(m, tril)
+    else:
+        ok = bool((m[tril] == 0).all()) and bool(torch.isinf(m[~tril]).all()) and bool((m[~tril] < 0).all())
+    if not ok:
+        raise RuntimeError("tinyfusers_b200 CLIPAttention: only the causal mask (triu(-inf, k=1) or its boolean form) is built "
+                           "into the attention kernel; use set_precision('fp32') for an arbitrary additive mask")
+
+
 class CLIPAttention:
     """CLIP self-attention (reference: tinyfusers/attention/attention.py:78-99): 12 heads x 64, q/k/v/out Linears with
     bias, additive causal mask, heads merged canonically. Fast path: ONE GEMM for [q | k | v] (bias fused), causal
@@ -372,23 +390,24 @@ class CLIPAttention:
         return packing.cached(self, "clipattn", tuple(m.weight for m in mods) + tuple(m.bias for m in mods), build)
 
     def __call__(self, hidden_states, causal_attention_mask=None):
-        """(B, T, 768) -> (B, T, 768). The mask argument is accepted for signature parity; the kernel applies the causal
-        mask the reference always passes (vae/encoder.py:79)."""
+        """(B, T, 768) -> (B, T, 768). The kernel applies the causal mask the reference always passes (vae/encoder.py:79:
+        triu(-inf, k = 1)); `causal_attention_mask` may be that mask (or its boolean form) or None - any other mask raises,
+        it is not silently replaced (arbitrary additive masks exist only in the fp32 parity mode)."""
         require_cuda(hidden_states, "hidden_states")
         if fp32.enabled():
             return fp32.clip_attention(self, hidden_states)
+        _check_causal_mask(causal_attention_mask, hidden_states.shape[1])
         ctx = standalone_context()
         B, T, E = hidden_states.shape
         Tp = (T + 7) // 8 * 8
-        outs = []
+        out = torch.empty((B, T, E), dtype=F32, device=hidden_states.device)
         for i in range(B):
             ctx.arena.reset()
-            xn = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
-            xn[:T] = hidden_states[i]
-            h = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
+            xn = as_f16(hidden_states[i], rows_pad_to=8)          # (Tp, E), pad rows zero
+            h = torch.empty((Tp, E), dtype=F16, device=hidden_states.device)
             self._run(ctx, xn.data_ptr(), h.data_ptr(), T, Tp, residual=False)
-            outs.append(h[:T].to(F32))
-        return torch.stack(outs)
+            out[i].copy_(as_f32(h)[:T])
+        return out
 
     # xn: (Tp, E) fp16 normalised input; h (Tp, E): h <- out_proj(attn) (+ h)
     def _run(self, ctx, xn_ptr, h_ptr, T, Tp, residual=True):

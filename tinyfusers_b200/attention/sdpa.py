@@ -7,7 +7,7 @@ the projection GEMMs write these layouts directly."""
 import torch
 
 from .. import fp32
-from ..runtime import F16, F32, require_cuda, standalone_context
+from ..runtime import F16, F32, as_f32, require_cuda, standalone_context
 
 
 def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
@@ -46,4 +46,4 @@ def scaled_dot_product_attention(q_cp, k_cp, v_cp, attn_mask=None):
     out = torch.empty((B, NH, Tq, HS), dtype=F16, device=dev)
     ctx.attention_v(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, V.data_ptr(), NH * dvp, out.data_ptr(), B, NH, Tq, Tk, Tkp,
                     HS, dp, dvp, head_major=True, causal=causal)
-    return out.to(F32)
+    return as_f32(out)

@@ -42,6 +42,7 @@ def _digest():
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(FLAGS).encode())
+    h.update(b"cudart-shared-1")
     return h.hexdigest()
 
 
@@ -73,7 +74,21 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libtinyfusers_b200 build failed")
-    link = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    # The CUDA runtime is linked DYNAMICALLY: the library then imports only the runtime symbols it calls (a statically linked
+    # runtime drags every entry point's name into the artefact) and shares the process's libcudart.so.12 with torch. rpath: the
+    # copy torch ships (already loaded whenever torch is) and the toolkit's, for a process that loads the library without torch.
+    rpaths = [os.path.join(os.path.dirname(os.__file__), "site-packages", "nvidia", "cuda_runtime", "lib"),
+              os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.cuda_runtime")
+        if spec and spec.submodule_search_locations:
+            rpaths.insert(0, os.path.join(list(spec.submodule_search_locations)[0], "lib"))
+    except Exception:
+        pass
+    link = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"]
+    for r in rpaths:
+        link += ["-Xlinker", "-rpath", "-Xlinker", r]
     subprocess.check_call(link)
     with open(STAMP, "w") as fh:
         fh.write(dig)

@@ -69,6 +69,15 @@ extern "C" int tf_init(int device) {
     return TF_ERR_DEVICE;
   }
   TF_CHECK_ARG(device >= 0 && device < count, "tf_init: device %d out of range (%d visible)", device, count);
+  // One process per GPU: function attributes (opt-in shared memory sizes), the SM count and the tuning
+  // table are set once per process, for the device of the first tf_init. A second device in the same process is refused
+  // loudly instead of failing later with "invalid argument" on the first > 48 KB launch.
+  static int g_device = -1;
+  if (g_device >= 0 && g_device != device) {
+    tf_set_error("tf_init: this process already serves device %d; tinyfusers_b200 runs one process per GPU (got device %d)",
+                 g_device, device);
+    return TF_ERR_DEVICE;
+  }
   TF_CUDA(cudaSetDevice(device));
   int major = 0, minor = 0;
   TF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
@@ -80,6 +89,7 @@ extern "C" int tf_init(int device) {
   }
   g_sms = 0;
   tf_num_sms();
+  g_device = device;
   return TF_OK;
 }
 

@@ -32,6 +32,27 @@
 
 namespace {
 
+// Debug aid: a host-mapped (pinned) buffer that survives a device trap. When set (tf_attention_set_debug), a barrier wait of
+// the attention kernels that times out records {code, block x/y/z, warp, key block} there before it traps, so the host can
+// tell WHICH wait hung after the context is gone. Null in production: one predictable branch on the (never taken) timeout path.
+__device__ unsigned long long* g_att_dbg = nullptr;
+
+__device__ __forceinline__ void att_wait(uint32_t bar, uint32_t parity, int code, int j) {
+  if (tf::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!tf::mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > TF_WAIT_TIMEOUT_CYCLES) {
+      unsigned long long* d = g_att_dbg;
+      if (d != nullptr && atomicCAS(d, 0ull, 1ull) == 0ull) {
+        d[1] = (unsigned long long)code; d[2] = blockIdx.x; d[3] = blockIdx.y; d[4] = blockIdx.z;
+        d[5] = threadIdx.x >> 5; d[6] = (unsigned long long)(long long)j; d[7] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
 constexpr int kAttThreads = 192;
 constexpr int BQ = 128;
 
@@ -107,7 +128,6 @@ __global__ void __launch_bounds__(kAttThreads, OCC)
 tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  tf::pdl_trigger();
   const uint32_t raw_u32 = tf::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -166,6 +186,7 @@ tf_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  tf::pdl_trigger();   // only once this CTA holds its tensor memory (see tf_gemm_kernel: trigger-before-alloc can deadlock)
   tf::pdl_wait();
   const uint32_t tmem_s0 = tmem_base;            // S: columns [0,BN)
   const uint32_t tmem_o = tmem_base + BN;        // O: dp columns, then 16 columns of L = P . 1 (the softmax denominator)
@@ -410,7 +431,6 @@ constexpr int BN2 = 64;
 struct Attn2Params {
   int B, NH, Tq, Tk, Tk_pad, d, dp, dov, v_atom, l_off, ol_cols, nkv, stages, causal;
   int tile_cols;   // TMEM columns per query tile: 128 + ol_cols
-  int order;       // 1: the two softmax warpgroups take turns on the exponential phase
   int l_sel;       // position of the row sum inside the 16-column group at l_off (0 or 8)
   int l_mma;       // 1: row sums by an extra N = 16 MMA against a ones tile (at l_off); 0: V carries a ones column at index d
   long long* timeline;   // debug (TF_ATT_TRACE build): clock stamps of CTA (0,0,0): [who: softmax 0, softmax 1, MMA][block < 64][8]
@@ -452,7 +472,6 @@ __global__ void __launch_bounds__(kA2Threads, 1)
 tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  tf::pdl_trigger();
   const uint32_t raw_u32 = tf::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -472,9 +491,14 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   auto kv_full = [&](int s) { return bar_base + 8u * (2 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (2 + ST + s); };
   auto s_full = [&](int t, int buf) { return bar_base + 8u * (2 + 2 * ST + 2 * t + buf); };
-  auto p_full = [&](int t) { return bar_base + 8u * (6 + 2 * ST + t); };
-  auto pv_done = [&](int t) { return bar_base + 8u * (8 + 2 * ST + t); };
-  const uint32_t tmem_slot = bar_base + 8u * (10 + 2 * ST);
+  // P_j complete (128 arrivals), one barrier per S buffer. A softmax warp may run a whole block ahead of a slower warp of its
+  // tile (S_{j+1} is issued before P_j is awaited), so with ONE barrier its arrival for block j+1 would be counted into phase j
+  // and the tensor core could read rows of P_j that are not written yet. Block j+2 cannot be reached before phase j is complete
+  // (S_{j+2} is issued after it), so two barriers alternating with the buffer keep the phases apart.
+  auto p_full = [&](int t, int buf) { return bar_base + 8u * (6 + 2 * ST + 2 * t + buf); };
+  auto pv_done = [&](int t) { return bar_base + 8u * (10 + 2 * ST + t); };
+  auto pv_last = [&](int t) { return bar_base + 8u * (12 + 2 * ST + t); };   // single use: P V of the LAST key block complete
+  const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * ST);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
   if (warp == 0 && lane == 0) {
@@ -487,8 +511,10 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tf::mbar_init(q_full(t), 1);
       tf::mbar_init(s_full(t, 0), 1);
       tf::mbar_init(s_full(t, 1), 1);
-      tf::mbar_init(p_full(t), 128);
+      tf::mbar_init(p_full(t, 0), 128);
+      tf::mbar_init(p_full(t, 1), 128);
       tf::mbar_init(pv_done(t), 1);
+      tf::mbar_init(pv_last(t), 1);
     }
     for (int s = 0; s < ST; ++s) {
       tf::mbar_init(kv_full(s), 1);
@@ -509,6 +535,7 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  tf::pdl_trigger();   // only once this CTA holds its tensor memory (see tf_gemm_kernel: trigger-before-alloc can deadlock)
   tf::pdl_wait();
 
   const int nkv = p.nkv;
@@ -527,7 +554,7 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < nkv; ++j) {
         const int s = j % ST;
         const uint32_t u = j / ST;
-        tf::mbar_wait(kv_empty(s), (u & 1u) ^ 1u);
+        att_wait(kv_empty(s), (u & 1u) ^ 1u, 1, j);
         tf::mbar_expect_tx(kv_full(s), k_bytes + v_bytes);
         const int key0 = b * p.Tk_pad + j * BN2;
         tf::tma_load_3d(smem_k + s * k_bytes, &tmK, kv_full(s), 0, key0, h * slabs);
@@ -560,7 +587,7 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint32_t qphase = 0;
     uint64_t kd = kd0;
     auto issue_qk = [&](int jj) {   // S_jj of both tiles; buffer jj % 2 held P_{jj-2}, whose P V MMAs were issued earlier (in order)
-      tf::mbar_wait(kv_full(qs), qphase);
+      att_wait(kv_full(qs), qphase, 2, jj);
       tf::tcgen05_fence_after();
       const uint32_t sb = (uint32_t)(jj & 1) * BN2;
       if (elected) {
@@ -576,8 +603,8 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       kd += k_step;
       if (++qs == ST) { qs = 0; qphase ^= 1u; kd = kd0; }
     };
-    tf::mbar_wait(q_full(0), 0);
-    tf::mbar_wait(q_full(1), 0);
+    att_wait(q_full(0), 0, 3, 0);
+    att_wait(q_full(1), 0, 4, 0);
     issue_qk(0);
     int vs = 0;
     uint64_t vd = vd0;
@@ -589,7 +616,7 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t acc0 = j > 0 ? 1u : 0u;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        tf::mbar_wait(p_full(t), (uint32_t)j & 1u);
+        att_wait(p_full(t, j & 1), (uint32_t)(j >> 1) & 1u, 5 + t, j);
         tf::tcgen05_fence_after();
         if (elected) {
           ATT2_STAMP(2, 2 + 2 * t);
@@ -603,6 +630,7 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (l_mma) tf::umma_f16_ts(od + p.l_off, pa + 8u * k, ones_d + 2u * k, idesc_l, k > 0 ? 1u : acc0);
           }
           tf::umma_commit(pv_done(t));
+          if (j == nkv - 1) tf::umma_commit(pv_last(t));
           ATT2_STAMP(2, 3 + 2 * t);
         }
         __syncwarp();
@@ -622,11 +650,10 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float sc = p.scale_log2;
     float m_run = -INFINITY;   // reference max of this row (scaled log2 domain); lazily updated (see tf_attention_kernel)
     const uint32_t o_addr = tmem_o(t) + lane_field;
-    if (p.order && t == 1) asm volatile("bar.arrive %0, 256;" ::"r"(1) : "memory");   // tile 0 takes the first turn
     const bool stamp = q == 0 && lane == 0;
     for (int j = 0; j < nkv; ++j) {
       if (stamp) ATT2_STAMP(t, 0);
-      tf::mbar_wait(s_full(t, j & 1), (uint32_t)(j >> 1) & 1u);
+      att_wait(s_full(t, j & 1), (uint32_t)(j >> 1) & 1u, 7 + t, j);
       tf::tcgen05_fence_after();
       if (stamp) ATT2_STAMP(t, 1);
       const uint32_t s_addr = tmem_s(t, j & 1) + lane_field;
@@ -657,12 +684,9 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float neg_m = -m_run;
       uint32_t pk[32];
       const uint64_t sc2 = tf::pack_f32x2(sc, sc), nm2 = tf::pack_f32x2(neg_m, neg_m);
-      // The exponential phases of the two warpgroups alternate (named barriers 1 / 2, 256 threads each: 128 wait, 128
-      // arrive): while one tile's rows occupy the MUFU pipe the other tile loads S, takes its row max, stores P and waits
-      // for the tensor core. Without the order the two start in lockstep and collide on the pipe (measured on
-      // tf_attention_kernel, profiles/attention_timeline_r1.md).
+      // (Forcing the two warpgroups to alternate on the exponential phase through named barriers was measured and dropped:
+      // the barrier latency cost more than the MUFU collisions it avoided, profiles/attention2_variants_r2.log.)
       if (stamp) ATT2_STAMP(t, 3);
-      if (p.order) asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
       if (stamp) ATT2_STAMP(t, 4);
 #pragma unroll
       for (int i = 0; i < 64; i += 8) {
@@ -685,16 +709,13 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       if (stamp) ATT2_STAMP(t, 5);
-      if (p.order && (t == 0 || j + 1 < nkv)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");   // the other tile's turn
-      // P V_{j-1} was issued a whole softmax block ago: this wait is (almost) always already satisfied. It is taken on EVERY
-      // block so that this thread observes every phase of pv_done in order - a parity wait that skips phases aliases
-      // (phase j-1 and phase j-3 have the same parity) and would let the rescale / epilogue below race the tensor core.
-      if (j > 0) {
-        tf::mbar_wait(pv_done(t), (uint32_t)(j - 1) & 1u);
-        tf::tcgen05_fence_after();
-      }
       // rescale the running output if any row of this warp moved its max (rare after the first blocks: lazy threshold 2^8)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        // O belongs to the tensor core until P V_{j-1} has completed. The parity wait below cannot alias an older phase:
+        // S_j (which this thread has just consumed) was issued after P V_{j-2} of this tile and tcgen05.mma complete in issue
+        // order, so every phase of pv_done up to j-2 is complete and the barrier is in phase j-1 or beyond.
+        att_wait(pv_done(t), (uint32_t)(j - 1) & 1u, 9 + t, j);
+        tf::tcgen05_fence_after();
         for (int c = 0; c < p.ol_cols; c += 16) {   // O and the L columns
           uint32_t o[16];
           tf::tmem_ld_x16(o_addr + c, o);
@@ -708,11 +729,15 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tf::tmem_st_x32(s_addr, pk);   // P_j over the first 32 columns of the S buffer this thread has just drained
       tf::tmem_st_wait();
       tf::tcgen05_fence_before();
-      tf::mbar_arrive(p_full(t));
+      tf::mbar_arrive(p_full(t, j & 1));
       if (stamp) ATT2_STAMP(t, 7);
     }
     // ---- epilogue: O / l -> fp16 -> global ----
-    tf::mbar_wait(pv_done(t), (uint32_t)(nkv - 1) & 1u);
+    // The last P V has its own single-use barrier. pv_done cannot serve here: this thread has not followed its phases (it only
+    // waits on it when a rescale is due), only phases up to nkv-3 are known complete, and a parity wait cannot tell phase
+    // nkv-2, nkv-1 and "all done" apart - waiting for nkv-1 could pass on nkv-3, waiting for nkv-2 first could hang when both
+    // have already completed.
+    att_wait(pv_last(t), 0, 11 + t, nkv);
     tf::tcgen05_fence_after();
     float inv_l;
     {
@@ -752,8 +777,10 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 int g_attn_version = 0;   // 0 auto, 1 tf_attention_kernel only, 2 tf_attention2_kernel wherever it applies
-int g_attn_emu = 2;       // exponentials per 8 evaluated on the FMA pipe (0, 2 or 4)
-int g_attn_order = 1;     // softmax warpgroups alternate on the exponential phase
+// Measured on B200 (tools/dev_attn2.py, profiles/attention2_r2.md), 4096 tokens x d = 40, batch 2, us per call: one-tile kernel
+// 133.3; this kernel with 0 / 2 / 4 of 8 exponentials on the FMA pipe 121.3 / 111.3 / 110.0 with the warpgroup order, 108.5 /
+// 105.0 (2 / 4) without it: forcing the two tiles to alternate costs more in barrier latency than the MUFU collisions it avoids.
+int g_attn_emu = 4;       // exponentials per 8 evaluated on the FMA pipe (0, 2 or 4)
 
 int g_force_attn_bn = 0;
 int g_force_attn_occ = 0;
@@ -761,16 +788,22 @@ long long* g_attn_timeline = nullptr;
 
 }  // namespace
 
+extern "C" int tf_attention_set_debug(void* host_mapped_buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(host_mapped_buf);   // >= 8 x 8 bytes, zeroed, pinned; or NULL
+  TF_CUDA(cudaMemcpyToSymbol(g_att_dbg, &p, sizeof(p)));
+  return TF_OK;
+}
+
 extern "C" int tf_attention_set_timeline(long long* dev_buf) {
   g_attn_timeline = dev_buf;   // >= 64 * 8 int64; debug only (stamps exist in TF_ATT_TRACE builds)
   return TF_OK;
 }
 
 extern "C" int tf_attention_set_variant(int version, int emu) {
-  TF_CHECK_ARG(version >= 0 && version <= 2 && (emu < 0 || emu % 10 == 0 || emu % 10 == 2 || emu % 10 == 4) && emu < 20,
-               "tf_attention_set_variant: version in {0 auto, 1, 2}, emu in {0, 2, 4} (+ 10: warpgroup order off; < 0: keep)");
+  TF_CHECK_ARG(version >= 0 && version <= 2 && (emu < 0 || emu == 0 || emu == 2 || emu == 4),
+               "tf_attention_set_variant: version in {0 auto, 1, 2}, emu in {0, 2, 4} (< 0: keep)");
   g_attn_version = version;
-  if (emu >= 0) { g_attn_emu = emu % 10; g_attn_order = emu < 10 ? 1 : 0; }
+  if (emu >= 0) g_attn_emu = emu;
   return TF_OK;
 }
 
@@ -832,7 +865,6 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
       p2.l_sel = ones_col ? (d & 15) : 0;           // ... and its position inside the group (d % 8 == 0: 0 or 8)
       p2.ol_cols = ol2;
       p2.nkv = ceil_div_i(Tk, BN2);
-      p2.order = g_attn_order;
       p2.timeline = g_attn_timeline;
       p2.tile_cols = 2 * BN2 + ol2;
       uint32_t cols2 = 32;

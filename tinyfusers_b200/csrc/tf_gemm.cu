@@ -75,6 +75,8 @@ struct GemmParams {
   const __half* residual;
   int ldr;
   float* partial;
+  int cluster_k;   // 1: the `splits` CTAs of one output tile form a thread-block cluster and fold their fp32 partials through
+                   // distributed shared memory inside this launch (no workspace round trip, no fold kernel); see the epilogue
   int flags;
   long long* timeline;  // optional debug: per-CTA clock stamps [grid][8] (tf_gemm_set_timeline)
   // optional GroupNorm statistics of the OUTPUT (fp16 epilogue only): gn_stats[image][slot][unit] = {sum, sumsq}
@@ -125,7 +127,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  tf::pdl_trigger();
   const long long t_entry = clock64();
   const uint32_t raw_u32 = tf::smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
@@ -176,6 +177,12 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tf::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Dependents may launch only now that this CTA HOLDS its tensor memory. Triggering at kernel entry (round 1) let CTAs of the
+  // next kernel become co-resident with a CTA of this one that had not allocated yet; they took the columns it needed and then
+  // sat in griddepcontrol.wait for this kernel to finish while it sat in tcgen05.alloc for them to leave: a (rare, timing-
+  // dependent) deadlock seen as a barrier timeout trap. With the trigger here every CTA of the primary owns its columns before
+  // any CTA of a dependent exists; a dependent that finds the columns taken just waits for this CTA to exit.
+  tf::pdl_trigger();
   // PDL: barriers / TMEM / descriptors were set up while the producer kernels drained. The dependency wait itself is
   // taken per role below: the TMA warp first puts the WEIGHT tiles of its first ring fill in flight (weights do not
   // depend on any kernel, and every layer's weights arrive cold from HBM), then waits, then loads activations.
@@ -423,6 +430,27 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = k2 ? 2 * (t1 / p.n_tiles) + (int)rank : t1 / p.n_tiles;
       const int n_tile = nt * p.bn;
       const int m_own = tile_row_to_m(p, mt, row);
+      if (!k2 && p.cluster_k) {
+        // split-K inside a cluster, phase 1: this CTA's fp32 partial tile -> its own shared memory (the operand ring is
+        // free: every MMA that read it has completed when the accumulator barrier fires). Row-major, pitch bn + 4 floats:
+        // the 16-byte stores of 8 consecutive rows fall into 8 different bank groups.
+        tf::mbar_wait(tfull_bar(as), aphase);
+        tf::tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccStride;
+        const uint32_t rrow = smem_a + (uint32_t)row * (uint32_t)(p.bn + 4) * 4u;
+        for (int c = hsel * 16; c < p.bn; c += 32) {      // the quarter's two warps alternate over 16-column chunks
+          uint32_t v[16];
+          tf::tmem_ld_x16(taddr + c, v);
+          tf::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rrow + (uint32_t)(c + 4 * j) * 4u), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+        }
+        tf::tcgen05_fence_before();
+        break;   // one work item per CTA in this mode; phases 2 and 3 follow the role branches (cluster barriers)
+      }
       // store coordinates of this warp's 32-row block
       int sc1, sc2 = 0, sc3 = 0;
       if (p.is_conv) {
@@ -680,6 +708,89 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) tf::tma_store_wait<0>();   // all bulk stores complete before the CTA retires
   }
 
+  if (!k2 && p.cluster_k) {
+    // split-K inside a cluster, phases 2 and 3. The S = splits CTAs of this cluster hold the S partial tiles of ONE output
+    // tile in their shared memories. CTA r folds the tile's columns [r w, (r+1) w), w = bn / S, over all S partials in rank
+    // order (fixed: results are bit-reproducible) through distributed shared memory, adds bias / residual, rounds to fp16
+    // and stores - and leaves the GroupNorm statistics of its columns, which is why w is a whole number of statistics
+    // units. The fp32 partials never leave the SMs: no workspace write + read (414 MB per step) and no fold launch.
+    __syncthreads();
+    tf::cluster_sync_all();
+    if (warp >= 2) {
+      const int S2 = p.splits;
+      const int tid = (int)threadIdx.x - 64;
+      const uint32_t crank = tf::cluster_ctarank();
+      const int w = p.bn / S2, hw = w >> 1;
+      const int c0 = (int)crank * w;
+      const int t1 = (int)blockIdx.x / S2;
+      const int nt = t1 % p.n_tiles, mt = t1 / p.n_tiles;
+      const int n_tile = nt * p.bn;
+      const uint32_t pitch = (uint32_t)(p.bn + 4) * 4u;
+      float* fin = reinterpret_cast<float*>(smem_raw + (smem_a + 128u * pitch - raw_u32));   // [128][w] final values (statistics)
+      const bool gn = p.gn_stats != nullptr;
+      __half* outh = reinterpret_cast<__half*>(p.out);
+      for (int i = tid; i < 128 * hw; i += 32 * kEpiWarps) {
+        const int r = i / hw, cp = i - r * hw;
+        const int col = c0 + 2 * cp;
+        const uint32_t off = smem_a + (uint32_t)r * pitch + (uint32_t)col * 4u;
+        float a0 = 0.f, a1 = 0.f;
+        for (int sidx = 0; sidx < S2; ++sidx) {
+          float x0, x1;
+          asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(tf::mapa_shared(off, (uint32_t)sidx)) : "memory");
+          a0 += x0; a1 += x1;
+        }
+        const int m = tile_row_to_m(p, mt, r);
+        const int n = n_tile + col;
+        float f0 = 0.f, f1 = 0.f;
+        if (m >= 0 && n < p.N) {
+          if (p.bias != nullptr) { a0 += __ldg(p.bias + n); a1 += __ldg(p.bias + n + 1); }
+          if (p.residual != nullptr) {
+            const float2 rr = __half22float2(*reinterpret_cast<const __half2*>(p.residual + (size_t)m * p.ldr + n));
+            a0 += rr.x; a1 += rr.y;
+          }
+          const __half2 hv = __floats2half2_rn(a0, a1);
+          *reinterpret_cast<__half2*>(outh + (size_t)m * p.ldc + n) = hv;
+          const float2 fr = __half22float2(hv);     // statistics of the ROUNDED values, like every other producer
+          f0 = fr.x; f1 = fr.y;
+        }
+        if (gn) { fin[r * w + 2 * cp] = f0; fin[r * w + 2 * cp + 1] = f1; }
+      }
+      if (gn) {
+        asm volatile("bar.sync 9, %0;" ::"r"(32 * kEpiWarps) : "memory");
+        // one warp per (32-row slot, statistics unit): lane = row, fixed-order shuffle tree
+        const int ew = warp - 2, upc = w / p.gn_unit;
+        const int utot = p.N / p.gn_unit;
+        for (int combo = ew; combo < 4 * upc; combo += kEpiWarps) {
+          const int slot4 = combo / upc, u = combo - slot4 * upc;
+          const float* src = fin + (slot4 * 32 + lane) * w + u * p.gn_unit;
+          float sm = 0.f, sq = 0.f;
+          for (int k = 0; k < p.gn_unit; ++k) { const float v = src[k]; sm += v; sq = fmaf(v, v, sq); }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+          int img, slot;
+          bool valid;
+          if (p.is_conv) {
+            const ConvGeom& g = p.g;
+            const int ppi = g.TW * g.TH;
+            const int tx = mt % g.tiles_x, t2 = mt / g.tiles_x;
+            img = (t2 / g.tiles_y) * g.TN + (slot4 * 32) / ppi;
+            valid = img < g.NI;
+            slot = ((t2 % g.tiles_y) * g.tiles_x + tx) * (ppi >> 5) + ((slot4 * 32) % ppi >> 5);
+          } else {
+            const int row0 = mt * BM + slot4 * 32;
+            valid = row0 < p.M;
+            img = row0 / p.gn_hw;
+            slot = (row0 % p.gn_hw) >> 5;
+          }
+          const int ug = (n_tile + c0) / p.gn_unit + u;
+          if (lane == 0 && valid && ug < utot)
+            p.gn_stats[((size_t)img * (p.gn_hw >> 5) + slot) * utot + ug] = make_float2(sm, sq);
+        }
+      }
+    }
+    // no CTA may retire (or reuse its shared memory) while a peer still reads its partial tile
+    tf::cluster_sync_all();
+  }
   tf::tcgen05_fence_before();
   // idle lanes / warps park at the CTA barrier (hardware-blocking); the cluster barrier, which polls, is only
   // entered once the whole CTA is done: neither CTA may retire while the other still signals it / reads its smem
@@ -819,6 +930,7 @@ static int lcm_i(int a, int b) {
 }
 
 static int g_force_bn = 0, g_force_splits = 0, g_force_ctas = 0;
+static int g_cluster_splitk = -1;   // -1: TINYFUSERS_B200_CLUSTER_SPLITK (default off), 0 / 1: forced (tf_gemm_set_cluster_splitk)
 
 // Measured tile choices (tools/autotune_gemm.py on a B200 -> native/b200/gemm_tuning.json, loaded by the binding at
 // init): (is_conv, M, N, K, class) -> (BN, split-K, CTAs per tile). class = epilogue / geometry bits that change the
@@ -927,6 +1039,20 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   size_t smem = (size_t)stages * stage_bytes + kEpiBytes + 2048;
   if (smem < 120 * 1024) smem = 120 * 1024;
   p.timeline = g_timeline;
+  if (p.cluster_k) {
+    // one CTA per (tile, split), the splits of a tile = one cluster; partial tiles + final values live in the operand ring
+    const size_t need = (size_t)128 * (p.bn + 4) * 4 + (p.gn_stats ? (size_t)128 * (p.bn / p.splits) * 4 : 0);
+    if (need > (size_t)stages * stage_bytes) {
+      tf_set_error("gemm: cluster split-K tile does not fit the operand ring (bn=%d splits=%d)", p.bn, p.splits);
+      return TF_ERR_ARG;
+    }
+    const int grid = p.m_tiles * p.n_tiles * p.splits;
+    (void)tf_launch_pdl_cluster(tf_gemm_kernel<1, false>, dim3(grid), dim3(kThreads), smem, stream, (unsigned)p.splits, tmA, tmB, tmC,
+                                tmA2, p);
+    TF_LAUNCH_CHECK();
+    tf_launch_count_add(1);
+    return TF_OK;
+  }
   if (p.ctas == 2) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
     const int max_pairs = tf_num_sms() / 2;
@@ -1009,9 +1135,68 @@ extern "C" int tf_gemm_set_max_stages(int max_stages) {
   return TF_OK;
 }
 
+extern "C" int tf_gemm_set_cluster_splitk(int on) {
+  g_cluster_splitk = on < 0 ? -1 : (on ? 1 : 0);   // < 0: back to the environment default
+  return TF_OK;
+}
+
 extern "C" int tf_gemm_set_ctas(int force_ctas) {
   g_force_ctas = force_ctas;   // 0 = auto, 1 = single-CTA tiles, 2 = CTA-pair tiles (where M > 128)
   return TF_OK;
+}
+
+// Split-K inside a thread-block cluster (fold through distributed shared memory in the same launch) instead of fp32
+// partials in a workspace + a fold kernel. Needs: plain fp16 epilogue, single-CTA tiles, <= 8 splits (portable cluster size),
+// bn = splits * w with w even and - when the launch leaves GroupNorm statistics - a whole number of statistics units.
+// Starting from the (bn, splits) the table / model chose for the workspace path, picks the admissible pair with the lowest
+// modelled cost. OFF by default - measured slower than the workspace path on every split-K shape of the step (B200, in-graph,
+// cold weights, tools/dev_clusterk.py -> profiles/cluster_splitk_r2.log): 8x8-level conv 15.1 us (workspace + fold kernel) vs
+// 19.3 us (best cluster pair), 16x16 level 23.0 vs 28.2, M = 512 FF-out GEMM 13.9 vs 18.5: the DSMEM fold (~20 B/clk per SM)
+// and the co-scheduling of 4-8-CTA clusters cost more than the fold launch they remove. TINYFUSERS_B200_CLUSTER_SPLITK=1 or
+// tf_gemm_set_cluster_splitk(1) turns it on (results are identical up to fp32 summation order; tests cover both).
+static bool clusterize(GemmParams& p, int flags, bool extras, int gn_unit, bool has_gn) {
+  if (g_cluster_splitk < 0) {
+    const char* e = getenv("TINYFUSERS_B200_CLUSTER_SPLITK");
+    g_cluster_splitk = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!g_cluster_splitk || p.splits <= 1 || extras || (flags & (TF_EPI_GEGLU | TF_EPI_OUT_F32)) || g_force_ctas == 2) return false;
+  const int unit = has_gn ? gn_unit : 1;
+  const int sms = tf_num_sms();
+  int best_bn = 0, best_s = 0;
+  double best_cost = 1e30;
+  for (int bn = 16; bn <= 256; bn += 16) {
+    for (int sp = 2; sp <= 8; ++sp) {
+      if (bn % (2 * sp) != 0) continue;
+      const int w = bn / sp;
+      if (w % unit != 0 || bn % unit != 0) continue;
+      const int kbs = ceil_div_i(p.k_blocks, sp);
+      if ((sp - 1) * kbs >= p.k_blocks || kbs < 2) continue;
+      const int n_tiles = ceil_div_i(p.N, bn);
+      if ((double)p.N / (n_tiles * bn) < 0.8) continue;
+      const int stage_bytes = A_STAGE_BYTES + bn * 128;
+      int stages = (kSmemBudget - 2048 - epi_bytes(false)) / stage_bytes;
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages < 2 || (size_t)128 * (bn + 4) * 4 + (has_gn ? (size_t)128 * w * 4 : 0) > (size_t)stages * stage_bytes) continue;
+      const long ctas = (long)p.m_tiles * n_tiles * sp;
+      const long waves = (ctas + sms - 1) / sms;
+      const double feed = (128.0 + bn) * 128.0 / 52.0;
+      const double per_kb = (2.0 * bn > feed) ? 2.0 * bn : feed;
+      // fold: every CTA pulls (sp - 1) / sp of a 128 x w fp32 slab through DSMEM (~20 B / clk) + two cluster barriers
+      const double fold = 128.0 * w * 4.0 * (sp - 1) / 20.0 + 1500.0;
+      const double cost = waves * (kbs * per_kb + 1500.0 + 2.0 * bn + fold);
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_s = sp; }
+    }
+  }
+  if (g_force_bn > 0 && g_force_splits > 1 && g_force_splits <= 8 && g_force_bn % (2 * g_force_splits) == 0 &&
+      (g_force_bn / g_force_splits) % unit == 0 && g_force_bn % unit == 0) {
+    best_bn = g_force_bn; best_s = g_force_splits;      // tools: measure a given pair
+  }
+  if (!best_bn) return false;
+  p.bn = best_bn; p.splits = best_s; p.ctas = 1;
+  p.n_tiles = ceil_div_i(p.N, p.bn);
+  p.kb_per_split = ceil_div_i(p.k_blocks, p.splits);
+  p.cluster_k = 1;
+  return true;
 }
 
 static int gn_check(const void* gn_stats, int gn_unit, int gn_hw, int M, int N, int flags, const char* who) {
@@ -1080,6 +1265,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   p.out = out; p.ldc = ldc; p.bias = bias;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   p.flags = flags;
+  if (clusterize(p, flags, row_stats != nullptr || ln_stats != nullptr, gn_unit, gn_stats != nullptr)) g_last_choice = TileChoice{p.bn, p.splits, 1};
   if (row_stats) {
     p.rs_ld = p.n_tiles;
     std::lock_guard<std::mutex> lock(g_tune_mutex);
@@ -1108,13 +1294,13 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   CUtensorMap tmC;
   {
     const bool geglu = (flags & TF_EPI_GEGLU) != 0;
-    const bool f32 = (flags & TF_EPI_OUT_F32) != 0 || p.splits > 1;
-    p.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
-    const void* base = p.splits > 1 ? workspace : out;
+    const bool part = p.splits > 1 && !p.cluster_k;     // cluster split-K stores straight from registers: tmC is unused
+    const bool f32 = (flags & TF_EPI_OUT_F32) != 0 || part;
+    p.partial = part ? reinterpret_cast<float*>(workspace) : nullptr;
+    const void* base = part ? workspace : out;
     const uint64_t cols = geglu ? (uint64_t)N / 2 : (uint64_t)N;
-    const bool part = p.splits > 1;
     const uint64_t ld = part ? (uint64_t)N : (uint64_t)ldc;
-    uint64_t dims[3] = {cols, (uint64_t)M, (uint64_t)p.splits};
+    uint64_t dims[3] = {cols, (uint64_t)M, (uint64_t)(part ? p.splits : 1)};
     uint64_t strides[2] = {ld * (f32 ? 4 : 2), (uint64_t)M * ld * (f32 ? 4 : 2)};
     uint32_t box[3] = {geglu ? 16u : 32u, 32u, 1u};
     uint32_t es[3] = {1, 1, 1};
@@ -1227,6 +1413,7 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   p.out = out; p.ldc = ldc; p.bias = bias;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   p.flags = flags;
+  if (clusterize(p, flags, false, gn_unit, gn_stats != nullptr)) g_last_choice = TileChoice{p.bn, p.splits, 1};
 
   CUtensorMap tmA, tmB;
   {
@@ -1250,13 +1437,13 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   }
   CUtensorMap tmC;
   {
-    const bool part = p.splits > 1;
+    const bool part = p.splits > 1 && !p.cluster_k;     // cluster split-K stores straight from registers: tmC is unused
     const bool f32 = (flags & TF_EPI_OUT_F32) != 0 || part;
     p.partial = part ? reinterpret_cast<float*>(workspace) : nullptr;
     const void* base = part ? workspace : out;
     const uint64_t ld = part ? (uint64_t)Cout : (uint64_t)ldc;
     const uint64_t es_b = f32 ? 4 : 2;
-    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NI, (uint64_t)p.splits};
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NI, (uint64_t)(part ? p.splits : 1)};
     uint64_t strides[4] = {ld * es_b, (uint64_t)Wo * ld * es_b, (uint64_t)Ho * Wo * ld * es_b,
                            (uint64_t)NI * Ho * Wo * ld * es_b};
     uint32_t box[5] = {32u, (uint32_t)g.sbw, (uint32_t)g.sbh, (uint32_t)(32 / (g.sbw * g.sbh)), 1u};

@@ -7,25 +7,34 @@ import numpy as np
 import torch
 
 from ..native.b200.ops import b200
-from ..runtime import F16, F32, stream_ptr
+from ..runtime import F16, F32, as_f32, stream_ptr
 from ..storage.state import _default_device
 
 
-def _ids_tensor(idx, device):
+def _ids_tensor(idx, device, vocab=None):
+    """Token ids -> int32 device tensor. With `vocab`, ids outside [0, vocab) raise (the gather kernel would clamp them, and a
+    silently clamped id is a wrong embedding): checked on the host copy the ids arrive as (numpy / CPU tensor), or with one
+    device reduction for ids that are already on the GPU."""
     if isinstance(idx, torch.Tensor):
-        return idx.to(device=device, dtype=torch.int32).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(idx), dtype=np.int32)).to(device)
+        t = idx
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(idx), dtype=np.int64))
+    if vocab is not None and t.numel():
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= vocab:
+            raise RuntimeError(f"tinyfusers_b200 embedding: token id out of range [0, {vocab}): min {lo}, max {hi}")
+    return t.to(device=device, dtype=torch.int32).contiguous()
 
 
 def embedding(weight, idx):
     """weight: (vocab, E) fp32 CUDA tensor; idx: (1, N) integer ids -> (N, E) fp32."""
-    ids = _ids_tensor(idx, weight.device).reshape(-1)
+    ids = _ids_tensor(idx, weight.device, weight.shape[0]).reshape(-1)
     N, E = ids.numel(), weight.shape[1]
     out = torch.empty((N, E), dtype=F16, device=weight.device)
     w = weight.to(F32).contiguous()
     st = b200.tf_embedding_f16(ids.data_ptr(), w.data_ptr(), None, out.data_ptr(), N, N, E, w.shape[0], stream_ptr())
     b200.check(st, "tf_embedding_f16")
-    return out.to(F32)
+    return as_f32(out)
 
 
 class Embedding:

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import fp32, get_layernorm_strided, packing
-from ..runtime import F16, F32, require_cuda, standalone_context
+from ..runtime import F16, F32, as_f16, as_f32, require_cuda, standalone_context
 from ..storage.state import _default_device
 
 
@@ -22,13 +22,13 @@ def layer_norm(x_gpu, scale_gpu, bias_gpu, epsilon_cpu):
         return fp32.layer_norm(x_gpu, scale_gpu.reshape(-1), bias_gpu.reshape(-1), float(np.asarray(epsilon_cpu).reshape(-1)[0]))
     ctx = standalone_context()
     _, B, T, C = x_gpu.shape
-    xh = x_gpu.to(F16).contiguous()
+    xh = as_f16(x_gpu)
     out = torch.empty_like(xh)
     g = scale_gpu.reshape(-1).to(F32).contiguous()
     b = bias_gpu.reshape(-1).to(F32).contiguous()
     il = B if get_layernorm_strided() else 1
     ctx.layernorm(xh.data_ptr(), out.data_ptr(), B * T, C, g.data_ptr(), b.data_ptr(), float(np.asarray(epsilon_cpu).reshape(-1)[0]), il)
-    return out.to(F32)
+    return as_f32(out)
 
 
 class LayerNorm:

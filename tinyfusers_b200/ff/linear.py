@@ -6,7 +6,7 @@ import torch
 
 from .. import fp32, packing
 from ..native.b200.ops import b200
-from ..runtime import F16, F32, require_cuda, standalone_context
+from ..runtime import F16, F32, as_f16, require_cuda, standalone_context
 from ..storage.state import _default_device
 
 
@@ -33,7 +33,7 @@ class Linear:
         x2 = x.reshape(-1, in_f)
         M = x2.shape[0]
         if Kp == in_f:
-            a = x2.to(F16).contiguous()
+            a = as_f16(x2)
         else:
             a = torch.zeros((M, Kp), dtype=F16, device=x.device)
             a[:, :in_f] = x2

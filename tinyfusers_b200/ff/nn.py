@@ -7,7 +7,7 @@ import torch
 
 from .. import fp32, packing
 from ..native.b200.ops import b200
-from ..runtime import F16, F32, require_cuda, standalone_context
+from ..runtime import F16, F32, as_f16, as_f32, require_cuda, standalone_context
 from .linear import Linear
 
 
@@ -25,10 +25,10 @@ class GEGLU:
         if fp32.enabled():
             return fp32.geglu(self, x)
         ctx = standalone_context()
-        a = x.reshape(-1, x.shape[-1]).to(F16).contiguous()
+        a = as_f16(x.reshape(-1, x.shape[-1]))
         out = torch.empty((a.shape[0], self.dim_out), dtype=F16, device=x.device)
         self._run(ctx, a.data_ptr(), a.shape[1], a.shape[0], out.data_ptr())
-        return out.to(F32).reshape(*x.shape[:-1], self.dim_out)
+        return as_f32(out).reshape(*x.shape[:-1], self.dim_out)
 
     def _packed_ln(self, norm):
         """The projection with the preceding LayerNorm folded in, in the TF_EPI_GEGLU row order: (W', c1, c2)."""
@@ -91,10 +91,10 @@ class CLIPMLP:
             return fp32.clip_mlp(self, hidden_states)
         ctx = standalone_context()
         ctx.arena.reset()
-        x2 = hidden_states.reshape(-1, 768).to(F16).contiguous()
-        h = torch.zeros_like(x2)
+        x2 = as_f16(hidden_states.reshape(-1, 768))
+        h = torch.empty_like(x2)
         self._run(ctx, x2.data_ptr(), h.data_ptr(), x2.shape[0], residual=False)
-        return h.to(F32).reshape(hidden_states.shape)
+        return as_f32(h).reshape(hidden_states.shape)
 
     # h (M, 768) fp16:  h <- fc2(quick_gelu(fc1(xn))) (+ h)
     def _run(self, ctx, xn_ptr, h_ptr, M, residual=True):

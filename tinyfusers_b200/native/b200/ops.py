@@ -35,6 +35,7 @@ _SIGNATURES = {
     "tf_launch_count_reset": (None, []),
     "tf_gemm_set_tuning": (c_int, [c_int, c_int]),
     "tf_gemm_set_ctas": (c_int, [c_int]),
+    "tf_gemm_set_cluster_splitk": (c_int, [c_int]),
     "tf_gemm_set_timeline": (c_int, [_P]),
     "tf_gemm_set_max_stages": (c_int, [c_int]),
     "tf_gemm_tuning_add": (c_int, [c_int] * 8),
@@ -66,6 +67,7 @@ _SIGNATURES = {
     "tf_attention_set_tuning": (c_int, [c_int]),
     "tf_attention_set_variant": (c_int, [c_int, c_int]),
     "tf_attention_set_timeline": (c_int, [_P]),
+    "tf_attention_set_debug": (c_int, [_P]),
     "tf_attention_causal_f16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_longlong, c_longlong, c_longlong, c_int,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "tf_plane_attention_f16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
@@ -83,6 +85,13 @@ _SIGNATURES = {
     "tf_nhwc_to_nchw": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_pad_tokens_f32_to_f16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "tf_cfg_ddim_step_f32": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
+    "tf_p2p_blocks": (c_int, [c_int, c_int]),
+    "tf_p2p_alloc": (c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), _P]),
+    "tf_p2p_open": (c_int, [_P, ctypes.POINTER(ctypes.c_void_p)]),
+    "tf_p2p_close": (c_int, [_P]),
+    "tf_p2p_free": (c_int, [_P]),
+    "tf_cfg_ddim_step_split_f32": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P, _P, _P, _P, _P,
+                                           c_int, _P]),
     "tf_add_int": (c_int, [_P, c_int, _P]),
     "tf_unary": (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
     "tf_nhwc_f32_to_nchw_f32": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P]),
@@ -126,10 +135,16 @@ class B200:
             raise RuntimeError(f"{name} failed with status {status}: {self.last_error()}")
 
     def init(self, device=0):
+        """One process per GPU: the first call binds the library to `device`; a different device later raises."""
+        device = int(device)
         if not self._initialised:
-            self.check(self.tf_init(int(device)), "tf_init")
+            self.check(self.tf_init(device), "tf_init")
             self._initialised = True
+            self._device = device
             self.load_tuning()
+        elif device != self._device:
+            raise RuntimeError(f"tinyfusers_b200 serves one GPU per process (bound to cuda:{self._device}, asked for cuda:{device}); "
+                               "launch one process per GPU (torchrun / example.sd1 --gpus N)")
 
     def load_tuning(self, path=None):
         """Measured GEMM / conv tile choices (tools/autotune_gemm.py, run on a B200). Optional: shapes without an entry

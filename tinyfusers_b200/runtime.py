@@ -363,16 +363,50 @@ def nchw_to_act(x, c_pad_to=8):
 
 def act_to_nchw(a, C=None, dtype=F32):
     C = a.c if C is None else C
-    out = torch.empty((a.n, C, a.h, a.w), dtype=dtype, device="cuda")
+    dev = a.keep[0].device if isinstance(a.keep, tuple) else (a.keep.device if a.keep is not None else torch.device("cuda", torch.cuda.current_device()))
+    out = torch.empty((a.n, C, a.h, a.w), dtype=dtype, device=dev)
     st = b200.tf_nhwc_to_nchw(a.ptr, a.stride, out.data_ptr(), 1 if dtype == F32 else 0, a.n, C, a.h * a.w, stream_ptr())
     b200.check(st, "tf_nhwc_to_nchw")
     return out
 
 
+def as_f16(x, rows_pad_to=1):
+    """fp32 / fp16 CUDA activation (..., C) -> NEW contiguous fp16 tensor (same shape; with rows_pad_to > 1 a 2-D (rows, C) input
+    gets zero rows appended up to a multiple of it). The conversion is a tf_* launch (tf_pad_tokens_f32_to_f16), not a torch op:
+    the stand-alone operator wrappers use torch for memory only."""
+    require_cuda(x, "x")
+    if x.dtype not in (F16, F32):
+        raise RuntimeError(f"tinyfusers_b200: activations must be fp32 or fp16, got {x.dtype}")
+    xc = x.contiguous()
+    C = xc.shape[-1]
+    rows = xc.numel() // C
+    rows_p = (rows + rows_pad_to - 1) // rows_pad_to * rows_pad_to
+    shape = tuple(xc.shape) if rows_p == rows else (rows_p, C)
+    out = torch.empty(shape, dtype=F16, device=xc.device)
+    if xc.dtype == F16:
+        if rows_p != rows:
+            out.zero_()
+        out.view(-1)[:xc.numel()].copy_(xc.view(-1))          # device copy, no arithmetic
+        return out
+    st = b200.tf_pad_tokens_f32_to_f16(xc.data_ptr(), out.data_ptr(), 1, rows, rows_p, C, stream_ptr())
+    b200.check(st, "tf_pad_tokens_f32_to_f16")
+    return out
+
+
+def as_f32(x):
+    """fp16 CUDA tensor -> new fp32 tensor of the same shape through tf_cast_f16_to_f32 (fp32 input: returned as is)."""
+    require_cuda(x, "x")
+    if x.dtype == F32:
+        return x
+    xc = x.contiguous()
+    out = torch.empty(xc.shape, dtype=F32, device=xc.device)
+    b200.check(b200.tf_cast_f16_to_f32(xc.data_ptr(), out.data_ptr(), xc.numel(), stream_ptr()), "tf_cast_f16_to_f32")
+    return out
+
+
 def tokens_to_act(x):
     """(B,T,C) CUDA tensor -> fp16 Act (n=B, h=T, w=1)."""
-    require_cuda(x, "x")
-    xh = x.to(F16).contiguous()  # dtype cast only; container-level
+    xh = as_f16(x)
     B, T, C = xh.shape
     return Act(xh.data_ptr(), B, T, 1, C, C, keep=xh)
 

@@ -17,7 +17,7 @@ from ..ff.group_norm import GroupNorm
 from ..ff.layer_norm import LayerNorm
 from ..ff.nn import CLIPMLP
 from ..native.b200.ops import b200
-from ..runtime import F16, F32, standalone_context, stream_ptr
+from ..runtime import F16, F32, as_f16, as_f32, standalone_context, stream_ptr
 from ..vision.conv2d import Conv2d
 from ..vision.resnet import ResnetBlock
 from .mid import Mid
@@ -53,17 +53,18 @@ class CLIPEncoderLayer:
         B, T, E = hidden_states.shape
         if fp32.enabled():
             return fp32.clip_encoder_layer(self, hidden_states)
+        from ..attention.attention import _check_causal_mask
+        _check_causal_mask(causal_attention_mask, T)
         ctx = standalone_context()
         Tp = (T + 7) // 8 * 8
-        outs = []
+        out = torch.empty((B, T, E), dtype=F32, device=hidden_states.device)
         for i in range(B):
             ctx.arena.reset()
-            h = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
-            h[:T] = hidden_states[i]
+            h = as_f16(hidden_states[i], rows_pad_to=8)            # (Tp, E) residual stream, pad rows zero
             xn = torch.zeros((Tp, E), dtype=F16, device=hidden_states.device)
             self._run(ctx, h.data_ptr(), xn.data_ptr(), T, Tp)
-            outs.append(h[:T].to(F32))
-        return torch.stack(outs)
+            out[i].copy_(as_f32(h)[:T])
+        return out
 
     # h (Tp, 768) fp16 residual stream, updated in place; xn: scratch for the normalised rows (rows >= T stay zero)
     def _run(self, ctx, h_ptr, xn_ptr, T, Tp):
@@ -102,7 +103,7 @@ class CLIPTextTransformer:
         """(B, T <= 77) token ids -> (B, T, 768) fp32 prompt embeddings (reference: encoder.py:78-81)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         b200.init(dev.index)
-        ids = _ids_tensor(input_ids, dev)
+        ids = _ids_tensor(input_ids, dev, self.embeddings.token_embedding.weight.shape[0])
         if ids.dim() == 1:
             ids = ids.reshape(1, -1)
         B, T = ids.shape

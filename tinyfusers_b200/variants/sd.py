@@ -109,6 +109,14 @@ class StableDiffusion:
         from .. import dp
         return dp.sample_sharded(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance, group)
 
+    def sample_cfg_split(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance, group=None):
+        """ONE image on TWO GPUs: rank 0 evaluates the unconditional half of `get_model_output`'s batch (reference sd.py:27-46),
+        rank 1 the conditional half; the two noise predictions are exchanged by peer stores over NVLink inside the CFG + DDIM
+        kernel (tinyfusers_b200/cfg_split.py). Both ranks return the same final latent, bit for bit."""
+        from .. import cfg_split
+        return cfg_split.sample_cfg_split(self, unconditional_context, context, latent, timesteps, alphas, alphas_prev, guidance,
+                                          group)
+
     def _sampler(self, latent_shape, ctx_tokens):
         B, C, H, W = latent_shape
         key = (torch.cuda.current_device(), B, H, W, ctx_tokens, get_quirks(), get_layernorm_strided())

@@ -49,7 +49,7 @@ def run(B, NH, T, d, causal=False, scale_in=1.0, variants=((1, 0, 0), (2, 0, 0),
         print(f"  B={B} NH={NH} T={T} d={d} causal={int(causal)} in_scale={scale_in} v{ver} emu{emu} ones{ones}: {us:8.2f} us  {4.0 * B * NH * T * T * d / us / 1e6 / (2 if causal else 1):6.1f} TFLOP/s  rel_err {err:.2e}", flush=True)
     b200.tf_attention_set_variant(0, -1)
 if __name__ == "__main__":
-    # argv: "ver,emu ver,emu ..." (emu + 10 = warpgroup order off) then optional "quick"
+    # argv: "ver,emu ver,emu ..." then optional "quick"
     var = tuple(tuple(int(x) for x in a.split(",")) for a in sys.argv[1:] if "," in a) or ((1, 0, 0), (1, 0, 1), (2, 0, 0), (2, 2, 0), (2, 0, 1), (2, 2, 1), (2, 4, 1), (2, 12, 1))
     quick = "quick" in sys.argv
     run(2, 8, 4096, 40, variants=var)
