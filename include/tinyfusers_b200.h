@@ -203,9 +203,11 @@ int tf_attention_v_f16(const void* q, int ldq, const void* k, int ldk, const voi
                        long long out_stride_b, long long out_stride_h, long long out_stride_t, int B, int NH, int Tq,
                        int Tk, int Tk_pad, int d, int dp, int dvp, float scale, int causal, void* stream);
 int tf_attention_set_tuning(int force_bn);
-/* Kernel variant for tf_attention_v_f16: version 0 = automatic (the two-query-tile ping-pong kernel where whole pairs of
-   128-row query tiles fill the GPU, the one-tile kernel elsewhere), 1 = one-tile kernel only, 2 = ping-pong wherever it
-   applies; emu = exponentials per 8 evaluated on the FMA pipe instead of MUFU.EX2 (0, 2, 4; < 0 keeps the current value). */
+/* Kernel variant for tf_attention_v_f16: version 0 = automatic (the split-row kernel where its grid is one wave, the
+   two-query-tile ping-pong kernel where whole pairs of 128-row query tiles fill the GPU, the one-tile kernel elsewhere),
+   1 = one-tile kernel only, 2 = ping-pong wherever it applies, 3 = split-row wherever it applies (head dim <= 48, V padded
+   to 64 columns); emu = exponentials per 8 evaluated on the FMA pipe instead of MUFU.EX2 (0, 2, 4; < 0: each kernel's
+   measured best). */
 int tf_attention_set_variant(int version, int emu);
 /* debug hook: per-block clock64 stamps of one softmax warp ([64][8] int64; NULL = off; TF_ATT_TRACE builds only) */
 int tf_attention_set_timeline(long long* dev_buf);

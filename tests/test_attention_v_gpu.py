@@ -99,7 +99,7 @@ def test_two_tile_kernel_peaked_rows_rescale():
     heads = lambda t: t.cuda().half().float().permute(0, 2, 1, 3)
     ref = torch.nn.functional.scaled_dot_product_attention(heads(q), heads(k), heads(v)).permute(0, 2, 1, 3)
     try:
-        for ver in (1, 2):
+        for ver in (1, 2, 3):
             b200.check(b200.tf_attention_set_variant(ver, 2), "variant")
             out.zero_()
             st = b200.tf_attention_v_f16(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, V.data_ptr(), NH * dvp, out.data_ptr(),
@@ -107,5 +107,24 @@ def test_two_tile_kernel_peaked_rows_rescale():
                                          torch.cuda.current_stream().cuda_stream)
             b200.check(st, "tf_attention_v_f16")
             assert rel_err(out.float(), ref) < 3e-3, ver
+    finally:
+        b200.tf_attention_set_variant(0, -1)
+
+
+@pytest.mark.parametrize("emu", [0, 2, 4])
+@pytest.mark.parametrize("B,NH,T,Tk,d,causal", [(2, 8, 4096, 4096, 40, False), (1, 2, 512, 512, 40, True), (1, 3, 384, 200, 40, False),
+                                                (1, 1, 256, 256, 48, False), (2, 2, 1024, 1024, 32, False), (1, 2, 256, 136, 40, False)])
+def test_split_row_kernel(B, NH, T, Tk, d, causal, emu):
+    """tf_attention3_kernel forced on (version 3): every row split over two threads with their own reference max and output
+    accumulator, combined in the epilogue - also with a causal mask (half rows that see no key in a block, or in no block at
+    all) and a ragged last key block (Tk % 64 != 0, incl. a second half that is masked entirely). Row sums by the ones-tile
+    MMA into V's pad columns or out of a ones column of V. Same tolerance as the other kernels."""
+    from tinyfusers_b200.native.b200.ops import b200
+    b200.init(0)
+    try:
+        b200.check(b200.tf_attention_set_variant(3, emu), "variant")
+        for ones in (False, True):
+            out, ref = _run(B, NH, T, Tk, d, causal=causal, pad64=True, ones_col=ones)
+            assert rel_err(out, ref) < 3e-3, (emu, ones)
     finally:
         b200.tf_attention_set_variant(0, -1)

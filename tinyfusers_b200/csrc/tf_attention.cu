@@ -651,9 +651,10 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float m_run = -INFINITY;   // reference max of this row (scaled log2 domain); lazily updated (see tf_attention_kernel)
     const uint32_t o_addr = tmem_o(t) + lane_field;
     const bool stamp = q == 0 && lane == 0;
+    bool s_ready = false;   // S_j already seen complete by the probe issued in the middle of block j-1
     for (int j = 0; j < nkv; ++j) {
       if (stamp) ATT2_STAMP(t, 0);
-      att_wait(s_full(t, j & 1), (uint32_t)(j >> 1) & 1u, 7 + t, j);
+      if (!s_ready) att_wait(s_full(t, j & 1), (uint32_t)(j >> 1) & 1u, 7 + t, j);
       tf::tcgen05_fence_after();
       if (stamp) ATT2_STAMP(t, 1);
       const uint32_t s_addr = tmem_s(t, j & 1) + lane_field;
@@ -709,6 +710,9 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       if (stamp) ATT2_STAMP(t, 5);
+      // Probe S_{j+1} now: the barrier unit answers in ~150 cycles even when the phase is long complete (measured: the wait at
+      // the loop top was 10 % of a softmax warp's time, profiles/attention2_r2.md); here that latency hides behind the P store.
+      s_ready = (j + 1 < nkv) && tf::mbar_test_wait(s_full(t, (j + 1) & 1), (uint32_t)((j + 1) >> 1) & 1u);
       // rescale the running output if any row of this warp moved its max (rare after the first blocks: lazy threshold 2^8)
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
         // O belongs to the tensor core until P V_{j-1} has completed. The parity wait below cannot alias an older phase:
@@ -776,11 +780,337 @@ tf_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
-int g_attn_version = 0;   // 0 auto, 1 tf_attention_kernel only, 2 tf_attention2_kernel wherever it applies
+
+// =====================================================================================================================
+// tf_attention3_kernel: one query tile per CTA, every row split over TWO softmax threads, two CTAs per SM (round 2).
+//
+// What limited tf_attention2_kernel (ncu, profiles/attention2_r2.md): two softmax warps per scheduler issue on 53 % of the
+// cycles and no pipe is above 40 % - MUFU 35 %, ALU 35 %, FMA 39 %, tensor 30 % - the warps wait on their own dependency
+// chains and on barrier / tensor-memory latencies with nobody to cover for them. Here 16 softmax warps share an SM (four per
+// scheduler) at the same registers per SM:
+//   * a 128-row tile is served by 8 warps = 256 threads; thread (half, row) owns keys [32 half, 32 half + 32) of every 64-key
+//     block of its row: 32 scores in registers, 16 packed P registers - 96 registers per thread, two 320-thread CTAs per SM;
+//   * the two halves of a row NEVER talk inside the loop: each keeps its own running reference max and accumulates into its OWN
+//     output accumulator, O_A += P_A V[keys 0..31], O_B += P_B V[keys 32..63] (two K = 16 TS MMAs each; the same tensor work as
+//     one K = 64 product). The epilogue combines them: O = (2^(mA-m) O_A + 2^(mB-m) O_B) / (2^(mA-m) lA + 2^(mB-m) lB);
+//   * S stays double-buffered and P stays in tensor memory (half A writes P over columns 0..15 of the buffer, half B over
+//     columns 32..47: each over scores only it reads).
+// TMEM per CTA (256 columns): [S buf 0 (64) | S buf 1 (64) | O_A (64) | O_B (64)]; the row sums live inside the O columns (a
+// ones column of V, or the L MMA into V's zero pad columns), which is what restricts this kernel to head dims <= 48 (SD 1.x
+// at 64x64 and 96x96 latents: d = 40) - the shapes that dominate the step.
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax (warp w: lane quarter w % 4, half (w - 2) / 4).
+// =====================================================================================================================
+constexpr int kA3Threads = 320;
+
+struct Attn3Params {
+  int B, NH, Tq, Tk, Tk_pad, d, dp, v_atom, l_off, l_sel, l_mma, resc_cols, nkv, stages, causal;
+  float scale_log2;
+  __half* out;
+  long long osb, osh, ost;
+};
+
+template <int EMU>
+__global__ void __launch_bounds__(kA3Threads, 2)
+tf_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const Attn3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = tf::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int ST = p.stages;
+  constexpr int DOV = 64;                                   // O columns per accumulator = padded V head dim
+
+  const uint32_t q_bytes = BQ * p.dp * 2;
+  const uint32_t k_bytes = BN2 * p.dp * 2;
+  const uint32_t v_bytes = BN2 * DOV * 2;
+  const uint32_t smem_q = smem_base;
+  const uint32_t smem_k = smem_q + q_bytes;
+  const uint32_t smem_v = smem_k + ST * k_bytes;
+  const uint32_t smem_ones = smem_v + ST * v_bytes;         // 16 x 64 fp16 ones: B operand of L = P . 1
+  const uint32_t bar_base = smem_ones + 2048;
+  const uint32_t q_full = bar_base;
+  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + ST + s); };
+  auto s_full = [&](int buf) { return bar_base + 8u * (1 + 2 * ST + buf); };
+  auto p_full = [&](int buf) { return bar_base + 8u * (3 + 2 * ST + buf); };   // 256 arrivals; one per S buffer (see tf_attention2_kernel)
+  const uint32_t pv_done = bar_base + 8u * (5 + 2 * ST);
+  const uint32_t pv_last = bar_base + 8u * (6 + 2 * ST);
+  const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * ST);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+  if (warp == 0 && lane == 0) {
+    tf::tma_prefetch_desc(&tmQ);
+    tf::tma_prefetch_desc(&tmK);
+    tf::tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    tf::mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      tf::mbar_init(kv_full(s), 1);
+      tf::mbar_init(kv_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tf::mbar_init(s_full(i), 1);
+      tf::mbar_init(p_full(i), 256);
+    }
+    tf::mbar_init(pv_done, 1);
+    tf::mbar_init(pv_last, 1);
+    tf::fence_mbar_init();
+  }
+  if (warp == 2) {
+    tf::tmem_alloc(tmem_slot, 256);
+    tf::tmem_relinquish();
+  }
+  if (warp == 3) {   // 2 KB of fp16 1.0
+    for (int i = lane; i < 128; i += 32)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_ones + i * 16u), "r"(0x3C003C00u) : "memory");
+    tf::fence_proxy_async_smem();
+  }
+  tf::tcgen05_fence_before();
+  __syncthreads();
+  tf::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  tf::pdl_trigger();   // only once this CTA holds its tensor memory (see tf_gemm_kernel)
+  tf::pdl_wait();
+
+  const int nkv = p.nkv;
+  const int slabs = p.dp / 16;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tf::mbar_expect_tx(q_full, q_bytes);
+      tf::tma_load_3d(smem_q, &tmQ, q_full, 0, b * p.Tq + qt * BQ, h * slabs);
+      const int nblk = DOV / p.v_atom;
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % ST;
+        const uint32_t u = j / ST;
+        att_wait(kv_empty(s), (u & 1u) ^ 1u, 21, j);
+        tf::mbar_expect_tx(kv_full(s), k_bytes + v_bytes);
+        const int key0 = b * p.Tk_pad + j * BN2;
+        tf::tma_load_3d(smem_k + s * k_bytes, &tmK, kv_full(s), 0, key0, h * slabs);
+        for (int nb = 0; nb < nblk; ++nb)
+          tf::tma_load_2d(smem_v + s * v_bytes + nb * (BN2 * p.v_atom * 2), &tmV, kv_full(s), h * DOV + nb * p.v_atom, key0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues; see tf_attention2_kernel) =====================
+    const bool elected = tf::elect_one();
+    const uint32_t idesc_s = tf::umma_idesc_f16(BQ, BN2);
+    const uint32_t idesc_o = tf::umma_idesc_f16(BQ, DOV) | (1u << 16);   // bit 16: B (V, natural layout) is MN-major
+    const uint32_t idesc_l = tf::umma_idesc_f16(BQ, 16);
+    const uint64_t qd0 = umma_desc_sw32_kmajor(smem_q), kd0 = umma_desc_sw32_kmajor(smem_k);
+    const uint64_t k_step = k_bytes >> 4, v_step = v_bytes >> 4;
+    const bool v128 = p.v_atom == 64;
+    const uint64_t vd0 = v128 ? umma_desc_sw128_mnmajor(smem_v, BN2 * 128u) : umma_desc_sw32_mnmajor(smem_v, BN2 * 32u);
+    const uint64_t v_kstep = v128 ? (2048u >> 4) : (512u >> 4);            // 16 keys further down the V tile
+    const uint64_t ones_d = tf::umma_desc_sw128_kmajor(smem_ones);
+    const bool l_mma = p.l_mma != 0;
+    const uint32_t ts0 = tmem_base, to0 = tmem_base + 2 * BN2;
+    int qs = 0;
+    uint32_t qphase = 0;
+    uint64_t kd = kd0;
+    auto issue_qk = [&](int jj) {   // S_jj; buffer jj % 2 held P_{jj-2}, whose P V MMAs were issued earlier (in order)
+      att_wait(kv_full(qs), qphase, 22, jj);
+      tf::tcgen05_fence_after();
+      if (elected) {
+        uint64_t qd = qd0, kk = kd;
+        for (int k = 0; k < slabs; ++k, qd += 256, kk += 128)
+          tf::umma_f16_ss(ts0 + (uint32_t)(jj & 1) * BN2, qd, kk, idesc_s, k > 0 ? 1u : 0u);
+        tf::umma_commit(s_full(jj & 1));
+      }
+      __syncwarp();
+      kd += k_step;
+      if (++qs == ST) { qs = 0; qphase ^= 1u; kd = kd0; }
+    };
+    att_wait(q_full, 0, 23, 0);
+    issue_qk(0);
+    int vs = 0;
+    uint64_t vd = vd0;
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) issue_qk(j + 1);
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+      att_wait(p_full(j & 1), (uint32_t)(j >> 1) & 1u, 24, j);
+      tf::tcgen05_fence_after();
+      if (elected) {
+        const uint32_t pa = ts0 + (uint32_t)(j & 1) * BN2;
+#pragma unroll
+        for (int k = 0; k < BN2 / 16; ++k) {
+          const uint32_t hf = (uint32_t)k >> 1;                 // keys 16k .. 16k+15 belong to half hf
+          const uint32_t pk_addr = pa + 32u * hf + 8u * ((uint32_t)k & 1u);   // P_A at columns 0..15, P_B at 32..47
+          const uint32_t od = to0 + hf * DOV;
+          const uint32_t acc = (k & 1) ? 1u : acc0;
+          tf::umma_f16_ts(od, pk_addr, vd + (uint64_t)k * v_kstep, idesc_o, acc);
+          if (l_mma) tf::umma_f16_ts(od + p.l_off, pk_addr, ones_d + 2u * k, idesc_l, acc);
+        }
+        tf::umma_commit(pv_done);
+        if (j == nkv - 1) tf::umma_commit(pv_last);
+        tf::umma_commit(kv_empty(vs));
+      }
+      __syncwarp();
+      vd += v_step;
+      if (++vs == ST) { vs = 0; vd = vd0; }
+    }
+  } else {
+    // ===================== softmax / rescale / epilogue: warps 2-5 keys [0,32) of every block, warps 6-9 keys [32,64) =====================
+    const int hf = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+    const int qrow0 = qt * BQ;
+    const float sc = p.scale_log2;
+    float m_run = -INFINITY;   // reference max of this HALF row (scaled log2 domain), lazily updated
+    const uint32_t o_addr = tmem_base + 2 * BN2 + (uint32_t)hf * DOV + lane_field;
+    bool s_ready = false;
+    for (int j = 0; j < nkv; ++j) {
+      if (!s_ready) att_wait(s_full(j & 1), (uint32_t)(j >> 1) & 1u, 25, j);
+      tf::tcgen05_fence_after();
+      const uint32_t s_addr = tmem_base + (uint32_t)(j & 1) * BN2 + 32u * (uint32_t)hf + lane_field;
+      uint32_t v[32];
+      tf::tmem_ld_x32(s_addr, v);
+      tf::tmem_ld_wait();
+      int valid = min(BN2, p.Tk - j * BN2);
+      if (p.causal) valid = min(valid, qrow0 + row + 1 - j * BN2);
+      valid -= 32 * hf;
+      if (valid < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= valid) v[i] = 0xff800000u;   // -inf
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = tf::fmax3(mx4[u], __uint_as_float(v[i + 2 * u]), __uint_as_float(v[i + 2 * u + 1]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;   // scale > 0
+      float alpha = 1.0f;
+      if (mx > m_run + 8.0f) {          // also taken on the first block with a visible key (m_run = -inf)
+        alpha = exp2f(m_run - mx);      // 0 then
+        m_run = mx;
+      }
+      // a half row that has not seen a visible key yet (causal mask / ragged tail): every score is -inf, P must be 0, not NaN
+      const float neg_m = m_run == -INFINITY ? 0.f : -m_run;
+      uint32_t pk[16];
+      const uint64_t sc2 = tf::pack_f32x2(sc, sc), nm2 = tf::pack_f32x2(neg_m, neg_m);
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const uint64_t xx = tf::fma_f32x2(tf::pack_f32x2(__uint_as_float(v[i + u]), __uint_as_float(v[i + u + 1])), sc2, nm2);
+          tf::unpack_f32x2(xx, x[u], x[u + 1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          if (u >= 8 - EMU) {
+            exp2_fma_pair(x[u], x[u + 1]);
+          } else {
+            x[u] = exp2f(x[u]);
+            x[u + 1] = exp2f(x[u + 1]);
+          }
+          __half2 h2v = __floats2half2_rn(x[u], x[u + 1]);
+          pk[(i + u) >> 1] = *reinterpret_cast<uint32_t*>(&h2v);
+        }
+      }
+      s_ready = (j + 1 < nkv) && tf::mbar_test_wait(s_full((j + 1) & 1), (uint32_t)((j + 1) >> 1) & 1u);
+      // rescale this half's accumulator if any row of the warp moved its max (rare after the first blocks: threshold 2^8)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        // O belongs to the tensor core until P V_{j-1} has completed; the parity wait cannot alias (see tf_attention2_kernel)
+        att_wait(pv_done, (uint32_t)(j - 1) & 1u, 26, j);
+        tf::tcgen05_fence_after();
+        for (int c = 0; c < p.resc_cols; c += 16) {
+          uint32_t o[16];
+          tf::tmem_ld_x16(o_addr + c, o);
+          tf::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tf::tmem_st_x16(o_addr + c, o);
+        }
+      }
+      tf::tmem_st_x16(s_addr, pk);   // P over the first 16 columns of the 32 score columns this thread has just drained
+      tf::tmem_st_wait();
+      tf::tcgen05_fence_before();
+      tf::mbar_arrive(p_full(j & 1));
+    }
+    // ---- epilogue: combine the two halves of every row, O / l -> fp16 -> global ----
+    att_wait(pv_last, 0, 27, nkv);
+    tf::tcgen05_fence_after();
+    float l_own;
+    {
+      uint32_t l16[16];
+      tf::tmem_ld_x16(o_addr + p.l_off, l16);
+      tf::tmem_ld_wait();
+      l_own = __uint_as_float(p.l_sel ? l16[8] : l16[0]);
+    }
+    // exchange through shared memory (the Q tile and the K ring are dead: every MMA that read them has completed): row r of half
+    // B leaves {m, l, O[0..d)} at pitch d + 2 floats (d + 2 = 2 mod 8 words: the rows of a warp spread over the banks)
+    const int pitch = p.d + 2;
+    float* xch = reinterpret_cast<float*>(smem_raw + (smem_q - raw_u32)) + (size_t)row * pitch;
+    if (hf == 1) {
+      xch[0] = m_run;
+      xch[1] = l_own;
+      for (int c = 0; c < p.d; c += 16) {
+        uint32_t o[16];
+        tf::tmem_ld_x16(o_addr + c, o);
+        tf::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < p.d) xch[2 + c + i] = __uint_as_float(o[i]);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) {
+      const float m_b = xch[0], l_b = xch[1];
+      const float m = fmaxf(m_run, m_b);               // finite: every row sees at least one key
+      const float w_a = exp2f(m_run - m), w_b = exp2f(m_b - m);   // exp2(-inf) = 0: a half that never saw a key drops out
+      const float inv_l = 1.0f / (w_a * l_own + w_b * l_b);
+      const float f_a = w_a * inv_l, f_b = w_b * inv_l;
+      const int tq = qrow0 + row;
+      __half* orow = p.out + (long long)b * p.osb + (long long)h * p.osh + (long long)tq * p.ost;
+      for (int c = 0; c < p.d; c += 16) {
+        uint32_t o[16];
+        tf::tmem_ld_x16(o_addr + c, o);
+        tf::tmem_ld_wait();
+        if (tq < p.Tq) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (c + g * 8 < p.d) {
+              tf::Pack16 pk8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = c + g * 8 + 2 * i;
+                pk8.h2[i] = __floats2half2_rn(fmaf(__uint_as_float(o[g * 8 + 2 * i]), f_a, xch[2 + e] * f_b),
+                                              fmaf(__uint_as_float(o[g * 8 + 2 * i + 1]), f_a, xch[3 + e] * f_b));
+              }
+              *reinterpret_cast<uint4*>(orow + c + g * 8) = pk8.v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tf::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tf::tcgen05_fence_after();
+    tf::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int g_attn_version = 0;   // 0 auto, 1 tf_attention_kernel only, 2 / 3: tf_attention2_kernel / tf_attention3_kernel wherever it applies
+// auto mode: tf_attention3_kernel when its grid is ONE wave of two CTAs per SM (4096 tokens x 8 heads x batch 2 = 512 tiles on
+// 592 slots: 99 us vs 107 us for the two-tile kernel, whose 256 CTAs take two waves of 148); on longer grids the two kernels
+// run at the same ~770 cycles per 128 x 64 score tile per SM and the two-tile kernel issues half the row-sum MMAs
+// (profiles/attention3_r2.log)
+long g_attn3_min_tiles = 300;
 // Measured on B200 (tools/dev_attn2.py, profiles/attention2_r2.md), 4096 tokens x d = 40, batch 2, us per call: one-tile kernel
 // 133.3; this kernel with 0 / 2 / 4 of 8 exponentials on the FMA pipe 121.3 / 111.3 / 110.0 with the warpgroup order, 108.5 /
 // 105.0 (2 / 4) without it: forcing the two tiles to alternate costs more in barrier latency than the MUFU collisions it avoids.
-int g_attn_emu = 4;       // exponentials per 8 evaluated on the FMA pipe (0, 2 or 4)
+int g_attn_emu = -1;      // exponentials per 8 evaluated on the FMA pipe (0, 2 or 4); < 0: each kernel's measured best
 
 int g_force_attn_bn = 0;
 int g_force_attn_occ = 0;
@@ -800,10 +1130,10 @@ extern "C" int tf_attention_set_timeline(long long* dev_buf) {
 }
 
 extern "C" int tf_attention_set_variant(int version, int emu) {
-  TF_CHECK_ARG(version >= 0 && version <= 2 && (emu < 0 || emu == 0 || emu == 2 || emu == 4),
-               "tf_attention_set_variant: version in {0 auto, 1, 2}, emu in {0, 2, 4} (< 0: keep)");
+  TF_CHECK_ARG(version >= 0 && version <= 3 && (emu < 0 || emu == 0 || emu == 2 || emu == 4),
+               "tf_attention_set_variant: version in {0 auto, 1, 2, 3}, emu in {0, 2, 4} (< 0: each kernel's default)");
   g_attn_version = version;
-  if (emu >= 0) g_attn_emu = emu;
+  g_attn_emu = emu;   // < 0: back to each kernel's own default
   return TF_OK;
 }
 
@@ -849,6 +1179,77 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
                    ((uintptr_t)out & 15) == 0,
                "tf_attention_f16: pointers must be 16-byte aligned");
 
+  // ---- split-row kernel (tf_attention3_kernel): natural-layout V padded to 64 columns with the row sums inside them (head
+  // dims <= 48), whole 128-row query tiles, and enough tiles to give every SM its two CTAs ----
+  {
+    const long tiles = (long)(Tq / BQ) * NH * B;
+    const bool can3 = vnat && dov == 64 && Tq % BQ == 0 && Tk >= 2 * BN2 && (ones_col ? d < 64 : d16 + 16 <= 64);
+    const bool want3 = g_attn_version == 3 || (g_attn_version == 0 && tiles >= g_attn3_min_tiles && tiles <= 4L * tf_num_sms());
+    if (can3 && want3) {
+      Attn3Params p3{};
+      p3.B = B; p3.NH = NH; p3.Tq = Tq; p3.Tk = Tk; p3.Tk_pad = Tk_pad; p3.d = d; p3.dp = dp;
+      p3.v_atom = v_atom; p3.causal = causal ? 1 : 0;
+      p3.l_mma = ones_col ? 0 : 1;
+      p3.l_off = ones_col ? (d & ~15) : 48;
+      p3.l_sel = ones_col ? (d & 15) : 0;
+      p3.resc_cols = ones_col ? (d & ~15) + 16 : 64;
+      p3.nkv = ceil_div_i(Tk, BN2);
+      p3.scale_log2 = scale * 1.4426950408889634f;
+      p3.out = reinterpret_cast<__half*>(out);
+      p3.osb = out_stride_b; p3.osh = out_stride_h; p3.ost = out_stride_t;
+      const size_t qb = (size_t)BQ * dp * 2, kb = (size_t)BN2 * dp * 2, vb = (size_t)BN2 * 64 * 2;
+      const long budget = (long)112 * 1024;               // two CTAs per SM
+      int st3 = (int)((budget - 1024 - (long)qb - 2048 - 1024) / (long)(kb + vb));
+      if (st3 > 6) st3 = 6;
+      if (st3 > p3.nkv) st3 = p3.nkv;
+      const size_t xch = (size_t)BQ * (d + 2) * 4;        // epilogue exchange, over the Q tile and the K ring
+      if (st3 >= 2 && xch <= qb + (size_t)st3 * kb) {
+        p3.stages = st3;
+        const size_t smem3 = 1024 + qb + (size_t)st3 * (kb + vb) + 2048 + 1024;
+        CUtensorMap tmQ, tmK, tmV;
+        {
+          uint64_t dims[3] = {16, (uint64_t)B * Tq, (uint64_t)(ldq / 16)};
+          uint64_t strides[2] = {(uint64_t)ldq * 2, 32};
+          uint32_t box[3] = {16, BQ, (uint32_t)(dp / 16)};
+          uint32_t es[3] = {1, 1, 1};
+          int rc = tf_encode_tmap(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_32B);
+          if (rc) return rc;
+        }
+        {
+          uint64_t dims[3] = {16, (uint64_t)B * Tk_pad, (uint64_t)(ldk / 16)};
+          uint64_t strides[2] = {(uint64_t)ldk * 2, 32};
+          uint32_t box[3] = {16, (uint32_t)BN2, (uint32_t)(dp / 16)};
+          uint32_t es[3] = {1, 1, 1};
+          int rc = tf_encode_tmap(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, k, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_32B);
+          if (rc) return rc;
+        }
+        {
+          uint64_t dims[2] = {(uint64_t)ldvt, (uint64_t)B * Tk_pad};
+          uint64_t strides[1] = {(uint64_t)ldvt * 2};
+          uint32_t box[2] = {(uint32_t)v_atom, (uint32_t)BN2};
+          uint32_t es[2] = {1, 1};
+          int rc = tf_encode_tmap(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt, dims, strides, box, es,
+                                  v_atom == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
+          if (rc) return rc;
+        }
+        static bool attr3_set = false;
+        if (!attr3_set) {
+          TF_CUDA(cudaFuncSetAttribute(tf_attention3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+          TF_CUDA(cudaFuncSetAttribute(tf_attention3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+          TF_CUDA(cudaFuncSetAttribute(tf_attention3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+          attr3_set = true;
+        }
+        dim3 grid3(Tq / BQ, NH, B);
+        const int emu3 = g_attn_emu < 0 ? 2 : g_attn_emu;     // measured best: 2 of 8 (99.2 us; 4 of 8: 103.3, none: 112.8)
+        if (emu3 == 0) TF_LAUNCH((tf_attention3_kernel<0>), grid3, kA3Threads, smem3, stream, tmQ, tmK, tmV, p3);
+        else if (emu3 == 4) TF_LAUNCH((tf_attention3_kernel<4>), grid3, kA3Threads, smem3, stream, tmQ, tmK, tmV, p3);
+        else TF_LAUNCH((tf_attention3_kernel<2>), grid3, kA3Threads, smem3, stream, tmQ, tmK, tmV, p3);
+        TF_LAUNCH_CHECK();
+        tf_launch_count_add(1);
+        return TF_OK;
+      }
+    }
+  }
   // ---- two-tile ping-pong kernel (tf_attention2_kernel): natural-layout V, whole pairs of 128-row query tiles, and a grid
   // that gives (nearly) every SM a CTA; everything else stays on tf_attention_kernel ----
   {
@@ -916,8 +1317,9 @@ static int attention_impl(const void* q, int ldq, const void* k, int ldk, const 
           attr2_set = true;
         }
         dim3 grid2(Tq / (2 * BQ), NH, B);
-        if (g_attn_emu == 0) TF_LAUNCH((tf_attention2_kernel<0>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
-        else if (g_attn_emu == 4) TF_LAUNCH((tf_attention2_kernel<4>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
+        const int emu2 = g_attn_emu < 0 ? 4 : g_attn_emu;
+        if (emu2 == 0) TF_LAUNCH((tf_attention2_kernel<0>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
+        else if (emu2 == 4) TF_LAUNCH((tf_attention2_kernel<4>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
         else TF_LAUNCH((tf_attention2_kernel<2>), grid2, kA2Threads, smem2, stream, tmQ, tmK, tmV, p2);
         TF_LAUNCH_CHECK();
         tf_launch_count_add(1);
