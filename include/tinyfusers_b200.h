@@ -144,6 +144,19 @@ int tf_gemm_last_choice(int* bn, int* splits, int* ctas);
 int tf_gemm_set_max_stages(int max_stages);
 /* debug hook: per-CTA clock64 stamps of the next GEMM/conv launches ([grid][8] int64; NULL = off) */
 int tf_gemm_set_timeline(long long* dev_buf);
+/* Next-layer weight prefetch into L2. Every layer's weights arrive cold from HBM (SD 1.5: 1.7 GB of fp16 weights per step
+ * through a 126 MB L2), and a launch cannot know which layer follows it - but a denoising step is the same launch sequence
+ * every time. mode 1: record the (pointer, bytes) of every static-weight GEMM / conv launch from now on (run ONE eager step);
+ * mode 2: replay - launch i of the same sequence (in practice: the capture of the step's CUDA graph) asks L2 for the weights
+ * of launch i + 1 once its own operand loads are in flight (cp.async.bulk.prefetch.L2, one slice per CTA), the last launch for
+ * those of launch 0 (the next step); mode 0: off. A launch whose weights differ from the recorded ones ends the replay.
+ * No reference counterpart (the reference's cuDNN / cuBLAS calls stream weights per call: tinyfusers/vision/conv2d.py:31-46,
+ * tinyfusers/ff/linear.py:119-120). Results are unaffected: a prefetch only warms the cache. */
+int tf_weight_prefetch_mode(int mode);
+/* weights smaller than min_bytes or larger than max_bytes are not prefetched (defaults 1 MiB / 96 MiB) */
+int tf_weight_prefetch_limits(long long min_bytes, long long max_bytes);
+/* launches recorded by the last mode-1 pass; launches (and bytes) that were handed a hint since the last mode change */
+int tf_weight_prefetch_stats(int* recorded, int* hinted, long long* hinted_bytes);
 
 /* ---- normalisation -------------------------------------------------------------------------------- */
 /* GroupNorm (+ optional SiLU), NHWC fp16 -> NHWC fp16, statistics fp32, biased variance.

@@ -33,6 +33,25 @@ def get_layernorm_strided() -> bool:
     return _LN_STRIDED
 
 
+import os as _os
+
+# OFF by default: measured on B200 (tools/ab_prefetch.py, profiles/ab_weight_prefetch_r2.json) 3.617 ms/step without, 3.623 with,
+# at batch 16 18.54 vs 18.48 - the small-M layers are bound by the L2 -> SM operand feed (every CTA of an output row block
+# re-reads the activation tile), not by the cold HBM fetch of their weights, which the TMA ring already overlaps.
+_WEIGHT_PREFETCH = _os.environ.get("TINYFUSERS_B200_WEIGHT_PREFETCH", "0") == "1"
+
+
+def set_weight_prefetch(flag: bool):
+    """Captured steps ask L2 for the NEXT layer's weights while the current layer drains (include/tinyfusers_b200.h,
+    tf_weight_prefetch_mode). Affects graphs captured after the call; results are identical either way."""
+    global _WEIGHT_PREFETCH
+    _WEIGHT_PREFETCH = bool(flag)
+
+
+def weight_prefetch_enabled() -> bool:
+    return _WEIGHT_PREFETCH
+
+
 def set_precision(mode: str):
     """"fp16" (default: the tcgen05 path, <= 1e-2) or "fp32" (parity mode of BASELINE.json configs[0], <= 1e-5;
     plain-fp32 kernels in the reference's layouts - tinyfusers_b200/fp32.py, csrc/tf_fp32.cu)."""

@@ -166,6 +166,11 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 }
 
 // ---- TMA ------------------------------------------------------------------------------------
+// L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16): no shared-memory destination,
+// no completion to wait for
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "tf_common.cuh"
 #include "tinyfusers_b200.h"
@@ -78,6 +79,12 @@ struct GemmParams {
   int cluster_k;   // 1: the `splits` CTAs of one output tile form a thread-block cluster and fold their fp32 partials through
                    // distributed shared memory inside this launch (no workspace round trip, no fold kernel); see the epilogue
   int flags;
+  // Next layer's weights (tf_weight_prefetch_mode): once this CTA's own operand loads are all in flight, its producer warp
+  // asks L2 to fetch slice blockIdx.x of [pf_ptr, pf_ptr + pf_bytes) - every layer's weights arrive cold from HBM (1.7 GB per
+  // step through a 126 MB L2), and the tail of this kernel, the fold / normalisation launches behind it and the next launch's
+  // prologue otherwise leave HBM idle.
+  const uint8_t* pf_ptr;
+  unsigned long long pf_bytes;
   long long* timeline;  // optional debug: per-CTA clock stamps [grid][8] (tf_gemm_set_timeline)
   // optional GroupNorm statistics of the OUTPUT (fp16 epilogue only): gn_stats[image][slot][unit] = {sum, sumsq}
   // over one 32-row slot x gn_unit consecutive channels, computed from the rounded fp16 values.
@@ -332,6 +339,15 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         advance();
+      }
+    }
+    if (p.pf_bytes != 0 && elected) {
+      constexpr unsigned long long kChunk = 32768;
+      const unsigned long long n_chunks = (p.pf_bytes + kChunk - 1) / kChunk;
+      for (unsigned long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const unsigned long long off = c * kChunk;
+        const unsigned long long rem = p.pf_bytes - off;
+        tf::l2_prefetch_bulk(p.pf_ptr + off, (uint32_t)(rem < kChunk ? rem : kChunk));
       }
     }
   } else if (warp == 1) {
@@ -1009,6 +1025,34 @@ static TileChoice choose_tiles(int m_tiles, int N, int k_blocks, int flags, bool
 }
 
 static long long* g_timeline = nullptr;
+
+// ---- next-layer weight prefetch: record / replay of the step's weight sequence ----
+// The library cannot know which layer follows a launch, but a denoising step is the same launch sequence every time. Mode 1
+// records (pointer, bytes) of every static-weight GEMM / conv launch; mode 2 (set right before the same sequence is enqueued
+// again - in practice: captured into the step's CUDA graph) hands launch i the weights of launch i + 1 (the last one those of
+// launch 0: the next step). A launch whose own weights differ from the recorded ones ends the replay (hints are then
+// dropped, never wrong: a prefetch only warms L2).
+struct WeightRec { const void* ptr; unsigned long long bytes; };
+static std::vector<WeightRec> g_wseq;
+static int g_wmode = 0;
+static size_t g_widx = 0;
+static long long g_pf_min_bytes = 1 << 20, g_pf_max_bytes = 96ll << 20;
+static long long g_pf_hinted = 0, g_pf_hinted_bytes = 0;   // since the last mode change
+
+static void prefetch_hint(GemmParams& p, const void* W, unsigned long long bytes, int flags) {
+  p.pf_ptr = nullptr; p.pf_bytes = 0;
+  if (!(flags & TF_GEMM_W_STATIC) || g_wmode == 0) return;
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  if (g_wmode == 1) { g_wseq.push_back({W, bytes}); return; }
+  if (g_widx >= g_wseq.size() || g_wseq[g_widx].ptr != W || g_wseq[g_widx].bytes != bytes) { g_wmode = 0; return; }
+  const WeightRec& nx = g_wseq[(g_widx + 1) % g_wseq.size()];
+  ++g_widx;
+  if ((long long)nx.bytes >= g_pf_min_bytes && (long long)nx.bytes <= g_pf_max_bytes && ((uintptr_t)nx.ptr & 15) == 0) {
+    p.pf_ptr = reinterpret_cast<const uint8_t*>(nx.ptr);
+    p.pf_bytes = nx.bytes & ~15ull;
+    ++g_pf_hinted; g_pf_hinted_bytes += (long long)p.pf_bytes;
+  }
+}
 static int g_max_stages = 0;   // debug: cap the smem ring depth (0 = as many as fit)
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmParams& p,
@@ -1097,6 +1141,29 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }
 
 }  // namespace
+
+extern "C" int tf_weight_prefetch_mode(int mode) {
+  TF_CHECK_ARG(mode >= 0 && mode <= 2, "tf_weight_prefetch_mode: 0 off, 1 record, 2 replay");
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  if (mode == 1) g_wseq.clear();
+  if (mode != 0) { g_pf_hinted = 0; g_pf_hinted_bytes = 0; }
+  g_widx = 0;
+  g_wmode = (mode == 2 && g_wseq.empty()) ? 0 : mode;
+  return TF_OK;
+}
+
+extern "C" int tf_weight_prefetch_stats(int* recorded, int* hinted, long long* hinted_bytes) {
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  if (recorded) *recorded = (int)g_wseq.size();
+  if (hinted) *hinted = (int)g_pf_hinted;
+  if (hinted_bytes) *hinted_bytes = g_pf_hinted_bytes;
+  return TF_OK;
+}
+
+extern "C" int tf_weight_prefetch_limits(long long min_bytes, long long max_bytes) {
+  g_pf_min_bytes = min_bytes; g_pf_max_bytes = max_bytes;
+  return TF_OK;
+}
 
 extern "C" int tf_gemm_set_timeline(long long* dev_buf) {
   g_timeline = dev_buf;  // >= 148*8 int64; debug only
@@ -1265,6 +1332,7 @@ static int gemm_impl(const void* A, int lda, const void* W, int ldw, void* out, 
   p.out = out; p.ldc = ldc; p.bias = bias;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   p.flags = flags;
+  prefetch_hint(p, W, (unsigned long long)N * (unsigned long long)ldw * 2ull, flags);
   if (clusterize(p, flags, row_stats != nullptr || ln_stats != nullptr, gn_unit, gn_stats != nullptr)) g_last_choice = TileChoice{p.bn, p.splits, 1};
   if (row_stats) {
     p.rs_ld = p.n_tiles;
@@ -1413,6 +1481,7 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
   p.out = out; p.ldc = ldc; p.bias = bias;
   p.residual = reinterpret_cast<const __half*>(residual); p.ldr = ldr;
   p.flags = flags;
+  prefetch_hint(p, w, (unsigned long long)Cout * (unsigned long long)p.K * 2ull, flags);
   if (clusterize(p, flags, false, gn_unit, gn_stats != nullptr)) g_last_choice = TileChoice{p.bn, p.splits, 1};
 
   CUtensorMap tmA, tmB;

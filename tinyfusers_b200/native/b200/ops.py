@@ -37,6 +37,9 @@ _SIGNATURES = {
     "tf_gemm_set_ctas": (c_int, [c_int]),
     "tf_gemm_set_cluster_splitk": (c_int, [c_int]),
     "tf_gemm_set_timeline": (c_int, [_P]),
+    "tf_weight_prefetch_mode": (c_int, [c_int]),
+    "tf_weight_prefetch_stats": (c_int, [_P, _P, _P]),
+    "tf_weight_prefetch_limits": (c_int, [ctypes.c_longlong, ctypes.c_longlong]),
     "tf_gemm_set_max_stages": (c_int, [c_int]),
     "tf_gemm_tuning_add": (c_int, [c_int] * 8),
     "tf_gemm_tuning_clear": (c_int, []),

@@ -14,7 +14,7 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from .. import fp32, get_layernorm_strided, get_quirks, packing
+from .. import fp32, get_layernorm_strided, get_quirks, packing, weight_prefetch_enabled
 from ..native.b200.ops import b200
 from ..runtime import F32, require_cuda, stream_ptr
 from ..vae.encoder import CLIPTextTransformer
@@ -214,17 +214,32 @@ class SamplerEngine:
     def capture(self, advance=True):
         """Capture one step into a CUDA graph; replays need no host work. advance=True also decrements the
         device step index (sampler loop); advance=False is the graph behind the drop-in __call__."""
-        if not getattr(self, "_warm", False):
+        pf = weight_prefetch_enabled()
+        if pf or not getattr(self, "_warm", False):
+            # eager pass: lazy attribute setup and weight packing (never inside a capture) - and, for the next-layer weight
+            # prefetch, the library records this step's weight sequence (tf_weight_prefetch_mode 1) so that the captured
+            # launches below can each name the weights of the launch behind them (mode 2)
             lat, idx = self.latent.clone(), self.idx.clone()
-            self.enqueue_step(advance=False)  # eager warm-up: lazy attribute setup, weight packing (never inside a capture)
+            if pf and getattr(self, "_warm", False):
+                b200.check(b200.tf_weight_prefetch_mode(1), "tf_weight_prefetch_mode")
+            self.enqueue_step(advance=False)
             torch.cuda.synchronize()
+            if pf and not getattr(self, "_warm", False):      # the first pass packed weights: record a settled second one
+                b200.check(b200.tf_weight_prefetch_mode(1), "tf_weight_prefetch_mode")
+                self.enqueue_step(advance=False)
+                torch.cuda.synchronize()
             self.latent.copy_(lat)
             self.idx.copy_(idx)
             self._warm = True
         lat = self.latent.clone()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.enqueue_step(update_latent=True, advance=advance)
+        try:
+            if pf:
+                b200.check(b200.tf_weight_prefetch_mode(2), "tf_weight_prefetch_mode")
+            with torch.cuda.graph(g):
+                self.enqueue_step(update_latent=True, advance=advance)
+        finally:
+            b200.tf_weight_prefetch_mode(0)
         self.latent.copy_(lat)
         return g
 
@@ -236,7 +251,7 @@ class SamplerEngine:
         gen = packing.generation()
         if getattr(self, "_graphs_gen", None) != gen:
             self._graphs, self._warm = {}, False
-        key = (advance, self.guidance)
+        key = (advance, self.guidance, weight_prefetch_enabled())
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = self.capture(advance)
