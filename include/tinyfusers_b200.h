@@ -158,6 +158,19 @@ int tf_weight_prefetch_limits(long long min_bytes, long long max_bytes);
 /* launches recorded by the last mode-1 pass; launches (and bytes) that were handed a hint since the last mode change */
 int tf_weight_prefetch_stats(int* recorded, int* hinted, long long* hinted_bytes);
 
+/* Nearest-neighbour 2x upsampling followed by a 3x3 convolution (pad 1), in ONE launch: out = conv3x3(upsample2x(x)).
+ * Output pixel (2y+a, 2x+b) sees only the 2 x 2 input pixels (y+a-1.., x+b-1..), so each output phase (a, b) is a 2 x 2
+ * convolution of the ORIGINAL image with the 3x3 taps that fall on the same input pixel summed beforehand: 4/9 of the
+ * multiply-adds of the reference's conv over the 4x tensor, and the 4x tensor is never written.
+ * x: (NI, H, W, Cin) NHWC fp16, Cin % 64 == 0. w4: (4, wrows, 4 Cin) fp16 - phase p = 2a + b, row = output channel,
+ * k = (2i + j) Cin + c = the summed taps for input pixel (y + a - 1 + i, x + b - 1 + j) (tinyfusers_b200/packing.py
+ * conv_up2x_weight builds it from the OIHW weight, summing in fp32). out: (NI, 2H, 2W, ldc >= Cout) NHWC fp16. bias fp32 or
+ * NULL. gn_stats / gn_unit as in tf_conv2d_nhwc_gn_f16 (NULL: none; needs H * W % 32 == 0).
+ * Replaces: Upsample.__call__ = reshape/expand 2x + Conv2d  tinyfusers/vision/unet.py:78-84. */
+int tf_conv2d_up2x_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w4, int wrows,
+                            int Cout, void* out, int ldc, const float* bias, int flags, void* gn_stats, int gn_unit,
+                            void* stream);
+
 /* ---- normalisation -------------------------------------------------------------------------------- */
 /* GroupNorm (+ optional SiLU), NHWC fp16 -> NHWC fp16, statistics fp32, biased variance.
  * Replaces: group_norm / GroupNorm.__call__ (>= 8 CuPy launches)   tinyfusers/ff/group_norm.py:3-21

@@ -106,6 +106,32 @@ def test_up_down_sample(oracle):
     assert rel_err(down(xd.cuda()), oracle.downsample(sd, "d", xd)) < TOL
 
 
+@pytest.mark.parametrize("n,c,h,w", [(2, 1280, 8, 8), (2, 1280, 16, 16), (2, 640, 32, 32), (1, 64, 4, 8), (3, 128, 8, 16), (1, 128, 12, 20)])
+def test_upsample_folded_into_conv(oracle, n, c, h, w):
+    """tf_conv2d_up2x_nhwc_f16 (four 2 x 2 phase convolutions of the original image with pre-summed taps) against the oracle's
+    upsample + 3x3 convolution (reference: vision/unet.py:78-84) and against the two-launch path (upsample2x kernel + conv) -
+    the two differ only by the fp16 rounding of the summed taps. The last shape (240 pixels) has no exact tiling: it must
+    take the two-launch path and still match."""
+    from tinyfusers_b200.vision import unet as U
+    sd = {}
+    oracle._add_conv(sd, "u.conv", c, c, 3, 16)
+    g = torch.Generator().manual_seed(16 + h)
+    x = torch.randn(n, c, h, w, generator=g)
+    up = U.Upsample(c)
+    _load(up, sd, "u")
+    ref = oracle.upsample(sd, "u", x)
+    fused = up(x.cuda())
+    assert fused.shape == ref.shape == (n, c, 2 * h, 2 * w)
+    assert rel_err(fused, ref) < TOL
+    old = U.FUSED_UPSAMPLE
+    try:
+        U.FUSED_UPSAMPLE = False
+        plain = up(x.cuda())
+    finally:
+        U.FUSED_UPSAMPLE = old
+    assert rel_err(fused, plain) < 3e-3
+
+
 def test_blocks_match_reference_goldens():
     """CUDA path against the outputs of the reference's OWN Python (tests/golden/reference_outputs.npz)."""
     import os

@@ -60,6 +60,13 @@ struct ConvGeom {
   int pad;               // 1 for 3x3
   int ksize;             // 3
   int sbw, sbh;          // store box of one epilogue warp (32 tile rows): sbw x sbh x (32/(sbw*sbh)) pixels
+  // up2: nearest-neighbour 2x upsampling folded into a 3x3 convolution (tf_conv2d_up2x_nhwc_f16). Output pixel (2y+a, 2x+b)
+  // only ever sees 2 x 2 distinct input pixels - rows y+a-1, y+a, columns x+b-1, x+b - so each of the four output phases
+  // (a, b) is a 2 x 2 convolution of the ORIGINAL image with the 3x3 taps that land on the same input pixel summed up front:
+  // 4/9 of the multiply-adds and no upsampled tensor. H, W, tiles_* then describe the INPUT image; m-tile index =
+  // phase * up2_tiles + tile inside the phase; the weight matrix holds the four phases' (Cout, 4 Cin) blocks one below the
+  // other (up2_wrows rows apart); the output tensor map is 5-D (c, b, x, a, image * H + y).
+  int up2, up2_tiles, up2_wrows;
 };
 
 struct GemmParams {
@@ -111,6 +118,7 @@ __device__ __forceinline__ int tile_row_to_m(const GemmParams& p, int mt, int r)
     return m < p.M ? m : -1;
   }
   const ConvGeom& g = p.g;
+  if (g.up2) mt %= g.up2_tiles;   // phase-local pixel index (these launches carry no per-row operand)
   int tx = mt % g.tiles_x;
   int t2 = mt / g.tiles_x;
   int ty = t2 % g.tiles_y;
@@ -234,7 +242,8 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       pre = min(S, kb1 - kb0);
       if (elected) {
-        const int brow = nt * p.bn + b_row_off;
+        const int mt_first = k2 ? 2 * (t_first / p.splits / p.n_tiles) + (int)rank : t_first / p.splits / p.n_tiles;
+        const int brow = nt * p.bn + b_row_off + ((p.is_conv && p.g.up2) ? (mt_first / p.g.up2_tiles) * p.g.up2_wrows : 0);
         for (int i = 0; i < pre; ++i) {
           const uint32_t bd = smem_b + i * b_stage_bytes;
           if (k2) {
@@ -257,19 +266,26 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = k2 ? 2 * (t1 / p.n_tiles) + (int)rank : t1 / p.n_tiles;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-      int x0 = 0, y0 = 0, n0 = 0;
+      int x0 = 0, y0 = 0, n0 = 0, w_row0 = 0;
       if (p.is_conv) {
         const ConvGeom& g = p.g;
-        int tx = mt % g.tiles_x;
-        int t2 = mt / g.tiles_x;
-        x0 = tx * g.TW * g.cscale - g.pad;
-        y0 = (t2 % g.tiles_y) * g.TH * g.cscale - g.pad;
+        int mtl = mt, padx = g.pad, pady = g.pad;
+        if (g.up2) {   // phase (a, b): taps reach input rows y+a-1, y+a and columns x+b-1, x+b
+          const int ph = mt / g.up2_tiles;
+          mtl = mt - ph * g.up2_tiles;
+          pady = 1 - (ph >> 1); padx = 1 - (ph & 1);
+          w_row0 = ph * g.up2_wrows;
+        }
+        int tx = mtl % g.tiles_x;
+        int t2 = mtl / g.tiles_x;
+        x0 = tx * g.TW * g.cscale - padx;
+        y0 = (t2 % g.tiles_y) * g.TH * g.cscale - pady;
         n0 = (t2 / g.tiles_y) * g.TN;
       }
       // position of k-block kb0: conv = (tap row r, tap column sx, channel block cb); gemm = column kcol
       int r = (kb0 / cblocks) / ksize, sx = (kb0 / cblocks) % ksize, cb = kb0 % cblocks;
       int kcol = kb0 * BK;
-      const int arow = mt * BM, brow = nt * p.bn + b_row_off;
+      const int arow = mt * BM, brow = nt * p.bn + b_row_off + w_row0;
       auto advance = [&]() {
         kcol += BK;
         if (++cb == cblocks) { cb = 0; if (++sx == ksize) { sx = 0; ++r; } }
@@ -468,10 +484,12 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         break;   // one work item per CTA in this mode; phases 2 and 3 follow the role branches (cluster barriers)
       }
       // store coordinates of this warp's 32-row block
-      int sc1, sc2 = 0, sc3 = 0;
+      int sc1, sc2 = 0, sc3 = 0, up_ph = 0;
       if (p.is_conv) {
         const ConvGeom& g = p.g;
-        const int tx = mt % g.tiles_x, t2 = mt / g.tiles_x;
+        int mtl = mt;
+        if (g.up2) { up_ph = mt / g.up2_tiles; mtl = mt - up_ph * g.up2_tiles; }
+        const int tx = mtl % g.tiles_x, t2 = mtl / g.tiles_x;
         const int r0 = q * 32;
         sc1 = tx * g.TW + r0 % g.TW;
         sc2 = (t2 % g.tiles_y) * g.TH + (r0 / g.TW) % g.TH;
@@ -657,7 +675,8 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // split-K partials live in a tensor with one extra (split) dimension, so a tile's overhang is clipped
           // per split instead of spilling into the next split's slab
           if (p.is_conv) {
-            if (partial) tf::tma_store_5d(&tmC, stg_c, col, sc1, sc2, sc3, split);
+            if (p.g.up2) tf::tma_store_5d(&tmC, stg_c, col, up_ph & 1, sc1, up_ph >> 1, sc3 * p.g.H + sc2);   // (c, b, x, a, image * H + y)
+            else if (partial) tf::tma_store_5d(&tmC, stg_c, col, sc1, sc2, sc3, split);
             else tf::tma_store_4d(&tmC, stg_c, col, sc1, sc2, sc3);
           } else {
             if (partial) tf::tma_store_3d(&tmC, stg_c, col, sc1, split);
@@ -691,10 +710,13 @@ tf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.is_conv) {
           const ConvGeom& g = p.g;
           const int ppi = g.TW * g.TH;   // pixels of one image inside a tile (>= 32, exact tiling: host-checked)
-          const int tx = mt % g.tiles_x, t2 = mt / g.tiles_x;
+          const int ph = g.up2 ? mt / g.up2_tiles : 0;
+          const int mtl = mt - ph * g.up2_tiles;
+          const int tx = mtl % g.tiles_x, t2 = mtl / g.tiles_x;
           img = (t2 / g.tiles_y) * g.TN + (q * 32) / ppi;
           valid = img < g.NI;
-          slot = ((t2 % g.tiles_y) * g.tiles_x + tx) * (ppi >> 5) + ((q * 32) % ppi >> 5);
+          // up2: the four phases of an image fill consecutive quarters of its slot range (a slot is any 32 pixels of one image)
+          slot = ph * ((g.H * g.W) >> 5) + ((t2 % g.tiles_y) * g.tiles_x + tx) * (ppi >> 5) + ((q * 32) % ppi >> 5);
         } else {
           const int row0 = mt * BM + q * 32;
           valid = row0 < p.M;
@@ -1534,6 +1556,104 @@ static int conv_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_s
     return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream), &tmA2);
   }
   return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Nearest-neighbour 2x upsampling + 3x3 convolution (pad 1) in one launch, without the upsampled tensor and with 4/9 of the
+// multiply-adds (see ConvGeom::up2). x: (NI, H, W, Cin) NHWC fp16; w4: the four phase matrices (4, wrows, 4 Cin) fp16, phase
+// p = 2a + b, k = (2 i + j) Cin + c for input pixel (y + a - 1 + i, x + b - 1 + j); out: (NI, 2H, 2W, >= Cout) NHWC fp16.
+static int conv_up2x_impl(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w4, int wrows, int Cout,
+                          void* out, int ldc, const float* bias, int flags, void* stream, void* gn_stats, int gn_unit) {
+  TF_CHECK_ARG(x && w4 && out, "tf_conv2d_up2x_nhwc_f16: null pointer");
+  TF_CHECK_ARG(Cin % BK == 0, "tf_conv2d_up2x_nhwc_f16: Cin must be a multiple of 64 (got %d)", Cin);
+  TF_CHECK_ARG(Cout % 8 == 0 && ldc % 8 == 0 && wrows >= Cout, "tf_conv2d_up2x_nhwc_f16: Cout and ldc must be multiples of 8, wrows >= Cout");
+  TF_CHECK_ARG(!(flags & (TF_EPI_GEGLU | TF_EPI_OUT_F32)), "tf_conv2d_up2x_nhwc_f16: fp16 output only");
+  TF_CHECK_ARG(x_pixel_stride >= Cin && x_pixel_stride % 8 == 0, "tf_conv2d_up2x_nhwc_f16: bad input pixel stride");
+  TF_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w4 & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "tf_conv2d_up2x_nhwc_f16: pointers must be 16-byte aligned");
+  TF_CHECK_ARG((long long)NI * H < (1ll << 31), "tf_conv2d_up2x_nhwc_f16: too many rows");
+  {
+    int rc = gn_check(gn_stats, gn_unit, 4 * H * W, NI * 4 * H * W, Cout, flags, "tf_conv2d_up2x_nhwc_gn_f16");
+    if (rc) return rc;
+    if (gn_stats) TF_CHECK_ARG((H * W) % 32 == 0, "tf_conv2d_up2x_nhwc_gn_f16: statistics need H * W %% 32 == 0 (got %d x %d)", H, W);
+  }
+  GemmParams p{};
+  p.is_conv = 1;
+  p.gn_stats = reinterpret_cast<float2*>(gn_stats); p.gn_unit = gn_unit; p.gn_hw = 4 * H * W;
+  p.M = NI * 4 * H * W; p.N = Cout; p.K = 4 * Cin;
+  ConvGeom& g = p.g;
+  g.H = H; g.W = W; g.NI = NI; g.cblocks = Cin / BK; g.cscale = 1; g.pad = 1; g.ksize = 2;
+  long best_tiles = -1;
+  for (int tw = 128; tw >= 1; tw >>= 1) {
+    for (int th = 128 / tw; th >= 1; th >>= 1) {
+      const int tn = 128 / (tw * th);
+      if (tw > 256 || th > 256) continue;
+      // a 32-row store block (and a statistics slot) must stay inside one image: >= 32 pixels of an image per tile, exact tiling
+      if (W % tw != 0 || H % th != 0 || tw * th < 32) continue;
+      const long tiles = (long)(W / tw) * (H / th) * ceil_div_i(NI, tn);
+      if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; g.TW = tw; g.TH = th; g.TN = tn; }
+    }
+  }
+  if (best_tiles < 0) {
+    tf_set_error("tf_conv2d_up2x_nhwc_f16: no exact 128-pixel tiling of the %dx%d input", H, W);
+    return TF_ERR_UNSUPPORTED;
+  }
+  g.tiles_x = W / g.TW;
+  g.tiles_y = H / g.TH;
+  g.up2 = 1;
+  g.up2_tiles = g.tiles_x * g.tiles_y * ceil_div_i(NI, g.TN);
+  g.up2_wrows = wrows;
+  p.m_tiles = 4 * g.up2_tiles;
+  p.k_blocks = p.kb_main = 4 * g.cblocks;
+  g.sbw = g.TW >= 32 ? 32 : g.TW;
+  g.sbh = g.TW >= 32 ? 1 : 32 / g.TW;     // TW * TH >= 32: a block never leaves its image
+  const int klass = (flags & 3) | (gn_stats ? 4 : 0) | 32;
+  TileChoice tc = choose_tiles(p.m_tiles, Cout, p.k_blocks, flags, false, 0, p.M, g_force_bn, 0,
+                               gn_stats ? lcm_i(32, gn_unit) : 32, TuneKey(1, p.M, Cout, p.K, klass));
+  if (g.up2_tiles % 2 != 0) tc.ctas = 1;   // a CTA pair shares one weight tile: both m-tiles must belong to one phase
+  tc.splits = 1;
+  g_last_choice = tc;
+  p.bn = tc.bn; p.splits = 1; p.ctas = tc.ctas;
+  p.n_tiles = ceil_div_i(Cout, p.bn);
+  p.kb_per_split = p.k_blocks;
+  p.out = out; p.ldc = ldc; p.bias = bias;
+  p.residual = nullptr; p.ldr = 0;
+  p.flags = flags;
+  prefetch_hint(p, w4, 4ull * (unsigned long long)wrows * (unsigned long long)p.K * 2ull, flags);
+
+  CUtensorMap tmA, tmB, tmC;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+    uint64_t strides[3] = {(uint64_t)x_pixel_stride * 2, (uint64_t)W * x_pixel_stride * 2, (uint64_t)H * W * x_pixel_stride * 2};
+    uint32_t box[4] = {BK, (uint32_t)g.TW, (uint32_t)g.TH, (uint32_t)g.TN};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = tf_encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)4 * wrows};
+    uint64_t strides[1] = {(uint64_t)p.K * 2};
+    uint32_t box[2] = {BK, (uint32_t)(p.bn / p.ctas)};
+    uint32_t es[2] = {1, 1};
+    int rc = tf_encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    // output pixel (n, 2y + a, 2x + b): address = c + b ldc + x 2 ldc + a 2W ldc + (n H + y) 4W ldc
+    const uint64_t l = (uint64_t)ldc * 2;
+    uint64_t dims[5] = {(uint64_t)Cout, 2, (uint64_t)W, 2, (uint64_t)NI * H};
+    uint64_t strides[4] = {l, 2 * l, 2 * (uint64_t)W * l, 4 * (uint64_t)W * l};
+    uint32_t box[5] = {32u, 1u, (uint32_t)g.sbw, 1u, (uint32_t)g.sbh};
+    uint32_t es[5] = {1, 1, 1, 1, 1};
+    int rc = tf_encode_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, out, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  return launch_gemm(tmA, tmB, tmC, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tf_conv2d_up2x_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w4, int wrows,
+                                       int Cout, void* out, int ldc, const float* bias, int flags, void* gn_stats, int gn_unit,
+                                       void* stream) {
+  return conv_up2x_impl(x, NI, H, W, Cin, x_pixel_stride, w4, wrows, Cout, out, ldc, bias, flags, stream, gn_stats, gn_unit);
 }
 
 extern "C" int tf_conv2d_nhwc_f16(const void* x, int NI, int H, int W, int Cin, int x_pixel_stride, const void* w,

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "tf_conv2d_nhwc_gn_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
                                       _P, _P, c_int, c_int, _P, c_size_t, _P, c_int, _P]),
     "tf_gn_stats_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "tf_conv2d_up2x_nhwc_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, _P, c_int, _P]),
     "tf_conv2d_nhwc_skip_f16": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, _P, c_int,
                                         _P, c_size_t, _P, c_int, _P]),
     "tf_groupnorm_fused_nhwc_f16": (c_int, [_P, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int, _P, c_int, c_int,

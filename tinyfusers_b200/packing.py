@@ -102,6 +102,30 @@ def conv3x3_weight(w, cin_pad_to=64, cout_pad_to=8):
     return p.contiguous()
 
 
+def conv_up2x_weight(w, cin_pad_to=64, cout_pad_to=8):
+    """OIHW fp32 3x3 weight -> (4, Cout_pad, 4 * Cin_pad) fp16 for tf_conv2d_up2x_nhwc_f16: the convolution of a nearest-neighbour
+    2x upsampled image as four 2 x 2 convolutions of the original one. Output phase (a, b) = (row, column) parity; its tap (i, j)
+    reads input pixel (y + a - 1 + i, x + b - 1 + j) and carries the SUM of the 3x3 taps that land on that pixel - rows
+    {0} / {1, 2} for a = 0, {0, 1} / {2} for a = 1 (same for columns). Summed in fp32, rounded to fp16 once."""
+    w = w.detach().to(F32)
+    O, I, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    Ip = (I + cin_pad_to - 1) // cin_pad_to * cin_pad_to
+    Op = (O + cout_pad_to - 1) // cout_pad_to * cout_pad_to
+    sets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    p = torch.zeros((4, Op, 4, Ip), dtype=F32, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for i in (0, 1):
+                for j in (0, 1):
+                    acc = torch.zeros((O, I), dtype=F32, device=w.device)
+                    for ky in sets[a][i]:
+                        for kx in sets[b][j]:
+                            acc += w[:, :, ky, kx]
+                    p[2 * a + b, :O, 2 * i + j, :I] = acc
+    return p.reshape(4, Op, 4 * Ip).to(F16).contiguous()
+
+
 def conv1x1_weight(w, cout_pad_to=8):
     w = w.detach()
     O, I = w.shape[0], w.shape[1]

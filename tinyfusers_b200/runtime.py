@@ -225,6 +225,15 @@ class Context:
         st = self._timed(("conv3x3", x.n, x.h, x.w, x.c, cout, stride, residual is not None, gn[1] if gn else 0), fn)
         b200.check(st, "tf_conv2d_nhwc_f16")
 
+    def conv_up2x(self, x, w4, wrows, cout, out, bias=None, gn=None):
+        """out (n, 2h, 2w, cout) = conv3x3(upsample2x(x)) in one launch; w4 = packing.conv_up2x_weight."""
+        if self.skip("gemm"):
+            return
+        fn = lambda: b200.tf_conv2d_up2x_nhwc_f16(x.ptr, x.n, x.h, x.w, x.c, x.stride, w4, wrows, cout, out.ptr, out.stride, bias,
+                                                  b200.TF_GEMM_W_STATIC, gn[0] if gn else None, gn[1] if gn else 0, stream_ptr())
+        st = self._timed(("conv_up2x", x.n, x.h, x.w, x.c, cout, gn[1] if gn else 0), fn)
+        b200.check(st, "tf_conv2d_up2x_nhwc_f16")
+
     def conv3x3_skip(self, x, x2, w, cout, out, bias=None, gn=None):
         """out = conv3x3(x) + conv1x1(x2) + bias in one launch; w = [3x3 weight rows | 1x1 weight rows] per output channel."""
         if self.skip("gemm"):

@@ -10,6 +10,8 @@ Fast path of one forward (batch 2B for CFG):
     first conv's bias; conv_in reads the fp32 NCHW latent directly and forms the CFG batch by index;
   * conv_out writes fp32 NHWC (channels padded to 16) that the fused CFG+DDIM kernel consumes.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -22,6 +24,18 @@ from ..runtime import F16, F32, Act, Context, act_to_nchw, nchw_to_act, new_act_
 from ..storage.tensor import Tensor
 from .conv2d import Conv2d
 from .resnet import ResBlock
+
+
+FUSED_UPSAMPLE = os.environ.get("TINYFUSERS_B200_FUSED_UPSAMPLE", "1") != "0"
+
+
+def _pow2_tiling(h, w):
+    """a 128-pixel tile TW x TH x TN (powers of two) with TW | w, TH | h and >= 32 pixels of one image exists"""
+    for tw in (128, 64, 32, 16, 8, 4, 2, 1):
+        for th in (128, 64, 32, 16, 8, 4, 2, 1):
+            if tw * th <= 128 and tw * th >= 32 and w % tw == 0 and h % th == 0:
+                return True
+    return False
 
 
 class Upsample:
@@ -39,7 +53,27 @@ class Upsample:
         self._run(ctx, a, out)
         return act_to_nchw(out, self.conv.weight.shape[0])
 
+    def _packed_up2x(self):
+        def build():
+            w4 = packing.conv_up2x_weight(self.conv.weight, 64, 8)
+            b = packing.f32(self.conv.bias)
+            if b is not None and b.shape[0] != w4.shape[1]:
+                b = torch.nn.functional.pad(b, (0, w4.shape[1] - b.shape[0]))
+            return w4, b
+        return packing.cached(self, "up2x", (self.conv.weight, self.conv.bias), build)
+
     def _run(self, ctx, x, out):
+        """Upsampling folded into the convolution (tf_conv2d_up2x_nhwc_f16: four 2 x 2 phase convolutions of the original image,
+        4/9 of the multiply-adds, no 4x tensor) wherever the input tiles exactly; the two-launch path otherwise."""
+        if FUSED_UPSAMPLE and (x.h * x.w) % 32 == 0 and x.c % 64 == 0 and _pow2_tiling(x.h, x.w):
+            w4, b = self._packed_up2x()
+            cout_p = w4.shape[1]
+            gn = None
+            if out.gn is not None and len(out.gn) == 1 and out.gn[0][0] == 0 and out.gn[0][1] == cout_p:
+                gn = (out.gn[0][2], out.gn[0][3])
+            if gn is not None or out.gn is None:
+                ctx.conv_up2x(x, w4.data_ptr(), cout_p, cout_p, out, bias=b.data_ptr() if b is not None else None, gn=gn)
+                return out
         mark = ctx.arena.mark()
         up = ctx.new_act(x.n, x.h * 2, x.w * 2, x.c)
         ctx.upsample2x(x, up)

@@ -17,17 +17,23 @@ def gemm(M, N, K, geglu=False, reps=3):
     for _ in range(reps):
         b200.check(b200.tf_gemm_f16(A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), No, M, N, K, b.data_ptr(), None, 0, 2 if geglu else 0, ws.data_ptr(), ws.numel(), S()), "gemm")
 def attn(B, NH, T, d, reps=3):
-    dp = (d + 15) // 16 * 16
-    Q = torch.randn(B * T, NH * dp, device=dev).half(); K = torch.randn(B * T, NH * dp, device=dev).half(); Vt = torch.randn(NH * dp, B * T, device=dev).half()
-    out = torch.empty(B, NH, T, d, dtype=torch.half, device=dev)
+    """the production path: V in its natural layout, head dim padded like the model pads it (tf_attention_v_f16)"""
+    from tinyfusers_b200.attention.attention import _pad64
+    dp = (d + 15) // 16 * 16; dvp = _pad64(d)
+    Q = torch.zeros(B, T, NH, dp, device=dev).half(); Q[..., :d] = torch.randn(B, T, NH, d, device=dev)
+    K = torch.zeros(B, T, NH, dp, device=dev).half(); K[..., :d] = torch.randn(B, T, NH, d, device=dev)
+    V = torch.zeros(B, T, NH, dvp, device=dev).half(); V[..., :d] = torch.randn(B, T, NH, d, device=dev)
+    out = torch.empty(B, T, NH, d, dtype=torch.half, device=dev)
     for _ in range(reps):
-        b200.check(b200.tf_attention_f16(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, Vt.data_ptr(), B * T, out.data_ptr(), NH * T * d, T * d, d, B, NH, T, T, T, d, dp, 1 / math.sqrt(d), S()), "attn")
+        b200.check(b200.tf_attention_v_f16(Q.data_ptr(), NH * dp, K.data_ptr(), NH * dp, V.data_ptr(), NH * dvp, out.data_ptr(), T * NH * d, d, NH * d,
+                                           B, NH, T, T, T, d, dp, dvp, 1 / math.sqrt(d), 0, S()), "attn")
 conv(2, 64, 64, 320, 320)
 conv(2, 32, 32, 640, 640)
 gemm(8192, 2560, 320)
 gemm(8192, 320, 320)
 attn(2, 8, 4096, 40)
 conv(1, 512, 512, 128, 128, reps=2)      # VAE decoder, last stage (M = 262 144 pixels)
-attn(16, 8, 4096, 40, reps=2)            # C4 (8 images / GPU): 3 CTAs per SM variant
+attn(16, 8, 4096, 40, reps=2)            # C4 (8 images / GPU): the two-tile kernel
+attn(2, 8, 1024, 80)
 torch.cuda.synchronize()
 print("done")
