@@ -6,7 +6,7 @@ around graph replays - the same conditions as the captured step (PDL overlap of 
 Prints n x us per shape, the achieved TFLOP/s and the share of the summed time."""
 import collections, contextlib, io, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import ref_ops as R
+from tinyfusers_b200 import synthetic as R
 from tinyfusers_b200.storage.state import update_state
 from tinyfusers_b200.variants.sd import StableDiffusion
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
@@ -42,7 +42,7 @@ def chain(fn):
     for _ in range(5): g.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1000 / (5 * N)
-flop = lambda k: (2.0 * k[1] * k[2] * k[3] if k[0] == "gemm" else 2.0 * k[1] * (k[2] // k[6]) * (k[3] // k[6]) * k[5] * 9 * k[4] if k[0] == "conv3x3" else 4.0 * k[1] * k[2] * k[3] * k[4] * k[5] if k[0] == "attention" else 0)
+flop = lambda k: (2.0 * k[1] * k[2] * k[3] if k[0] == "gemm" else 2.0 * k[1] * (k[2] // k[6]) * (k[3] // k[6]) * k[5] * 9 * k[4] if k[0] == "conv3x3" else 4.0 * k[1] * k[2] * k[3] * k[4] * k[5] if k[0] == "attention" else 2.0 * k[1] * 4 * k[2] * k[3] * k[5] * 9 * k[4] if k[0] == "conv_up2x" else 0)   # conv_up2x: the reference's multiply-adds (3x3 over the 4x image)
 rows = []
 for key, (n, fn) in uniq.items():
     rows.append((key, n, chain(fn)))
