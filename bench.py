@@ -310,7 +310,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- BASELINE.json configs[3] (C4): 8 images per GPU, every rank, final latents gathered; configs[4] (C5) at N = 1 ----
     headline = B_img == 1 and HW == 64
     c4 = c5 = None
-    if headline and not args.quick:
+    if headline and not args.quick and os.environ.get("TF_BENCH_SKIP_C45") != "1":   # (dev switch: C3 without the C4 / C5 blocks before it)
         k4 = max(5, min(args.steps, 20))
         ms4, reg4, s4, l4, fin4, _ = throughput(8, 64, k4, 3, 3)
         f4 = unet_flops(model.model.diffusion_model, 16, 64, 64)

@@ -142,6 +142,26 @@ def test_graphs_follow_weight_updates(sd_model, oracle):
     assert torch.equal(call(), x1)
 
 
+def test_packing_in_other_domains_keeps_the_unet_graph(sd_model, oracle):
+    """Weights packed inside another engine's domain (the VAE decoder's first decode, the CLIP encoder's first prompt) must not
+    throw away the UNet sampler's captured step (a re-capture costs ~0.3 s: bench C3 measured it inside the timed image);
+    packing outside any domain - a stand-alone module call - still invalidates it, like update_state."""
+    from tinyfusers_b200 import packing
+
+    class Holder:
+        pass
+    lat, unc, ctx = oracle.make_inputs(1, 32, seed=11, ctx_seed=12)
+    s = sd_model._sampler(lat.shape, 77)
+    s.load(unc.cuda(), ctx.cuda(), lat.cuda())
+    g1 = s._graph(True)
+    w = torch.randn(8, 8, device="cuda")
+    with packing.domain("vae"):
+        packing.cached(Holder(), "w", (w,), lambda: w.half())
+    assert s._graph(True) is g1
+    packing.cached(Holder(), "w", (w,), lambda: w.half())
+    assert s._graph(True) is not g1
+
+
 def test_sampler_step_matches_oracle(oracle, unet_sd, sd_model):
     lat, unc, ctx = oracle.make_inputs(1, 32)
     ts, alphas, alphas_prev = oracle.sampler_schedule(50)

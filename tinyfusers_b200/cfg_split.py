@@ -95,7 +95,7 @@ class CfgSplitSampler:
         b200.check(b200.tf_add_int(self.seq.data_ptr(), 1, stream_ptr()), "tf_add_int")
 
     def _graph(self):
-        gen = packing.generation()
+        gen = packing.generation("unet")
         if self._graphs_gen != gen:
             self._graphs = {}
         g = self._graphs.get(self.guidance)
@@ -114,7 +114,7 @@ class CfgSplitSampler:
             # the warm-up advanced seq by one on both ranks (kept: it only has to agree between the ranks); the capture itself
             # executes nothing
             self._graphs[self.guidance] = g
-            self._graphs_gen = packing.generation()
+            self._graphs_gen = packing.generation("unet")
         return g
 
     def run(self, n_steps, use_graph=True):

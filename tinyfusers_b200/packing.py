@@ -12,16 +12,35 @@ import weakref
 # addresses of packed weights, so whoever holds a graph (variants.sd.SamplerEngine, vae.decoder.DecoderEngine) records the
 # generation at capture time and re-captures when it has moved.
 _generation = 0
+# Engines that hold graphs enqueue their kernels inside `with packing.domain(name)`: a weight (re)packed there only moves that
+# domain's counter, so packing the VAE decoder's weights (first decode) does not throw away the UNet sampler's captured step.
+# Packing outside any domain (stand-alone module calls) and update_state move the global counter, which every holder sees.
+_domain = None
+_domain_gen = {}
 
 
-def generation():
-    return _generation
+def generation(name=None):
+    """name=None: the global counter; otherwise (global, domain) - what a graph holder of that domain compares."""
+    return _generation if name is None else (_generation, _domain_gen.get(name, 0))
 
 
 def bump_generation():
     global _generation
     _generation += 1
     return _generation
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def domain(name):
+    global _domain
+    prev, _domain = _domain, name
+    try:
+        yield
+    finally:
+        _domain = prev
 
 
 def _version(t):
@@ -62,7 +81,10 @@ def cached(obj, name, tensors, builder):
         torch.cuda.current_stream().synchronize()
     refs = tuple((None, 0) if t is None else (weakref.ref(t), _version(t)) for t in tensors)
     obj.__dict__[slot] = (refs, val)
-    bump_generation()
+    if _domain is None:
+        bump_generation()
+    else:
+        _domain_gen[_domain] = _domain_gen.get(_domain, 0) + 1
     return val
 
 

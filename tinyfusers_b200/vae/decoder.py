@@ -7,7 +7,7 @@ in a stack arena sized by a dry run; conv_in reads the fp32 NCHW latent directly
 """
 import torch
 
-from .. import fp32
+from .. import fp32, packing
 from ..ff.group_norm import GroupNorm
 from ..native.b200.ops import b200
 from ..runtime import F32, Act, Context, require_cuda, stream_ptr
@@ -99,7 +99,8 @@ class DecoderEngine:
         self.ctx.arena.reserve(self.arena_bytes, dev)
 
     def _enqueue(self):
-        return self.model._run(self.ctx, self.latent.data_ptr(), self.n, self.H, self.W, self.img.data_ptr())
+        with packing.domain("vae"):
+            return self.model._run(self.ctx, self.latent.data_ptr(), self.n, self.H, self.W, self.img.data_ptr())
 
     def decode_nhwc_f32(self, latent):
         """-> the engine's (n, 8H, 8W, 8) fp32 NHWC buffer (channels 0..2 valid)."""

@@ -10,7 +10,7 @@ keys load, and raises when called."""
 import numpy as np
 import torch
 
-from .. import fp32
+from .. import fp32, packing
 from ..attention.attention import CLIPAttention
 from ..ff.embedding import Embedding, _ids_tensor
 from ..ff.group_norm import GroupNorm
@@ -123,8 +123,9 @@ class CLIPTextTransformer:
             xn = torch.zeros((Tp, 768), dtype=F16, device=dev)
             b200.check(b200.tf_embedding_f16(ids[i].data_ptr(), tok.data_ptr(), pos.data_ptr(), h.data_ptr(), T, T, 768,
                                              tok.shape[0], S), "tf_embedding_f16")
-            for l in self.encoder.layers:
-                l._run(ctx, h.data_ptr(), xn.data_ptr(), T, Tp)
-            self.final_layer_norm._run(ctx, h.data_ptr(), xn.data_ptr(), 1, T, 768)
+            with packing.domain("clip"):      # packing the text encoder's weights must not drop the UNet sampler's graphs
+                for l in self.encoder.layers:
+                    l._run(ctx, h.data_ptr(), xn.data_ptr(), T, Tp)
+                self.final_layer_norm._run(ctx, h.data_ptr(), xn.data_ptr(), 1, T, 768)
             b200.check(b200.tf_cast_f16_to_f32(xn.data_ptr(), out[i].data_ptr(), T * 768, S), "tf_cast_f16_to_f32")
         return out

@@ -248,7 +248,7 @@ class SamplerEngine:
         packed fp16 weights, so when `packing.generation()` has moved since capture (update_state, a weight assigned and
         repacked by an eager call) every graph of this engine is dropped and the step is re-captured after an eager
         warm-up that repacks - a stale graph would replay old (or freed) weights."""
-        gen = packing.generation()
+        gen = packing.generation("unet")
         if getattr(self, "_graphs_gen", None) != gen:
             self._graphs, self._warm = {}, False
         key = (advance, self.guidance, weight_prefetch_enabled())
@@ -257,7 +257,7 @@ class SamplerEngine:
             g = self._graphs[key] = self.capture(advance)
             # the warm-up step inside capture() may have repacked (bumping the generation): the graphs are valid for the
             # generation seen AFTER it, provided nothing moved during the capture itself (packing.cached raises there)
-            self._graphs_gen = packing.generation()
+            self._graphs_gen = packing.generation("unet")
         return g
 
     def step_once(self, use_graph=True):

@@ -372,9 +372,10 @@ class UNetEngine:
         self.graph = None
 
     def _enqueue(self, t_ptr=None, idx_ptr=None):
-        return self.model._run(self.ctx, self.latent.data_ptr(), self.n_src, self.n, self.H, self.W,
-                               self.t.data_ptr() if t_ptr is None else t_ptr, idx_ptr, self.context.data_ptr(),
-                               self.ctx_tokens, self.eps.data_ptr())
+        with packing.domain("unet"):     # weights packed here only invalidate graphs that hold UNet weights
+            return self.model._run(self.ctx, self.latent.data_ptr(), self.n_src, self.n, self.H, self.W,
+                                   self.t.data_ptr() if t_ptr is None else t_ptr, idx_ptr, self.context.data_ptr(),
+                                   self.ctx_tokens, self.eps.data_ptr())
 
     def forward_nchw(self, x, timesteps, context):
         self.latent.copy_(x.reshape(self.latent.shape))
