@@ -33,6 +33,32 @@ def test_resblock(oracle, cin, cout, hw):
     assert rel_err(out, oracle.res_block(sd, "rb", x, emb)) < TOL
 
 
+@pytest.mark.parametrize("cin,cout,hw", [(1280, 1280, 8), (2560, 1280, 8), (1280, 1280, 16)])
+def test_resblock_cluster_splitk(oracle, cin, cout, hw):
+    """The optional split-K fold inside a thread-block cluster (tf_gemm_set_cluster_splitk: partial tiles reduced through
+    distributed shared memory in the conv launch itself, GroupNorm statistics included; off by default because it measured
+    slower) on the small-M ResBlocks whose convolutions split K: against the oracle, and against the default workspace + fold
+    path (same fp32 products, different summation order)."""
+    from tinyfusers_b200.native.b200.ops import b200
+    from tinyfusers_b200.vision.resnet import ResBlock
+    sd = {}
+    oracle.add_res_block(sd, "rb", cin, cout, seed=21)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, cin, hw, hw, generator=g)
+    emb = torch.randn(1, 1280, generator=g)
+    rb = ResBlock(cin, 1280, cout)
+    _load(rb, sd, "rb")
+    ref = oracle.res_block(sd, "rb", x, emb)
+    plain = rb(x.cuda(), emb.cuda())
+    try:
+        b200.check(b200.tf_gemm_set_cluster_splitk(1), "cluster split-K on")
+        clus = rb(x.cuda(), emb.cuda())
+    finally:
+        b200.tf_gemm_set_cluster_splitk(-1)
+    assert rel_err(clus, ref) < TOL
+    assert rel_err(clus, plain) < 3e-3
+
+
 @pytest.mark.parametrize("quirks", [True, False])
 @pytest.mark.parametrize("c,d,T,B", [(320, 40, 256, 2), (640, 80, 64, 2), (1280, 160, 64, 1)])
 def test_cross_attention_self_and_cross(oracle, quirks, c, d, T, B):

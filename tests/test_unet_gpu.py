@@ -162,6 +162,29 @@ def test_packing_in_other_domains_keeps_the_unet_graph(sd_model, oracle):
     assert s._graph(True) is not g1
 
 
+def test_weight_prefetch_hints_do_not_change_results(sd_model, oracle):
+    """The optional next-layer weight prefetch (tf_weight_prefetch_mode: the library records the step's weight sequence in one
+    eager pass, each captured launch then asks L2 for the next layer's weights; off by default, measured without gain): hints
+    are really baked into the graph (tf_weight_prefetch_stats) and three sampler steps are bit-identical with and without."""
+    import ctypes
+    import tinyfusers_b200
+    from tinyfusers_b200.native.b200.ops import b200
+    lat, unc, ctx = oracle.make_inputs(1, 32, seed=13, ctx_seed=14)
+    ts, alphas, alphas_prev = oracle.sampler_schedule(50)
+    run = lambda: sd_model.sample(unc.cuda(), ctx.cuda(), lat.cuda(), ts[:3], alphas[:3], alphas_prev[:3], 7.5)
+    x_off = run()
+    try:
+        tinyfusers_b200.set_weight_prefetch(True)
+        x_on = run()
+        rec, hin, byt = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+        b200.check(b200.tf_weight_prefetch_stats(ctypes.byref(rec), ctypes.byref(hin), ctypes.byref(byt)), "stats")
+    finally:
+        tinyfusers_b200.set_weight_prefetch(False)
+    assert rec.value > 100 and hin.value > 50 and byt.value > (1 << 30), (rec.value, hin.value, byt.value)
+    assert torch.equal(x_on, x_off)
+    assert torch.equal(run(), x_off)
+
+
 def test_sampler_step_matches_oracle(oracle, unet_sd, sd_model):
     lat, unc, ctx = oracle.make_inputs(1, 32)
     ts, alphas, alphas_prev = oracle.sampler_schedule(50)
