@@ -1,7 +1,7 @@
 """Dev (GPU box): per-call device time of one eager UNet CFG step, aggregated by kernel shape (CUDA events)."""
 import collections, contextlib, io, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import ref_ops as R
+from tinyfusers_b200 import synthetic as R
 from tinyfusers_b200.storage.state import update_state
 from tinyfusers_b200.variants.sd import StableDiffusion
 sd = R.make_unet_state_dict()

@@ -2,7 +2,7 @@
 import collections, contextlib, io, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from oracle import ref_ops as R
+from tinyfusers_b200 import synthetic as R
 from tinyfusers_b200.runtime import standalone_context
 from tinyfusers_b200.storage.state import update_state
 from tinyfusers_b200.vae.encoder import CLIPTextTransformer
