@@ -1089,6 +1089,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     TF_CUDA(cudaFuncSetAttribute(tf_gemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
+  if (p.gn_stats != nullptr && p.splits == 1 && p.bn % p.gn_unit != 0) {
+    // only reachable through the measurement hooks (tf_gemm_set_tuning): a statistics unit must not straddle two tiles
+    tf_set_error("gemm: tile width %d is not a whole number of %d-channel statistics units", p.bn, p.gn_unit);
+    return TF_ERR_ARG;
+  }
   const int stage_bytes = A_STAGE_BYTES + p.bn * 128 / p.ctas;
   const bool extras = p.row_stats != nullptr || p.ln_stats != nullptr;
   const int kEpiBytes = epi_bytes(extras);
