@@ -188,7 +188,7 @@ def test_blocks_match_reference_goldens():
 
 
 def test_spatial_transformer_with_layernorm_folded_into_gemms(oracle):
-    """Opt-in path (TINYFUSERS_B200_FUSE_LN=1): norm1 / norm2 folded into the projections that consume them
+    """Opt-in path (TINYFUSERS_B200_FUSE_LN=1 | 2): norm1 / norm2 (/ norm3) folded into the projections that consume them
     (tf_gemm_ex_f16: row statistics from the producing GEMM, gamma in the weights, mean / rstd applied in the epilogue)."""
     from tinyfusers_b200.attention.attention import SpatialTransformer
     from tinyfusers_b200.runtime import standalone_context

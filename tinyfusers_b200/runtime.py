@@ -128,10 +128,12 @@ class Context:
         self.context = None        # Act view of the zero-padded fp16 prompt context (B, Tpad, 768)
         self.context_tokens = 0
         self.fuse_gn = os.environ.get("TINYFUSERS_B200_FUSE_GN", "1") != "0"
-        # LayerNorm folded into the consuming GEMM (row statistics from the producing GEMM's epilogue). Correct and tested,
-        # but break-even at best on the SD1.5 step at batch 2 (260.8 vs 261.0 steps/s: the producers' statistics and the
-        # consumers' per-tile fold cost the GEMM epilogues 0.10 ms, the 27 removed LayerNorm launches save 0.09 ms), so it
-        # is opt-in: TINYFUSERS_B200_FUSE_LN=1 (norm2 + sub-4096-token norm1) or =2 (all three norms).
+        # LayerNorm folded into the consuming GEMM (row statistics from the producing GEMM's epilogue, gamma folded into the
+        # weights, mean / rstd applied per row in the consumer's epilogue). Correct and tested, opt-in:
+        # TINYFUSERS_B200_FUSE_LN=1 (norm2 + sub-4096-token norm1: 30 LayerNorm launches fewer, 376 -> 346) measures +0.4 % at
+        # batch 2 (279.2 -> 280.2 steps/s), +0.7 % at batch 16 and +0.2 % at 768^2 in same-box A/B runs - inside the box-to-box
+        # spread - by moving 0.09 ms of norm time into 0.10 ms of GEMM-epilogue time; =2 (all three norms, also the
+        # epilogue-bound GEGLU projection) is slower (271.1 steps/s). Not the default: no measurable step gain.
         self.fuse_ln = os.environ.get("TINYFUSERS_B200_FUSE_LN", "0") in ("1", "2")
         self.fuse_ln_all = os.environ.get("TINYFUSERS_B200_FUSE_LN", "0") == "2"   # also norm1 at 4096 tokens and norm3 (GEGLU)
         self.ctx_kv = None         # dict: id(CrossAttention) -> (k_ptr, ldk, vt_ptr, ldvt) projected once per forward
