@@ -27,6 +27,7 @@ from .resnet import ResBlock
 
 
 FUSED_UPSAMPLE = os.environ.get("TINYFUSERS_B200_FUSED_UPSAMPLE", "1") != "0"
+NVTX = os.environ.get("TINYFUSERS_B200_NVTX", "0") == "1"
 
 
 def _pow2_tiling(h, w):
@@ -288,22 +289,31 @@ class UNetModel:
         skip_view = lambda i: svs[i]
         x_view = lambda j: xvs[j]
 
-        def run_block(layers, x, final_out):
+        def run_layer(layer, x, final_out, last):
+            if isinstance(layer, ResBlock):
+                out = final_out if last else ctx.new_act(x.n, x.h, x.w, layer.out_channels, gn=True)
+                return layer._run(ctx, x, emb_bias(layer), out)
+            if isinstance(layer, SpatialTransformer):
+                out = final_out if last else ctx.new_act(x.n, x.h, x.w, x.c, gn=True)
+                return layer._run(ctx, x, cact, out)
+            if isinstance(layer, Upsample):
+                out = final_out if last else ctx.new_act(x.n, x.h * 2, x.w * 2, x.c)
+                return layer._run(ctx, x, out)
+            if isinstance(layer, Downsample):
+                return layer._run(ctx, x, final_out)
+            raise RuntimeError(f"unexpected layer {type(layer)}")
+
+        def run_block(layers, x, final_out, tag=""):
             for li, layer in enumerate(layers):
                 last = li == len(layers) - 1
-                if isinstance(layer, ResBlock):
-                    out = final_out if last else ctx.new_act(x.n, x.h, x.w, layer.out_channels, gn=True)
-                    x = layer._run(ctx, x, emb_bias(layer), out)
-                elif isinstance(layer, SpatialTransformer):
-                    out = final_out if last else ctx.new_act(x.n, x.h, x.w, x.c, gn=True)
-                    x = layer._run(ctx, x, cact, out)
-                elif isinstance(layer, Upsample):
-                    out = final_out if last else ctx.new_act(x.n, x.h * 2, x.w * 2, x.c)
-                    x = layer._run(ctx, x, out)
-                elif isinstance(layer, Downsample):
-                    x = layer._run(ctx, x, final_out)
+                if NVTX:    # TINYFUSERS_B200_NVTX=1: one NVTX range per layer of an eagerly enqueued step (profilers group by it)
+                    torch.cuda.nvtx.range_push(f"{tag}.{li}.{type(layer).__name__}")
+                    try:
+                        x = run_layer(layer, x, final_out, last)
+                    finally:
+                        torch.cuda.nvtx.range_pop()
                 else:
-                    raise RuntimeError(f"unexpected layer {type(layer)}")
+                    x = run_layer(layer, x, final_out, last)
             return x
 
         # --- input blocks ---
@@ -315,11 +325,11 @@ class UNetModel:
                 x = dst
             else:
                 mark = ar.mark()
-                x = run_block(blk, x, dst)
+                x = run_block(blk, x, dst, f"input_blocks.{i}")
                 ar.release(mark)
         # --- middle ---
         mark = ar.mark()
-        x = run_block(self.middle_block, x, x_view(0))
+        x = run_block(self.middle_block, x, x_view(0), "middle_block")
         ar.release(mark)
         # --- output blocks ---
         for j, blk in enumerate(self.output_blocks):
@@ -328,7 +338,7 @@ class UNetModel:
             else:
                 dst = ctx.new_act(n, H, W, blk[0].out_channels, gn=True)
             mark = ar.mark()
-            x = run_block(blk, cats[j], dst)
+            x = run_block(blk, cats[j], dst, f"output_blocks.{j}")
             ar.release(mark)
         # --- out: GroupNorm + SiLU + conv 320 -> 4 (padded to 16, fp32) ---
         hn = ctx.new_act(n, H, W, x.c)
