@@ -42,6 +42,16 @@ int tf_set_pdl(int enable);
 long long tf_launch_count(void);
 void tf_launch_count_reset(void);
 
+/* ---- CUDA-graph capture without a host framework ------------------------------------------------------------------
+ * Every tf_* call is graph-capturable. The package captures with torch.cuda.CUDAGraph; a host that binds the library from
+ * CuPy / ctypes (the reference's world: tinyfusers/native/cudart/ops.py binds cudart the same way) captures and replays the
+ * step through these: begin on a non-default stream, enqueue tf_* calls on it, end -> an instantiated graph, launch it any
+ * number of times. Replaces nothing in the reference (it launches every operator eagerly: example/sd1.py:68-73). */
+int tf_graph_begin_capture(void* stream);
+int tf_graph_end_capture(void* stream, void** graph_exec_out);
+int tf_graph_launch(void* graph_exec, void* stream);
+int tf_graph_destroy(void* graph_exec);
+
 /* ---- epilogue flags for tf_gemm_f16 / tf_conv2d_nhwc_f16 ----------------------------------------- */
 #define TF_EPI_NONE 0
 #define TF_EPI_OUT_F32 1 /* write fp32 instead of fp16 */

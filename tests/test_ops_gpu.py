@@ -313,3 +313,53 @@ def test_gemm_single_and_pair_cta_tiles(oracle, case, ctas):
     finally:
         b200.tf_gemm_set_ctas(0)
         b200.tf_gemm_set_tuning(0, 0)
+
+
+def test_c_abi_graph_capture_without_torch_graphs():
+    """tf_graph_begin_capture / end_capture / launch / destroy: a GEMM -> LayerNorm -> GEMM chain captured through the library's
+    own C-ABI (what a CuPy / ctypes host of the reference would use; the package itself captures with torch.cuda.CUDAGraph)
+    replays to the bit-identical result of the eager chain, and follows its inputs on the next launch."""
+    import ctypes
+    from tinyfusers_b200.native.b200.ops import b200
+    b200.init(0)
+    g = _g(31)
+    M, K, N = 256, 320, 640
+    A = torch.randn(M, K, generator=g).half().cuda()
+    W1 = (torch.randn(N, K, generator=g) / math.sqrt(K)).half().cuda()
+    W2 = (torch.randn(K, N, generator=g) / math.sqrt(N)).half().cuda()
+    gamma, beta = torch.ones(N).cuda(), torch.zeros(N).cuda()
+    h = torch.empty(M, N, dtype=torch.half, device="cuda")
+    hn = torch.empty_like(h)
+    out = torch.empty(M, K, dtype=torch.half, device="cuda")
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    S = side.cuda_stream
+
+    def chain():
+        b200.check(b200.tf_gemm_f16(A.data_ptr(), K, W1.data_ptr(), K, h.data_ptr(), N, M, N, K, None, None, 0, 0, ws.data_ptr(), ws.numel(), S), "gemm1")
+        b200.check(b200.tf_layernorm_f16(h.data_ptr(), hn.data_ptr(), M, N, gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, S), "ln")
+        b200.check(b200.tf_gemm_f16(hn.data_ptr(), N, W2.data_ptr(), N, out.data_ptr(), K, M, K, N, None, None, 0, 0, ws.data_ptr(), ws.numel(), S), "gemm2")
+    torch.cuda.synchronize()
+    chain()
+    side.synchronize()
+    eager = out.clone()
+    exec_ = ctypes.c_void_p()
+    b200.check(b200.tf_graph_begin_capture(S), "begin")
+    chain()
+    b200.check(b200.tf_graph_end_capture(S, ctypes.byref(exec_)), "end")
+    try:
+        out.zero_()
+        torch.cuda.synchronize()
+        b200.check(b200.tf_graph_launch(exec_, S), "launch")
+        side.synchronize()
+        assert torch.equal(out, eager)
+        ref = torch.nn.functional.layer_norm((A.float() @ W1.float().T).half().float(), (N,)).half().float() @ W2.float().T
+        assert rel_err(out, ref) < TOL
+        A.mul_(2.0)                       # same graph, new input contents
+        torch.cuda.synchronize()
+        b200.check(b200.tf_graph_launch(exec_, S), "launch")
+        side.synchronize()
+        assert not torch.equal(out, eager)
+        assert rel_err(out, ref) < TOL    # LayerNorm makes the chain scale-invariant
+    finally:
+        b200.check(b200.tf_graph_destroy(exec_), "destroy")

@@ -134,3 +134,40 @@ int tf_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int rank, const voi
   }
   return TF_OK;
 }
+
+
+// ---- CUDA-graph capture without a host framework ----------------------------------------------------------------------
+// The package captures the denoising step with torch.cuda.CUDAGraph (torch is its container library). A host that binds this
+// library from something else (the reference's own CuPy / ctypes world: tinyfusers/native/cudart/ops.py) gets the same
+// capture / replay through these four calls: every tf_* launch is graph-capturable (no hidden synchronisation, programmatic
+// dependent launch attributes are recorded as graph edges).
+extern "C" int tf_graph_begin_capture(void* stream) {
+  TF_CUDA(cudaStreamBeginCapture(reinterpret_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal));
+  return TF_OK;
+}
+
+extern "C" int tf_graph_end_capture(void* stream, void** graph_exec_out) {
+  TF_CHECK_ARG(graph_exec_out != nullptr, "tf_graph_end_capture: null output");
+  cudaGraph_t graph = nullptr;
+  TF_CUDA(cudaStreamEndCapture(reinterpret_cast<cudaStream_t>(stream), &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    tf_set_error("tf_graph_end_capture: cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  *graph_exec_out = exec;
+  return TF_OK;
+}
+
+extern "C" int tf_graph_launch(void* graph_exec, void* stream) {
+  TF_CHECK_ARG(graph_exec != nullptr, "tf_graph_launch: null graph");
+  TF_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), reinterpret_cast<cudaStream_t>(stream)));
+  return TF_OK;
+}
+
+extern "C" int tf_graph_destroy(void* graph_exec) {
+  if (graph_exec) TF_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+  return TF_OK;
+}

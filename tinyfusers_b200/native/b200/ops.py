@@ -36,6 +36,10 @@ _SIGNATURES = {
     "tf_gemm_set_tuning": (c_int, [c_int, c_int]),
     "tf_gemm_set_ctas": (c_int, [c_int]),
     "tf_gemm_set_cluster_splitk": (c_int, [c_int]),
+    "tf_graph_begin_capture": (c_int, [_P]),
+    "tf_graph_end_capture": (c_int, [_P, _P]),
+    "tf_graph_launch": (c_int, [_P, _P]),
+    "tf_graph_destroy": (c_int, [_P]),
     "tf_gemm_set_timeline": (c_int, [_P]),
     "tf_weight_prefetch_mode": (c_int, [c_int]),
     "tf_weight_prefetch_stats": (c_int, [_P, _P, _P]),
